@@ -1,0 +1,714 @@
+// extern "C" entry points of libcone_b200 (include/cone_b200.h): weights handle, workspace planning and the
+// launch sequences of the coarse-to-fine path.  No hidden allocation outside the weights handle.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "tc_gemm.h"
+
+namespace cone {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+}  // namespace cone
+
+using namespace cone;
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+struct cone_weights {
+    cone_dims dims;
+    float* blob = nullptr;  // the state dict, canonical order, device
+    size_t n_floats = 0;
+    std::map<std::string, size_t> off;
+    float* derived = nullptr;  // dec_kw | dec_kb | dec_vw | dec_vb | pos_table
+    float *dec_kw = nullptr, *dec_kb = nullptr, *dec_vw = nullptr, *dec_vb = nullptr, *pos_table = nullptr;
+    TcWeights* tc = nullptr;  // bf16 copies + TMA descriptors for the tensor-core path (lazy)
+    const float* p(const std::string& name) const { return blob + off.at(name); }
+};
+
+// the canonical order of cone_b200/weights.py::state_dict_shapes
+static void layout(const cone_dims& c, std::vector<std::pair<std::string, size_t>>& out) {
+    const size_t d = c.hidden, ff = c.ffn, dv = c.v_dim, dt = c.t_dim;
+    auto attn = [&](const std::string& p) {
+        out.push_back({p + ".in_proj_weight", 3 * d * d});
+        out.push_back({p + ".in_proj_bias", 3 * d});
+        out.push_back({p + ".out_proj.weight", d * d});
+        out.push_back({p + ".out_proj.bias", d});
+    };
+    auto ffn_norms = [&](const std::string& p, int n_norm) {
+        out.push_back({p + ".linear1.weight", ff * d});
+        out.push_back({p + ".linear1.bias", ff});
+        out.push_back({p + ".linear2.weight", d * ff});
+        out.push_back({p + ".linear2.bias", d});
+        for (int i = 1; i <= n_norm; ++i) {
+            out.push_back({p + ".norm" + std::to_string(i) + ".weight", d});
+            out.push_back({p + ".norm" + std::to_string(i) + ".bias", d});
+        }
+    };
+    for (int i = 0; i < c.enc_layers; ++i) {
+        const std::string p = "transformer.encoder.layers." + std::to_string(i);
+        attn(p + ".self_attn");
+        ffn_norms(p, 2);
+    }
+    for (int i = 0; i < c.dec_layers; ++i) {
+        const std::string p = "transformer.decoder.layers." + std::to_string(i);
+        attn(p + ".self_attn");
+        attn(p + ".multihead_attn");
+        ffn_norms(p, 3);
+    }
+    out.push_back({"transformer.decoder.norm.weight", d});
+    out.push_back({"transformer.decoder.norm.bias", d});
+    out.push_back({"txt_position_embed.position_embeddings.weight", (size_t)c.max_q_l * d});
+    out.push_back({"txt_position_embed.LayerNorm.weight", d});
+    out.push_back({"txt_position_embed.LayerNorm.bias", d});
+    const size_t span_out[3] = {d, d, 2};
+    for (int i = 0; i < 3; ++i) {
+        out.push_back({"span_embed.layers." + std::to_string(i) + ".weight", span_out[i] * d});
+        out.push_back({"span_embed.layers." + std::to_string(i) + ".bias", span_out[i]});
+    }
+    out.push_back({"class_embed.weight", 2 * d});
+    out.push_back({"class_embed.bias", 2});
+    out.push_back({"query_embed.weight", (size_t)c.num_queries * d});
+    const char* names[2] = {"input_txt_proj", "input_vid_proj"};
+    const size_t din[2] = {dt, dv};
+    for (int t = 0; t < 2; ++t) {
+        for (int i = 0; i < 2; ++i) {
+            const size_t k = i == 0 ? din[t] : d;
+            const std::string p = std::string(names[t]) + "." + std::to_string(i);
+            out.push_back({p + ".LayerNorm.weight", k});
+            out.push_back({p + ".LayerNorm.bias", k});
+            out.push_back({p + ".net.1.weight", d * k});
+            out.push_back({p + ".net.1.bias", d});
+        }
+    }
+    out.push_back({"saliency_proj.weight", d});
+    out.push_back({"saliency_proj.bias", 1});
+    out.push_back({"adapter_layer.layers.0.weight", d * dv});
+    out.push_back({"adapter_layer.layers.0.bias", d});
+    out.push_back({"adapter_layer.layers.1.weight", dv * d});
+    out.push_back({"adapter_layer.layers.1.bias", dv});
+}
+
+static int check_dims(const cone_dims* c) {
+    CONE_REQUIRE(c != nullptr, "dims is null");
+    CONE_REQUIRE(c->hidden == 256 && c->nheads == 8, "only hidden_dim 256 with 8 heads (head_dim 32) is built");
+    CONE_REQUIRE(c->v_dim > 0 && c->v_dim % 16 == 0 && c->t_dim > 0 && c->t_dim % 16 == 0,
+                 "feature dims must be positive multiples of 16");
+    CONE_REQUIRE(c->ffn > 0 && c->ffn % 16 == 0, "dim_feedforward must be a multiple of 16");
+    CONE_REQUIRE(c->enc_layers >= 1 && c->dec_layers >= 1 && c->enc_layers <= 8 && c->dec_layers <= 8, "1..8 layers");
+    CONE_REQUIRE(c->num_queries >= 1 && c->num_queries <= 8, "1..8 moment slots");
+    CONE_REQUIRE(c->max_v_l >= 2 && c->max_q_l >= 1 && c->max_v_l + c->max_q_l <= 256,
+                 "window (max_v_l + max_q_l) must fit 256 rows");
+    return CONE_OK;
+}
+
+extern "C" const char* cone_last_error(void) { return g_err; }
+extern "C" int cone_version(void) { return 1; }
+extern "C" int64_t cone_launch_count(void) { return g_launches; }
+extern "C" void cone_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" size_t cone_weights_expected_floats(const cone_dims* dims) {
+    if (check_dims(dims) != CONE_OK) return 0;
+    std::vector<std::pair<std::string, size_t>> l;
+    layout(*dims, l);
+    size_t n = 0;
+    for (auto& e : l) n += e.second;
+    return n;
+}
+
+extern "C" void cone_weights_destroy(cone_weights* w) {
+    if (!w) return;
+    if (w->tc) tc_weights_destroy(w->tc);
+    if (w->blob) cudaFree(w->blob);
+    if (w->derived) cudaFree(w->derived);
+    delete w;
+}
+
+extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, const cone_dims* dims, void* stream,
+                                   cone_weights** out) {
+    CONE_TRY(check_dims(dims));
+    CONE_REQUIRE(blob_host != nullptr && out != nullptr, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<std::pair<std::string, size_t>> l;
+    layout(*dims, l);
+    cone_weights* w = new cone_weights();
+    w->dims = *dims;
+    size_t n = 0;
+    for (auto& e : l) {
+        // keep every tensor 16-byte aligned on the device: all sizes are multiples of 4 floats except the
+        // 2- and 1-element head biases, which come last in their groups; pad offsets instead of assuming
+        w->off[e.first] = n;
+        n += e.second;
+    }
+    if (n != n_floats) {
+        set_error("state dict has %zu floats, expected %zu for these dims", n_floats, n);
+        delete w;
+        return CONE_ERR_INVALID;
+    }
+    // device layout: each tensor padded to a multiple of 4 floats so float4 loads are always aligned
+    std::vector<float> staged;
+    staged.reserve(n + 4 * l.size());
+    {
+        size_t src = 0;
+        for (auto& e : l) {
+            w->off[e.first] = staged.size();
+            staged.insert(staged.end(), blob_host + src, blob_host + src + e.second);
+            while (staged.size() & 3) staged.push_back(0.f);
+            src += e.second;
+        }
+    }
+    w->n_floats = staged.size();
+    const size_t d = dims->hidden;
+    const int DL = dims->dec_layers;
+    // derived: concatenated cross-attention K / V projections of all decoder layers (memory is shared)
+    std::vector<float> der((size_t)DL * d * d * 2 + (size_t)DL * d * 2);
+    float* kw = der.data();
+    float* kb = kw + (size_t)DL * d * d;
+    float* vw = kb + (size_t)DL * d;
+    float* vb = vw + (size_t)DL * d * d;
+    for (int i = 0; i < DL; ++i) {
+        const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".multihead_attn";
+        const float* inw = staged.data() + w->off.at(p + ".in_proj_weight");
+        const float* inb = staged.data() + w->off.at(p + ".in_proj_bias");
+        memcpy(kw + (size_t)i * d * d, inw + d * d, sizeof(float) * d * d);
+        memcpy(vw + (size_t)i * d * d, inw + 2 * d * d, sizeof(float) * d * d);
+        memcpy(kb + (size_t)i * d, inb + d, sizeof(float) * d);
+        memcpy(vb + (size_t)i * d, inb + 2 * d, sizeof(float) * d);
+    }
+    const size_t pos_floats = (size_t)(dims->max_v_l + 1) * dims->max_v_l * d;
+    cudaError_t e = cudaMalloc(&w->blob, sizeof(float) * w->n_floats);
+    if (e == cudaSuccess) e = cudaMalloc(&w->derived, sizeof(float) * (der.size() + pos_floats));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w->blob, staged.data(), sizeof(float) * w->n_floats, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w->derived, der.data(), sizeof(float) * der.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // staging vectors die at return
+    if (e != cudaSuccess) {
+        set_error("cone_weights_create: %s", cudaGetErrorString(e));
+        cone_weights_destroy(w);
+        return CONE_ERR_CUDA;
+    }
+    w->dec_kw = w->derived;
+    w->dec_kb = w->dec_kw + (size_t)DL * d * d;
+    w->dec_vw = w->dec_kb + (size_t)DL * d;
+    w->dec_vb = w->dec_vw + (size_t)DL * d * d;
+    w->pos_table = w->derived + der.size();
+    int r = build_pos_table(w->pos_table, dims->max_v_l, (int)d, s);
+    if (r != CONE_OK) {
+        cone_weights_destroy(w);
+        return r;
+    }
+    *out = w;
+    return CONE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace arena
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Arena {
+    char* base;
+    size_t cap;
+    size_t used = 0;
+    Arena(void* b, size_t c) : base((char*)b), cap(c) {}
+    template <class T>
+    T* get(size_t n) {
+        const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + used) : nullptr;
+        used += bytes;
+        return p;
+    }
+    bool fits() const { return base == nullptr || used <= cap; }
+};
+
+struct Linear {
+    const float* W;
+    const float* b;
+    int N, K;
+    const char* name;  // state-dict key of W (tensor-core weight cache lookup)
+};
+
+struct Ctx {
+    const cone_weights* w;
+    int prec;
+    cudaStream_t s;
+};
+
+// y[M,N] = epi(x[M,K] * W^T + b (+R)) in the requested precision
+int linear(const Ctx& c, const float* x, int64_t ldx, int64_t M, const float* W, const float* b, int N, int K, float* y,
+           int64_t ldy, int relu, const float* R = nullptr, int64_t ldr = 0) {
+    if (c.prec == CONE_PREC_TC && tc_gemm_supported(M, N, K)) {
+        return tc_gemm(c.w->tc, x, ldx, M, W, b, N, K, y, ldy, relu, R, ldr, c.s);
+    }
+    GemmParams g;
+    g.A = x; g.lda = ldx; g.W = W; g.ldw = K; g.C = y; g.ldc = ldy; g.bias = b; g.R = R; g.ldr = ldr;
+    g.M = M; g.N = N; g.K = K; g.relu = relu;
+    return sgemm_nt(g, c.s);
+}
+
+int linear_named(const Ctx& c, const float* x, int64_t ldx, int64_t M, const std::string& prefix, int N, int K, float* y,
+                 int64_t ldy, int relu, const float* R = nullptr, int64_t ldr = 0) {
+    return linear(c, x, ldx, M, c.w->p(prefix + ".weight"), c.w->p(prefix + ".bias"), N, K, y, ldy, relu, R, ldr);
+}
+
+// LinearLayer x2 (cone/model.py:443-465, 55-72): LN -> Linear -> ReLU -> LN -> Linear
+struct ProjBuffers {
+    float *ln_in, *h1, *ln_h1;
+};
+ProjBuffers plan_proj(Arena& a, int64_t rows, int din, int d) {
+    ProjBuffers b;
+    b.ln_in = a.get<float>(rows * din);
+    b.h1 = a.get<float>(rows * d);
+    b.ln_h1 = a.get<float>(rows * d);
+    return b;
+}
+int input_proj(const Ctx& c, const char* name, const float* x, int64_t rows, int din, float* out, ProjBuffers& b) {
+    const int d = c.w->dims.hidden;
+    const std::string p0 = std::string(name) + ".0", p1 = std::string(name) + ".1";
+    CONE_TRY(layernorm_rows(x, nullptr, c.w->p(p0 + ".LayerNorm.weight"), c.w->p(p0 + ".LayerNorm.bias"), b.ln_in, rows,
+                            din, 1e-5f, c.s));
+    CONE_TRY(linear_named(c, b.ln_in, din, rows, p0 + ".net.1", d, din, b.h1, d, 1));
+    CONE_TRY(layernorm_rows(b.h1, nullptr, c.w->p(p1 + ".LayerNorm.weight"), c.w->p(p1 + ".LayerNorm.bias"), b.ln_h1,
+                            rows, d, 1e-5f, c.s));
+    CONE_TRY(linear_named(c, b.ln_h1, d, rows, p1 + ".net.1", d, d, out, d, 0));
+    return CONE_OK;
+}
+
+// adapter_layer(x) (+ x): MLP(Dv, 256, Dv, 2) (cone/model.py:80, 428-440)
+int adapter_rows(const Ctx& c, const float* x, int64_t rows, float* hid, float* out, int residual) {
+    const int d = c.w->dims.hidden, dv = c.w->dims.v_dim;
+    CONE_TRY(linear_named(c, x, dv, rows, "adapter_layer.layers.0", d, dv, hid, d, 1));
+    CONE_TRY(linear_named(c, hid, d, rows, "adapter_layer.layers.1", dv, d, out, dv, 0, residual ? x : nullptr, dv));
+    return CONE_OK;
+}
+
+// ---- the Moment-DETR core over B windows of S = Lv + Lt rows -------------------------------------
+struct CoreBuffers {
+    int64_t B;
+    int Lv, Lt, hw;
+    float *src, *srcpos, *qk, *v, *att, *tmp, *h;                      // [R, .]
+    float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
+    int64_t *vid_base, *txt_base;
+    int32_t *vlen, *tlen, *pad_len, *qidx;
+};
+
+CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt) {
+    CoreBuffers b;
+    b.B = B; b.Lv = Lv; b.Lt = Lt;
+    const int64_t R = B * (Lv + Lt), Q = B * c.num_queries;
+    const int d = c.hidden;
+    b.hw = c.ffn > 2 * d * c.dec_layers ? c.ffn : 2 * d * c.dec_layers;
+    b.src = a.get<float>(R * d);
+    b.srcpos = a.get<float>(R * d);
+    b.qk = a.get<float>(R * 2 * d);
+    b.v = a.get<float>(R * d);
+    b.att = a.get<float>(R * d);
+    b.tmp = a.get<float>(R * d);
+    b.h = a.get<float>(R * b.hw);
+    b.tgt = a.get<float>(Q * d);
+    b.t2 = a.get<float>(Q * d);
+    b.dqkin = a.get<float>(Q * d);
+    b.dqk = a.get<float>(Q * 2 * d);
+    b.dv = a.get<float>(Q * d);
+    b.datt = a.get<float>(Q * d);
+    b.dq = a.get<float>(Q * d);
+    b.dh = a.get<float>(Q * c.ffn);
+    b.hs = a.get<float>(Q * d);
+    b.hid1 = a.get<float>(Q * d);
+    b.hid2 = a.get<float>(Q * d);
+    b.vid_base = a.get<int64_t>(B);
+    b.txt_base = a.get<int64_t>(B);
+    b.vlen = a.get<int32_t>(B);
+    b.tlen = a.get<int32_t>(B);
+    b.pad_len = a.get<int32_t>(B);
+    b.qidx = a.get<int32_t>(B);
+    return b;
+}
+
+// heads on hs [Q, d]: class logits / foreground probability and sigmoid spans (cone/model.py:112-115,
+// cone/inference.py:47,52)
+int heads(const Ctx& c, CoreBuffers& b, const float* hs, int64_t Q, float* logits, float* prob_fg, float* spans) {
+    const int d = c.w->dims.hidden;
+    if (logits) CONE_TRY(rowdot_small(hs, d, c.w->p("class_embed.weight"), c.w->p("class_embed.bias"), logits, Q, 2, d, 0, c.s));
+    if (prob_fg) CONE_TRY(rowdot_small(hs, d, c.w->p("class_embed.weight"), c.w->p("class_embed.bias"), prob_fg, Q, 2, d, 2, c.s));
+    if (spans) {
+        CONE_TRY(linear_named(c, hs, d, Q, "span_embed.layers.0", d, d, b.hid1, d, 1));
+        CONE_TRY(linear_named(c, b.hid1, d, Q, "span_embed.layers.1", d, d, b.hid2, d, 1));
+        CONE_TRY(rowdot_small(b.hid2, d, c.w->p("span_embed.layers.2.weight"), c.w->p("span_embed.layers.2.bias"), spans, Q,
+                              2, d, 1, c.s));
+    }
+    return CONE_OK;
+}
+
+// b.src must hold the projected window rows; vlen / tlen the valid lengths.
+int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg, float* spans, float* saliency,
+                     float* aux_logits, float* aux_spans) {
+    const cone_dims& dm = c.w->dims;
+    const int d = dm.hidden, ff = dm.ffn, nq = dm.num_queries, H = dm.nheads;
+    const int S = b.Lv + b.Lt;
+    const int64_t R = b.B * S, Q = b.B * nq;
+    // encoder (cone/transformer.py:233-246)
+    for (int l = 0; l < dm.enc_layers; ++l) {
+        const std::string p = "transformer.encoder.layers." + std::to_string(l);
+        const float* inw = c.w->p(p + ".self_attn.in_proj_weight");
+        const float* inb = c.w->p(p + ".self_attn.in_proj_bias");
+        CONE_TRY(add_pos_rows(b.src, c.w->pos_table, b.vlen, b.srcpos, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+        CONE_TRY(linear(c, b.srcpos, d, R, inw, inb, 2 * d, d, b.qk, 2 * d, 0));                 // q | k
+        CONE_TRY(linear(c, b.src, d, R, inw + (size_t)2 * d * d, inb + 2 * d, d, d, b.v, d, 0));  // v
+        CONE_TRY(enc_self_attention(b.qk, 2 * d, b.v, d, b.att, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H, c.s));
+        CONE_TRY(linear_named(c, b.att, d, R, p + ".self_attn.out_proj", d, d, b.tmp, d, 0, b.src, d));
+        CONE_TRY(layernorm_rows(b.tmp, nullptr, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), b.src, R, d, 1e-5f, c.s));
+        CONE_TRY(linear_named(c, b.src, d, R, p + ".linear1", ff, d, b.h, b.hw, 1));
+        CONE_TRY(linear_named(c, b.h, b.hw, R, p + ".linear2", d, ff, b.tmp, d, 0, b.src, d));
+        CONE_TRY(layernorm_rows(b.tmp, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.src, R, d, 1e-5f, c.s));
+    }
+    if (saliency) {  // saliency_proj(vid_mem) (cone/model.py:119-122), video rows only
+        CONE_TRY(rowdot_small(b.src, d, c.w->p("saliency_proj.weight"), c.w->p("saliency_proj.bias"), saliency, b.B * b.Lv,
+                              1, d, 0, c.s, b.Lv, S));
+    }
+    // decoder (cone/transformer.py:296-317, 117-146): memory K/V projections of all layers in two GEMMs
+    const int DL = dm.dec_layers;
+    float* kdec = b.h;
+    float* vdec = b.h + (size_t)DL * d;
+    CONE_TRY(add_pos_rows(b.src, c.w->pos_table, b.vlen, b.srcpos, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+    CONE_TRY(linear(c, b.srcpos, d, R, c.w->dec_kw, c.w->dec_kb, DL * d, d, kdec, b.hw, 0));
+    CONE_TRY(linear(c, b.src, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, vdec, b.hw, 0));
+    CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * Q * d, c.s));
+    const float* qpos = c.w->p("query_embed.weight");
+    for (int l = 0; l < DL; ++l) {
+        const std::string p = "transformer.decoder.layers." + std::to_string(l);
+        const float* inw = c.w->p(p + ".self_attn.in_proj_weight");
+        const float* inb = c.w->p(p + ".self_attn.in_proj_bias");
+        CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Q, nq, d, c.s));
+        CONE_TRY(linear(c, b.dqkin, d, Q, inw, inb, 2 * d, d, b.dqk, 2 * d, 0));
+        CONE_TRY(linear(c, b.tgt, d, Q, inw + (size_t)2 * d * d, inb + 2 * d, d, d, b.dv, d, 0));
+        CONE_TRY(dec_self_attention(b.dqk, 2 * d, b.dv, d, b.datt, d, b.B, nq, H, c.s));
+        CONE_TRY(linear_named(c, b.datt, d, Q, p + ".self_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
+        CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), b.tgt, Q, d, 1e-5f, c.s));
+        const float* cw = c.w->p(p + ".multihead_attn.in_proj_weight");
+        const float* cb = c.w->p(p + ".multihead_attn.in_proj_bias");
+        CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Q, nq, d, c.s));
+        CONE_TRY(linear(c, b.dqkin, d, Q, cw, cb, d, d, b.dq, d, 0));
+        CONE_TRY(dec_cross_attention(b.dq, d, kdec + (size_t)l * d, b.hw, vdec + (size_t)l * d, b.hw, b.datt, d, b.vlen,
+                                     b.tlen, b.B, nq, b.Lv, b.Lt, H, c.s));
+        CONE_TRY(linear_named(c, b.datt, d, Q, p + ".multihead_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
+        CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.tgt, Q, d, 1e-5f, c.s));
+        CONE_TRY(linear_named(c, b.tgt, d, Q, p + ".linear1", ff, d, b.dh, ff, 1));
+        CONE_TRY(linear_named(c, b.dh, ff, Q, p + ".linear2", d, ff, b.t2, d, 0, b.tgt, d));
+        CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm3.weight"), c.w->p(p + ".norm3.bias"), b.tgt, Q, d, 1e-5f, c.s));
+        const bool last = (l == DL - 1);
+        if (last || aux_logits || aux_spans) {
+            CONE_TRY(layernorm_rows(b.tgt, nullptr, c.w->p("transformer.decoder.norm.weight"),
+                                    c.w->p("transformer.decoder.norm.bias"), b.hs, Q, d, 1e-5f, c.s));
+            if (last) {
+                CONE_TRY(heads(c, b, b.hs, Q, logits, prob_fg, spans));
+            } else {
+                CONE_TRY(heads(c, b, b.hs, Q, aux_logits ? aux_logits + (size_t)l * Q * 2 : nullptr, nullptr,
+                               aux_spans ? aux_spans + (size_t)l * Q * 2 : nullptr));
+            }
+        }
+    }
+    return CONE_OK;
+}
+
+// A9 after pooling: adapter + residual, normalise, dot with the normalised CLS
+struct MatchBuffers {
+    float *pooled, *hid, *adapted, *tnorm;
+};
+MatchBuffers plan_match(Arena& a, const cone_dims& c, int64_t B, int64_t n_cls) {
+    MatchBuffers m;
+    const int64_t Q = B * c.num_queries;
+    m.pooled = a.get<float>(Q * c.v_dim);
+    m.hid = a.get<float>(Q * c.hidden);
+    m.adapted = a.get<float>(Q * c.v_dim);
+    m.tnorm = a.get<float>(n_cls * c.v_dim);
+    return m;
+}
+int match_core(const Ctx& c, const float* frames, int64_t n_frames, const CoreBuffers& b, const float* spans,
+               const float* cls, int64_t n_cls, MatchBuffers& m, float* out, int nq) {
+    const int dv = c.w->dims.v_dim;
+    CONE_TRY(span_mean_pool(frames, n_frames, b.vid_base, b.vlen, b.pad_len, spans, m.pooled, b.B, nq, dv, c.s));
+    CONE_TRY(adapter_rows(c, m.pooled, b.B * nq, m.hid, m.adapted, 1));
+    CONE_TRY(l2norm_rows(cls, m.tnorm, n_cls, dv, 0.f, c.s));  // text_cls / ||text_cls|| (model.py:142)
+    CONE_TRY(norm_dot(m.adapted, m.tnorm, b.qidx, out, b.B, nq, dv, c.s));
+    return CONE_OK;
+}
+
+int ensure_tc(const cone_weights* w, int prec, cudaStream_t s) {
+    if (prec != CONE_PREC_TC) return CONE_OK;
+    cone_weights* mw = const_cast<cone_weights*>(w);
+    if (mw->tc == nullptr) CONE_TRY(tc_weights_create(&mw->tc, s));
+    return CONE_OK;
+}
+
+int check_prec(int prec) {
+    CONE_REQUIRE(prec == CONE_PREC_FP32 || prec == CONE_PREC_TC, "unknown precision %d", prec);
+    return CONE_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int cone_l2_normalize(const float* x, float* out, int64_t rows, int32_t dim, float eps, void* stream) {
+    return l2norm_rows(x, out, rows, dim, eps, (cudaStream_t)stream);
+}
+
+extern "C" size_t cone_prepare_workspace_bytes(const cone_dims* dims, int64_t n_frames) {
+    if (check_dims(dims) != CONE_OK) return 0;
+    Arena a(nullptr, 0);
+    a.get<float>(n_frames * dims->v_dim);  // xn
+    a.get<float>(n_frames * dims->hidden); // adapter hidden
+    a.get<float>(n_frames * dims->v_dim);  // adapted
+    plan_proj(a, n_frames, dims->v_dim, dims->hidden);
+    return a.used + tc_scratch_bytes(n_frames, dims->v_dim > dims->ffn ? dims->v_dim : dims->ffn);
+}
+
+extern "C" int cone_video_prepare(const cone_weights* w, const float* frames_raw, int64_t n_frames, float* ctx_out,
+                                  float* vidproj_out, void* workspace, size_t workspace_bytes, int precision,
+                                  void* stream) {
+    CONE_REQUIRE(w && frames_raw, "null argument");
+    CONE_TRY(check_prec(precision));
+    Ctx c{w, precision, (cudaStream_t)stream};
+    CONE_TRY(ensure_tc(w, precision, c.s));
+    const cone_dims& dm = w->dims;
+    // frames are processed in slabs sized to the workspace
+    int64_t slab = n_frames;
+    while (slab > 1 && cone_prepare_workspace_bytes(&dm, slab) > workspace_bytes) slab = (slab + 1) / 2;
+    if (cone_prepare_workspace_bytes(&dm, slab) > workspace_bytes) {
+        set_error("cone_video_prepare: workspace of %zu bytes cannot hold one frame", workspace_bytes);
+        return CONE_ERR_WORKSPACE;
+    }
+    for (int64_t f0 = 0; f0 < n_frames; f0 += slab) {
+        const int64_t n = (n_frames - f0) < slab ? (n_frames - f0) : slab;
+        Arena a(workspace, workspace_bytes);
+        float* xn = a.get<float>(n * dm.v_dim);
+        float* hid = a.get<float>(n * dm.hidden);
+        float* ad = a.get<float>(n * dm.v_dim);
+        ProjBuffers pb = plan_proj(a, n, dm.v_dim, dm.hidden);
+        tc_set_scratch(w->tc, a.base ? a.base + a.used : nullptr, workspace_bytes > a.used ? workspace_bytes - a.used : 0);
+        const float* x = frames_raw + f0 * dm.v_dim;
+        if (ctx_out) {
+            // host-side L2 norm of the dataset (dataloader:459), adapter + residual, no-eps norm (inference.py:255-257)
+            CONE_TRY(l2norm_rows(x, xn, n, dm.v_dim, 1e-5f, c.s));
+            CONE_TRY(adapter_rows(c, xn, n, hid, ad, 1));
+            CONE_TRY(l2norm_rows(ad, ctx_out + f0 * dm.v_dim, n, dm.v_dim, 0.f, c.s));
+        }
+        if (vidproj_out) CONE_TRY(input_proj(c, "input_vid_proj", x, n, dm.v_dim, vidproj_out + f0 * dm.hidden, pb));
+    }
+    return CONE_OK;
+}
+
+extern "C" int cone_adapter(const cone_weights* w, const float* x, float* out, int64_t rows, int residual,
+                            void* workspace, size_t workspace_bytes, int precision, void* stream) {
+    CONE_REQUIRE(w && x && out, "null argument");
+    CONE_TRY(check_prec(precision));
+    Ctx c{w, precision, (cudaStream_t)stream};
+    CONE_TRY(ensure_tc(w, precision, c.s));
+    Arena a(workspace, workspace_bytes);
+    float* hid = a.get<float>(rows * w->dims.hidden);
+    if (!a.fits()) {
+        set_error("cone_adapter: workspace needs %zu bytes", a.used);
+        return CONE_ERR_WORKSPACE;
+    }
+    tc_set_scratch(w->tc, a.base + a.used, workspace_bytes - a.used);
+    return adapter_rows(c, x, rows, hid, out, residual);
+}
+
+extern "C" int cone_frame_scores(const float* ctx, int32_t v_dim, const int64_t* video_offsets, const int32_t* q_first,
+                                 int32_t n_videos, int32_t max_video_frames, int32_t max_video_queries,
+                                 const float* cls_norm, float* score_out, const int64_t* score_offsets, int precision,
+                                 void* stream) {
+    CONE_REQUIRE(ctx && video_offsets && q_first && cls_norm && score_out && score_offsets, "null argument");
+    CONE_TRY(check_prec(precision));
+    // The window ranking must be bit-stable: scores are always computed in fp32.
+    return sgemm_frame_scores(ctx, cls_norm, v_dim, video_offsets, q_first, n_videos, max_video_frames,
+                              max_video_queries, score_out, score_offsets, (cudaStream_t)stream);
+}
+
+extern "C" int cone_window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count,
+                                    int32_t n_queries, int32_t max_v_l, int32_t* ranklist_out, float* winscore_out,
+                                    int32_t ranklist_stride, void* stream) {
+    CONE_REQUIRE(frame_score && score_offsets && frame_count && ranklist_out, "null argument");
+    return window_ranklist(frame_score, score_offsets, frame_count, n_queries, max_v_l, ranklist_out, winscore_out,
+                           ranklist_stride, (cudaStream_t)stream);
+}
+
+namespace {
+size_t ground_chunk_bytes(const cone_dims& dm, int64_t nqc, int topk, int Lv, int Lt) {
+    Arena a(nullptr, 0);
+    const int64_t B = nqc * topk;
+    plan_core(a, dm, B, Lv, Lt);
+    plan_match(a, dm, B, nqc);
+    a.get<float>(nqc * Lt * dm.hidden);  // txtproj
+    plan_proj(a, nqc * Lt, dm.t_dim, dm.hidden);
+    return a.used + tc_scratch_bytes(B * (Lv + Lt), dm.ffn);
+}
+}  // namespace
+
+extern "C" size_t cone_workspace_bytes(const cone_dims* dims, int64_t n_windows, int32_t lv, int32_t lt) {
+    if (check_dims(dims) != CONE_OK) return 0;
+    // dense forward: vid/txt projections of every row + core + matching
+    Arena a(nullptr, 0);
+    plan_core(a, *dims, n_windows, lv, lt);
+    plan_match(a, *dims, n_windows, n_windows);
+    a.get<float>(n_windows * lv * dims->hidden);
+    a.get<float>(n_windows * lt * dims->hidden);
+    plan_proj(a, n_windows * lv, dims->v_dim, dims->hidden);
+    plan_proj(a, n_windows * lt, dims->t_dim, dims->hidden);
+    return a.used + tc_scratch_bytes(n_windows * (lv + lt), dims->ffn) + 4096;
+}
+
+extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_raw, int64_t n_frames,
+                                   const float* vidproj, const int64_t* q_video_start, const int32_t* q_video_len,
+                                   const int32_t* ranklist, int32_t ranklist_stride, const float* tok,
+                                   const int32_t* tok_len, const float* cls_norm, const int32_t* q_batch,
+                                   int32_t n_batches, int32_t n_queries, int32_t topk, float* pred_spans,
+                                   float* prob_fg, float* match, int32_t* win_start, int32_t* win_len, void* workspace,
+                                   size_t workspace_bytes, int precision, void* stream) {
+    CONE_REQUIRE(w && frames_raw && vidproj && q_video_start && q_video_len && ranklist && tok && tok_len && cls_norm &&
+                     q_batch && pred_spans && prob_fg && match && win_start && win_len && workspace,
+                 "null argument");
+    CONE_REQUIRE(topk >= 1 && n_batches >= 1 && n_queries >= 0, "bad sizes");
+    CONE_TRY(check_prec(precision));
+    Ctx c{w, precision, (cudaStream_t)stream};
+    CONE_TRY(ensure_tc(w, precision, c.s));
+    const cone_dims& dm = w->dims;
+    const int Lv = dm.max_v_l, Lt = dm.max_q_l, nq = dm.num_queries;
+    if (n_queries == 0) return CONE_OK;
+
+    // window descriptors of every query, and the per-eval-batch padded length the reference pools over
+    CONE_TRY(build_windows(ranklist, ranklist_stride, q_video_len, n_queries, topk, Lv, win_start, win_len, c.s));
+    Arena head(workspace, workspace_bytes);
+    int32_t* batch_max = head.get<int32_t>(n_batches);
+    if (!head.fits()) {
+        set_error("cone_ground_windows: workspace too small");
+        return CONE_ERR_WORKSPACE;
+    }
+    CONE_TRY(batch_max_len(win_len, q_batch, n_queries, topk, batch_max, n_batches, c.s));
+
+    const size_t avail = workspace_bytes - head.used;
+    int64_t nqc = n_queries;
+    while (nqc > 1 && ground_chunk_bytes(dm, nqc, topk, Lv, Lt) > avail) nqc = (nqc + 1) / 2;
+    if (ground_chunk_bytes(dm, nqc, topk, Lv, Lt) > avail) {
+        set_error("cone_ground_windows: workspace of %zu bytes cannot hold one query (%zu needed)", workspace_bytes,
+                  ground_chunk_bytes(dm, 1, topk, Lv, Lt) + head.used);
+        return CONE_ERR_WORKSPACE;
+    }
+    for (int64_t q0 = 0; q0 < n_queries; q0 += nqc) {
+        const int64_t n = (n_queries - q0) < nqc ? (n_queries - q0) : nqc;
+        const int64_t B = n * topk;
+        Arena a((char*)workspace + head.used, avail);
+        CoreBuffers cb = plan_core(a, dm, B, Lv, Lt);
+        MatchBuffers mb = plan_match(a, dm, B, n);
+        float* txtproj = a.get<float>(n * Lt * dm.hidden);
+        ProjBuffers pb = plan_proj(a, n * Lt, dm.t_dim, dm.hidden);
+        tc_set_scratch(w->tc, a.base + a.used, avail > a.used ? avail - a.used : 0);
+        // text projection once per query (the reference recomputes it for each of the k windows)
+        CONE_TRY(input_proj(c, "input_txt_proj", tok + q0 * Lt * dm.t_dim, n * Lt, dm.t_dim, txtproj, pb));
+        CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
+                                        topk, Lt, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
+        CONE_TRY(gather_window_rows(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));
+        float* spans_c = pred_spans + q0 * topk * nq * 2;
+        CONE_TRY(transformer_core(c, cb, nullptr, prob_fg + q0 * topk * nq, spans_c, nullptr, nullptr, nullptr));
+        CONE_TRY(match_core(c, frames_raw, n_frames, cb, spans_c, cls_norm + q0 * dm.v_dim, n, mb, match + q0 * topk * nq, nq));
+    }
+    return CONE_OK;
+}
+
+extern "C" int cone_forward(const cone_weights* w, const float* src_txt, const int32_t* txt_len, const float* src_vid,
+                            const int32_t* vid_len, int32_t B, int32_t Lt, int32_t Lv, float* pred_logits,
+                            float* pred_spans, float* saliency, float* aux_logits, float* aux_spans, void* workspace,
+                            size_t workspace_bytes, int precision, void* stream) {
+    CONE_REQUIRE(w && src_txt && txt_len && src_vid && vid_len && pred_logits && pred_spans && workspace, "null argument");
+    CONE_TRY(check_prec(precision));
+    const cone_dims& dm = w->dims;
+    CONE_REQUIRE(Lv >= 1 && Lv <= dm.max_v_l, "cone_forward: L_vid=%d exceeds max_v_l=%d of the weights handle", Lv, dm.max_v_l);
+    CONE_REQUIRE(Lt >= 1 && Lv + Lt <= 256, "cone_forward: window of %d rows exceeds 256", Lv + Lt);
+    if (B == 0) return CONE_OK;
+    Ctx c{w, precision, (cudaStream_t)stream};
+    CONE_TRY(ensure_tc(w, precision, c.s));
+    Arena a(workspace, workspace_bytes);
+    CoreBuffers cb = plan_core(a, dm, B, Lv, Lt);
+    float* vidproj = a.get<float>((int64_t)B * Lv * dm.hidden);
+    float* txtproj = a.get<float>((int64_t)B * Lt * dm.hidden);
+    ProjBuffers pv = plan_proj(a, (int64_t)B * Lv, dm.v_dim, dm.hidden);
+    ProjBuffers pt = plan_proj(a, (int64_t)B * Lt, dm.t_dim, dm.hidden);
+    if (!a.fits()) {
+        set_error("cone_forward: workspace needs %zu bytes, got %zu", a.used, workspace_bytes);
+        return CONE_ERR_WORKSPACE;
+    }
+    tc_set_scratch(w->tc, a.base + a.used, workspace_bytes - a.used);
+    CONE_TRY(input_proj(c, "input_vid_proj", src_vid, (int64_t)B * Lv, dm.v_dim, vidproj, pv));
+    CONE_TRY(input_proj(c, "input_txt_proj", src_txt, (int64_t)B * Lt, dm.t_dim, txtproj, pt));
+    CONE_TRY(fill_window_desc_dense(cb.vid_base, cb.txt_base, cb.qidx, B, Lv, Lt, c.s));
+    CONE_CUDA(cudaMemcpyAsync(cb.vlen, vid_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, c.s));
+    CONE_CUDA(cudaMemcpyAsync(cb.tlen, txt_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, c.s));
+    CONE_TRY(gather_window_rows(vidproj, (int64_t)B * Lv, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));
+    return transformer_core(c, cb, pred_logits, nullptr, pred_spans, saliency, aux_logits, aux_spans);
+}
+
+extern "C" int cone_clip_matching(const cone_weights* w, const float* src_cls_txt, const float* src_vid_appear,
+                                  const int32_t* vid_len, const float* spans, int32_t B, int32_t Lv, int32_t nq,
+                                  float* out, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+    CONE_REQUIRE(w && src_cls_txt && src_vid_appear && vid_len && spans && out && workspace, "null argument");
+    CONE_TRY(check_prec(precision));
+    CONE_REQUIRE(nq >= 1 && nq <= 64, "cone_clip_matching: bad number of proposals");
+    if (B == 0) return CONE_OK;
+    const cone_dims& dm = w->dims;
+    Ctx c{w, precision, (cudaStream_t)stream};
+    CONE_TRY(ensure_tc(w, precision, c.s));
+    Arena a(workspace, workspace_bytes);
+    CoreBuffers cb{};
+    cb.B = B;
+    cb.vid_base = a.get<int64_t>(B);
+    cb.txt_base = a.get<int64_t>(B);
+    cb.vlen = a.get<int32_t>(B);
+    cb.pad_len = a.get<int32_t>(B);
+    cb.qidx = a.get<int32_t>(B);
+    MatchBuffers mb;
+    const int64_t Q = (int64_t)B * nq;
+    mb.pooled = a.get<float>(Q * dm.v_dim);
+    mb.hid = a.get<float>(Q * dm.hidden);
+    mb.adapted = a.get<float>(Q * dm.v_dim);
+    mb.tnorm = a.get<float>((int64_t)B * dm.v_dim);
+    if (!a.fits()) {
+        set_error("cone_clip_matching: workspace needs %zu bytes, got %zu", a.used, workspace_bytes);
+        return CONE_ERR_WORKSPACE;
+    }
+    tc_set_scratch(w->tc, a.base + a.used, workspace_bytes - a.used);
+    CONE_TRY(fill_window_desc_dense(cb.vid_base, cb.txt_base, cb.qidx, B, Lv, 0, c.s));
+    CONE_CUDA(cudaMemcpyAsync(cb.vlen, vid_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, c.s));
+    CONE_TRY(fill_i32(cb.pad_len, B, Lv, c.s));  // the dense tensor is already padded to Lv rows
+    return match_core(c, src_vid_appear, (int64_t)B * Lv, cb, spans, src_cls_txt, B, mb, out, nq);
+}
+
+extern "C" int cone_fuse_nms(const float* pred_spans, const float* prob_fg, const float* match, const int32_t* win_start,
+                             const int32_t* win_len, int32_t n_queries, int32_t topk, int32_t nq, float clip_length,
+                             double nms_thd, int32_t max_before_nms, int32_t max_after_nms, double* out,
+                             int32_t* out_count, double* rows_out, int32_t* rows_count, void* stream) {
+    CONE_REQUIRE(pred_spans && prob_fg && match && win_start && win_len && out && out_count, "null argument");
+    return fuse_nms(pred_spans, prob_fg, match, win_start, win_len, n_queries, topk, nq, clip_length, nms_thd,
+                    max_before_nms, max_after_nms, out, out_count, rows_out, rows_count, (cudaStream_t)stream);
+}
+
+extern "C" int cone_temporal_nms(const double* st, const double* ed, const double* score, int32_t n, double nms_thd,
+                                 int32_t max_after_nms, int32_t* keep_out, int32_t* n_keep_out, void* stream) {
+    CONE_REQUIRE(keep_out && n_keep_out && (n == 0 || (st && ed && score)), "null argument");
+    return temporal_nms_single(st, ed, score, n, nms_thd, max_after_nms, keep_out, n_keep_out, (cudaStream_t)stream);
+}

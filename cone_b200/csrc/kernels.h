@@ -1,0 +1,97 @@
+// Internal launcher declarations shared by the .cu files of libcone_b200.
+#pragma once
+#include "common.cuh"
+
+namespace cone {
+
+// ---------------------------------------------------------------- gemm_simt.cu
+// C[M,N] = epi(A[M,K] * W[N,K]^T): both operands K-major (row-major activations x nn.Linear weight).
+struct GemmParams {
+    const float* A = nullptr;
+    int64_t lda = 0;
+    const float* W = nullptr;
+    int64_t ldw = 0;
+    float* C = nullptr;
+    int64_t ldc = 0;
+    const float* bias = nullptr;  // [N] or null
+    const float* R = nullptr;     // residual [M,N] or null, added after bias, before relu
+    int64_t ldr = 0;
+    int64_t M = 0;
+    int N = 0, K = 0;
+    int relu = 0;
+};
+int sgemm_nt(const GemmParams& p, cudaStream_t s);
+
+// Grouped frame-score GEMM: for video v, C_v[q, f] = cls[q] . ctx[f]   (q in the video's queries)
+int sgemm_frame_scores(const float* ctx, const float* cls, int K, const int64_t* video_offsets, const int32_t* q_first,
+                       int n_videos, int max_video_frames, int max_video_queries, float* score,
+                       const int64_t* score_offsets, cudaStream_t s);
+
+// out[row, n] = epi(x[row,:K] . W[n,:K] + bias[n]) for tiny N (<= 8). mode: 0 none, 1 sigmoid,
+// 2 "softmax over the N outputs, write element 0 only" (out has 1 column), 3 softmax all
+// group_out/group_in > 0 remap rows: output row r reads input row (r / group_out) * group_in + r % group_out
+int rowdot_small(const float* x, int64_t ldx, const float* W, const float* bias, float* out, int64_t rows, int N, int K,
+                 int mode, cudaStream_t s, int group_out = 0, int group_in = 0);
+
+// ---------------------------------------------------------------- rowops.cu
+int layernorm_rows(const float* x, const float* residual, const float* gamma, const float* beta, float* out,
+                   int64_t rows, int D, float eps, cudaStream_t s);
+int l2norm_rows(const float* x, float* out, int64_t rows, int D, float eps, cudaStream_t s);
+int build_pos_table(float* table, int max_v_l, int d, cudaStream_t s);  // [max_v_l+1, max_v_l, d]
+// window rows: src[b*S + r] = r < Lv ? vidproj[min(vid_base[b]+r, n_vid_rows-1)] : txtproj[txt_base[b] + r - Lv]
+int gather_window_rows(const float* vidproj, int64_t n_vid_rows, const int64_t* vid_base, const float* txtproj,
+                       const int64_t* txt_base, float* src, int64_t B, int Lv, int Lt, int d, cudaStream_t s);
+// out[b*S + r] = src[b*S + r] + (r < Lv ? pos[vlen[b]][r] : 0)
+int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, float* out, int64_t B, int Lv, int Lt,
+                 int d, int table_lv, cudaStream_t s);
+// out[row] = x[row] + table[row % period]   (x may be null = zeros)
+int add_row_table(const float* x, const float* table, float* out, int64_t rows, int period, int d, cudaStream_t s);
+int fill_window_desc_dense(int64_t* vid_base, int64_t* txt_base, int32_t* qidx, int64_t B, int Lv, int Lt,
+                           cudaStream_t s);
+int fill_i32(int32_t* p, int64_t n, int32_t value, cudaStream_t s);
+
+// ---------------------------------------------------------------- attention.cu
+// encoder self-attention over S = Lv+Lt rows per window, head_dim 32
+int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo,
+                       const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
+                       cudaStream_t s);
+// decoder self-attention over nq slots (no mask)
+int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo, int64_t B,
+                       int nq, int nheads, cudaStream_t s);
+// decoder cross-attention: nq queries x S memory keys with key-padding mask
+int dec_cross_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
+                        int Lt, int nheads, cudaStream_t s);
+
+// ---------------------------------------------------------------- prefilter.cu
+int window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count, int n_queries,
+                    int max_v_l, int32_t* ranklist, float* winscore, int ranklist_stride, cudaStream_t s);
+// window descriptors of the first `topk` ranked windows of each query
+int build_windows(const int32_t* ranklist, int ranklist_stride, const int32_t* q_video_len, int n_queries, int topk,
+                  int max_v_l, int32_t* win_start, int32_t* win_len, cudaStream_t s);
+int batch_max_len(const int32_t* win_len, const int32_t* q_batch, int n_queries, int topk, int32_t* batch_max,
+                  int n_batches, cudaStream_t s);
+// per-chunk descriptors for queries [q0, q0+nq)
+int fill_window_desc_chunk(const int64_t* q_video_start, const int32_t* win_start, const int32_t* win_len,
+                           const int32_t* tok_len, const int32_t* q_batch, const int32_t* batch_max, int q0, int nqc,
+                           int topk, int Lt, int64_t* vid_base, int32_t* vlen, int64_t* txt_base, int32_t* tlen,
+                           int32_t* pad_len, int32_t* qidx, cudaStream_t s);
+
+// ---------------------------------------------------------------- pool_match.cu
+// pooled[(b*nq+j), :] = mean of zero-padded window rows [start, min(end, pad_len)) (model.py:186-200)
+int span_mean_pool(const float* frames, int64_t n_frames, const int64_t* vid_base, const int32_t* vlen,
+                   const int32_t* pad_len, const float* spans, float* pooled, int64_t B, int nq, int Dv,
+                   cudaStream_t s);
+// out[b*nq+j] = (p / ||p||) . t[qidx[b]]
+int norm_dot(const float* p, const float* t, const int32_t* qidx, float* out, int64_t B, int nq, int Dv,
+             cudaStream_t s);
+
+// ---------------------------------------------------------------- fuse_nms.cu
+int fuse_nms(const float* pred_spans, const float* prob_fg, const float* match, const int32_t* win_start,
+             const int32_t* win_len, int n_queries, int topk, int nq, float clip_length, double nms_thd,
+             int max_before_nms, int max_after_nms, double* out, int32_t* out_count, double* rows_out,
+             int32_t* rows_count, cudaStream_t s);
+int temporal_nms_single(const double* st, const double* ed, const double* score, int n, double nms_thd,
+                        int max_after_nms, int32_t* keep_out, int32_t* n_keep_out, cudaStream_t s);
+
+}  // namespace cone
