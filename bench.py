@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the CONE coarse-to-fine grounding path on B200 (BASELINE.json metric: grounding queries/s,
+MAD-shape, device-timed).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port) on host cores
+
+A step = one pass of the whole hot path (stages 0-3: adapter + window pre-filter + Moment-DETR on the top-k
+windows + proposal matching + fusion/NMS) over one synthetic MAD-shaped movie with all its queries.  Per-GPU
+work is fixed as N grows (weak scaling): every rank owns `--movies` movies (its shard of the movie set); ranks
+exchange nothing on the data path and all-gather the fixed-size per-query prediction blocks at the end.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=8)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--config", default="mad768", choices=["mad768", "mad512", "ego4d"])
+    p.add_argument("--precision", default=os.environ.get("CONE_BENCH_PRECISION", "fp32"), choices=["fp32", "tc"])
+    p.add_argument("--movies", type=int, default=8, help="movies resident per GPU (cycled through by the steps)")
+    p.add_argument("--queries-per-movie", type=int, default=640)
+    p.add_argument("--frames", type=int, nargs=2, default=None, help="movie length range in frames")
+    p.add_argument("--cpu-sample-queries", type=int, default=256)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--workspace-gb", type=float, default=24.0)
+    p.add_argument("--seed", type=int, default=0)
+    return p.parse_args()
+
+
+def workload_name(cfg, args, frames):
+    return (f"{cfg.name}: synthetic movies of {frames[0]}-{frames[1]} frames x {cfg.v_feat_dim}-d, "
+            f"{args.queries_per_movie} queries/movie, window {cfg.max_v_l}, top-{cfg.topk_window} windows, "
+            f"nms {cfg.nms_thd}")
+
+
+def frames_range(cfg, args):
+    if args.frames:
+        return tuple(args.frames)
+    return (36000, 54000) if cfg.name.startswith("mad") else (900, 900)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops_per_query(cfg):
+    """transformer + heads FLOPs per query, counted as the reference computes them (text and
+    video projections once per window)."""
+    d, ff, S = cfg.hidden_dim, cfg.dim_feedforward, cfg.max_v_l + cfg.max_q_l
+    nq = cfg.num_queries
+    vid = cfg.max_v_l * (cfg.v_feat_dim * d + d * d) * 2
+    txt = cfg.max_q_l * (cfg.t_feat_dim * d + d * d) * 2
+    enc = cfg.enc_layers * (S * (4 * d * d + 2 * d * ff) * 2 + 2 * S * S * d * 2)
+    dec = cfg.dec_layers * (S * 2 * d * d * 2 + nq * (6 * d * d + 2 * d * ff) * 2 + 2 * nq * S * d * 2 + 2 * nq * nq * d * 2)
+    heads = nq * (2 * d * d + 2 * d + 2 * d) * 2
+    return cfg.topk_window * (vid + txt + enc + dec + heads)
+
+
+def cpu_oracle_sample(cfg, sd, ds, n_queries, threads):
+    """The reference's CPU path (oracle port) on a bounded sample: the first movie with its first n queries."""
+    import torch
+    from oracle import cone_oracle as O
+    torch.set_num_threads(threads)
+    qs = [q for q in ds.queries if q.video_idx == 0][:n_queries]
+    t0 = time.perf_counter()
+    O.eval_pipeline(sd, cfg, ds.videos[:1], qs, collect_raw=False)
+    dt = time.perf_counter() - t0
+    return len(qs) / dt, dt, len(qs)
+
+
+def run_reference(args):
+    import torch
+    from cone_b200.config import PRESETS
+    from cone_b200.synth import make_dataset
+    from cone_b200.weights import init_state_dict
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = PRESETS[args.config]
+    fr = frames_range(cfg, args)
+    threads = os.cpu_count() or 1
+    sd = init_state_dict(cfg, args.seed)
+    ds = make_dataset(cfg, 1, None, args.cpu_sample_queries, seed=args.seed, frames_range=fr)
+    times = []
+    for i in range(args.warmup + args.steps):
+        qps, dt, n = cpu_oracle_sample(cfg, sd, ds, args.cpu_sample_queries, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = args.steps * args.cpu_sample_queries / total
+    sample = (f"each step = stages 0-3 on 1 movie of {len(ds.videos[0])} frames with {args.cpu_sample_queries} of its "
+              f"{args.queries_per_movie} queries, torch-CPU fp32, {threads} threads")
+    line = {"impl": "reference", "metric": "grounding_queries_per_sec", "value": value, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, args, fr), "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cone_b200 import _lib
+    from cone_b200.config import PRESETS
+    from cone_b200.engine import ConeEngine
+    from cone_b200.inference import run_step, stage_step
+    from cone_b200.sharding import gather_predictions
+    from cone_b200.synth import make_dataset
+    from cone_b200.weights import init_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cone_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = PRESETS[args.config]
+    fr = frames_range(cfg, args)
+    sd = init_state_dict(cfg, args.seed)
+    # every rank owns its own shard of the movie set (weak scaling): movie ids rank*M .. rank*M+M-1
+    ds = make_dataset(cfg, args.movies, None, args.queries_per_movie, seed=args.seed + 1000 * rank, frames_range=fr,
+                      id_offset=rank * args.movies)
+    eng = ConeEngine(cfg, sd, device=dev, precision=args.precision, workspace_bytes=int(args.workspace_gb * (1 << 30)))
+    host_steps = [stage_step(cfg, ds.videos, ds.queries, [v]) for v in range(args.movies)]
+    dev_steps = [(s.frames.to(dev), s.qb.to(dev)) for s in host_steps]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed region: inputs resident in HBM (1.1 GB of movies cycled: larger than the 126 MB L2) ----
+    for i in range(args.warmup):
+        eng.ground(*dev_steps[i % args.movies])
+    barrier()
+    lib = _lib.load()
+    _lib.reset_launch_count()
+    has_prof = hasattr(lib, "cone_profile_enable")
+    if has_prof:
+        lib.cone_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_queries = 0
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            out = eng.ground(*dev_steps[i % args.movies])
+            n_queries += out.nms_count.shape[0]
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count()
+    prof = None
+    if has_prof:
+        from cone_b200.engine import read_profile
+        prof = read_profile()
+        lib.cone_profile_enable(0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    nq_t = torch.tensor([n_queries], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nq_t, op=dist.ReduceOp.SUM)
+    ms_max, nq_all = float(t.item()), float(nq_t.item())
+    value = nq_all / (ms_max / 1e3)
+
+    # ---- end to end: pinned host inputs -> H2D -> path -> D2H of the predictions (+ all-gather across ranks) ----
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for i in range(args.steps):
+        s = host_steps[i % args.movies]
+        out = run_step(eng, s)
+        if world > 1:
+            nms, cnt = gather_predictions(out.nms, out.nms_count)
+        else:
+            nms, cnt = out.nms, out.nms_count
+        nms_h, cnt_h = nms.cpu(), cnt.cpu()  # device->host read of the step's result
+        h2d += s.h2d_bytes()
+        d2h += nms_h.numel() * 8 + cnt_h.numel() * 4
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = nq_all / float(te.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        line = {"metric": "grounding_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+                "data": "synthetic",
+                "config": {"workload": workload_name(cfg, args, fr), "movies_per_gpu": args.movies,
+                           "queries_per_step": args.queries_per_movie, "precision": args.precision,
+                           "l2": "inputs larger than L2: steps cycle through %d movies (%.2f GB) resident in HBM" %
+                                 (args.movies, sum(v.nbytes for v in ds.videos) / 1e9),
+                           "parallelism": f"movie-sharded x{world}, all-gather of per-query predictions"},
+                "clocks": clocks.summary(), "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": d2h // args.steps}}
+        flops_q = algorithmic_flops_per_query(cfg)
+        line["roofline"] = roofline_entry(prof, peaks, flops_q, args, cfg)
+        if prof:
+            line["stage_ms_per_step"] = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            qps, dt, n = cpu_oracle_sample(cfg, sd, ds, args.cpu_sample_queries, threads)
+            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                                    "sample": f"stages 0-3 on movie 0 ({len(ds.videos[0])} frames) with {n} of its "
+                                              f"{args.queries_per_movie} queries, torch-CPU fp32 oracle port, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline_entry(prof, peaks, flops_per_query, args, cfg):
+    """Dominant kernel of the step: the dense-projection GEMM.  achieved = algorithmic GEMM FLOPs per launch /
+    average launch duration (CUDA events around every launch, on the launching stream)."""
+    key = "gemm_tc" if args.precision == "tc" else "gemm_fp32"
+    peak = peaks.get("bf16_tflops_sustained")
+    src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    if peak is None:
+        peak, src = 1400.0, "fallback B200_PROFILING.md (~1.4 PFLOP/s sustained)"
+    if not prof or key not in prof or not prof[key]["launches"]:
+        return {"bound": "tensor", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                "note": "per-kernel profile unavailable"}
+    p = prof[key]
+    achieved = p["flops"] / (p["ms"] * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": key, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None, "launches": p["launches"],
+            "avg_launch_ms": p["ms"] / p["launches"], "share_of_step": p["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
+            "peak_source": src}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -23,7 +23,67 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+// ---- per-kernel profile -------------------------------------------------------------------------
+namespace {
+struct ProfRec {
+    cudaEvent_t a, b;
+    int cat;
+    double flops, bytes;
+};
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfRec> g_prof;
+thread_local std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+ProfScope::ProfScope(cudaStream_t s, ProfCat cat, double flops, double bytes) : slot(-1), stream(s) {
+    if (!g_prof_on) return;
+    ProfRec r{take_event(), take_event(), (int)cat, flops, bytes};
+    cudaEventRecord(r.a, s);
+    slot = (int)g_prof.size();
+    g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
+
 }  // namespace cone
+
+static const char* kProfNames[cone::P_COUNT] = {"gemm_fp32", "gemm_tc", "enc_attention", "dec_attention", "layernorm",
+                                                "rowops", "frame_scores", "window_ranklist", "span_pool", "fuse_nms",
+                                                "convert"};
+extern "C" void cone_profile_enable(int on) {
+    cone::g_prof_on = on != 0;
+}
+extern "C" int cone_profile_categories(void) { return cone::P_COUNT; }
+extern "C" const char* cone_profile_name(int cat) { return (cat >= 0 && cat < cone::P_COUNT) ? kProfNames[cat] : ""; }
+// Waits for the recorded events, adds them up per category and clears the log.
+extern "C" int cone_profile_read(double* ms, int64_t* launches, double* flops, double* bytes, int ncat) {
+    for (int i = 0; i < ncat; ++i) {
+        ms[i] = 0; launches[i] = 0; flops[i] = 0; bytes[i] = 0;
+    }
+    for (auto& r : cone::g_prof) {
+        float t = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&t, r.a, r.b);
+        if (r.cat < ncat) {
+            ms[r.cat] += t; launches[r.cat] += 1; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes;
+        }
+        cone::g_event_pool.push_back(r.a);
+        cone::g_event_pool.push_back(r.b);
+    }
+    cone::g_prof.clear();
+    return CONE_OK;
+}
 
 using namespace cone;
 

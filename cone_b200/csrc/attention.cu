@@ -217,6 +217,7 @@ int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
         attr_set = true;
     }
     dim3 grid((unsigned)B, (unsigned)nheads);
+    ProfScope ps(s, P_ENC_ATTN, 4.0 * (double)B * nheads * S * S * HD, 16.0 * (double)B * S * nheads * HD);
     enc_self_attention_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(qk, ldqk, v, ldv, o, ldo, vlen, tlen, Lv, Lt,
                                                                nheads * HD);
     CONE_LAUNCH_CHECK("enc_self_attention");
@@ -228,6 +229,7 @@ int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
     if (B == 0) return CONE_OK;
     CONE_REQUIRE(nq <= 8, "dec_self_attention: at most 8 moment slots");
     const int warps = 4;
+    ProfScope ps(s, P_DEC_ATTN);
     dec_self_attention_kernel<<<(unsigned)cdiv64(B * nheads, warps), warps * 32, 0, s>>>(qk, ldqk, v, ldv, o, ldo, B, nq,
                                                                                        nheads, nheads * HD);
     CONE_LAUNCH_CHECK("dec_self_attention");
@@ -243,6 +245,7 @@ int dec_cross_attention(const float* q, int64_t ldq, const float* k, int64_t ldk
     CONE_REQUIRE((ldk & 3) == 0, "dec_cross_attention: ldk must be a multiple of 4");
     const int warps = 4;
     const size_t smem = sizeof(float) * warps * (8 * HD + 8 * (size_t)S);
+    ProfScope ps(s, P_DEC_ATTN, 4.0 * (double)B * nheads * nq * S * HD, 8.0 * (double)B * S * nheads * HD);
     dec_cross_attention_kernel<<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
         q, ldq, k, ldk, v, ldv, o, ldo, vlen, tlen, B, nq, Lv, Lt, nheads);
     CONE_LAUNCH_CHECK("dec_cross_attention");

@@ -266,6 +266,7 @@ int fuse_nms(const float* pred_spans, const float* prob_fg, const float* match, 
     CONE_REQUIRE(smem <= 200 * 1024, "fuse_nms: %d candidates per query exceed shared memory", topk * nq);
     if (smem > 48 * 1024)
         CONE_CUDA(cudaFuncSetAttribute(fuse_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(s, P_NMS);
     fuse_nms_kernel<<<n_queries, NMS_THREADS, smem, s>>>(pred_spans, prob_fg, match, win_start, win_len, topk, nq,
                                                          clip_length, nms_thd, max_before_nms, max_after_nms, out,
                                                          out_count, rows_out, rows_count);

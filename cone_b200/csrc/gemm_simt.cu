@@ -229,6 +229,7 @@ int sgemm_nt(const GemmParams& g, cudaStream_t s) {
                  "sgemm_nt: operands must be 16-byte aligned");
     TileArgs p{g.A, g.lda, g.W, g.ldw, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K, g.relu};
     dim3 grid((unsigned)cdiv64(g.M, BM), (unsigned)cdiv(g.N, BN), 1);
+    ProfScope ps(s, P_GEMM_FP32, 2.0 * (double)g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N));
     sgemm_nt_kernel<<<grid, NTHREADS, 0, s>>>(p);
     CONE_LAUNCH_CHECK("sgemm_nt");
     return CONE_OK;
@@ -241,6 +242,7 @@ int sgemm_frame_scores(const float* ctx, const float* cls, int K, const int64_t*
     CONE_REQUIRE((K & 3) == 0, "frame_scores: feature dim must be a multiple of 4");
     CONE_REQUIRE(n_videos <= 65535, "frame_scores: at most 65535 videos per call");
     dim3 grid((unsigned)cdiv(max_video_frames, BN), (unsigned)cdiv(max_video_queries, BM), (unsigned)n_videos);
+    ProfScope ps(s, P_SCORES);
     frame_scores_kernel<<<grid, NTHREADS, 0, s>>>(ctx, cls, K, video_offsets, q_first, score, score_offsets);
     CONE_LAUNCH_CHECK("frame_scores");
     return CONE_OK;
@@ -251,6 +253,7 @@ int rowdot_small(const float* x, int64_t ldx, const float* W, const float* bias,
     if (rows == 0) return CONE_OK;
     CONE_REQUIRE(N >= 1 && N <= 8 && (K & 3) == 0 && (ldx & 3) == 0, "rowdot_small: unsupported shape N=%d K=%d", N, K);
     const int warps = 8;
+    ProfScope ps(s, P_ROWOPS);
     rowdot_small_kernel<8><<<(unsigned)cdiv64(rows, warps), warps * 32, 0, s>>>(x, ldx, W, bias, out, rows, N, K, mode,
                                                                                         group_out, group_in);
     CONE_LAUNCH_CHECK("rowdot_small");

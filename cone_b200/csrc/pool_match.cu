@@ -87,6 +87,7 @@ int span_mean_pool(const float* frames, int64_t n_frames, const int64_t* vid_bas
     if (B == 0) return CONE_OK;
     CONE_REQUIRE((Dv & 3) == 0, "span_mean_pool: Dv must be a multiple of 4");
     const int threads = (Dv / 4) >= 256 ? 256 : ((Dv / 4 + 31) / 32) * 32;
+    ProfScope ps(s, P_POOL);
     span_mean_pool_kernel<<<(unsigned)(B * nq), threads, 0, s>>>(frames, n_frames, vid_base, vlen, pad_len, spans, pooled,
                                                                nq, Dv);
     CONE_LAUNCH_CHECK("span_mean_pool");
@@ -97,6 +98,7 @@ int norm_dot(const float* p, const float* t, const int32_t* qidx, float* out, in
              cudaStream_t s) {
     if (B == 0) return CONE_OK;
     const int warps = 8;
+    ProfScope ps(s, P_POOL);
     norm_dot_kernel<<<(unsigned)cdiv64(B * nq, warps), warps * 32, 0, s>>>(p, t, qidx, out, B * nq, nq, Dv);
     CONE_LAUNCH_CHECK("norm_dot");
     return CONE_OK;

@@ -128,6 +128,7 @@ int window_ranklist(const float* frame_score, const int64_t* score_offsets, cons
     if (smem > 48 * 1024) {
         CONE_CUDA(cudaFuncSetAttribute(window_ranklist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    ProfScope ps(s, P_RANKLIST);
     window_ranklist_kernel<<<n_queries, 256, smem, s>>>(frame_score, score_offsets, frame_count, max_v_l, ranklist,
                                                         winscore, ranklist_stride, npad);
     CONE_LAUNCH_CHECK("window_ranklist");

@@ -179,6 +179,7 @@ int layernorm_rows(const float* x, const float* residual, const float* gamma, co
                    int64_t rows, int D, float eps, cudaStream_t s) {
     if (rows == 0) return CONE_OK;
     CONE_REQUIRE((D & 3) == 0, "layernorm: D must be a multiple of 4");
+    ProfScope ps(s, P_LAYERNORM, 0.0, (residual ? 12.0 : 8.0) * (double)rows * D);
     layernorm_rows_kernel<<<(unsigned)cdiv64(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(x, residual, gamma,
                                                                                                beta, out, rows, D, eps);
     CONE_LAUNCH_CHECK("layernorm_rows");
@@ -188,6 +189,7 @@ int layernorm_rows(const float* x, const float* residual, const float* gamma, co
 int l2norm_rows(const float* x, float* out, int64_t rows, int D, float eps, cudaStream_t s) {
     if (rows == 0) return CONE_OK;
     CONE_REQUIRE((D & 3) == 0, "l2norm: D must be a multiple of 4");
+    ProfScope ps(s, P_LAYERNORM, 0.0, 8.0 * (double)rows * D);
     l2norm_rows_kernel<<<(unsigned)cdiv64(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(x, out, rows, D, eps);
     CONE_LAUNCH_CHECK("l2norm_rows");
     return CONE_OK;
@@ -203,6 +205,7 @@ int build_pos_table(float* table, int max_v_l, int d, cudaStream_t s) {
 int gather_window_rows(const float* vidproj, int64_t n_vid_rows, const int64_t* vid_base, const float* txtproj,
                        const int64_t* txt_base, float* src, int64_t B, int Lv, int Lt, int d, cudaStream_t s) {
     if (B == 0) return CONE_OK;
+    ProfScope ps(s, P_ROWOPS, 0.0, 8.0 * (double)B * (Lv + Lt) * d);
     gather_window_rows_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(vidproj, n_vid_rows, vid_base,
                                                                                    txtproj, txt_base, src, B, Lv, Lt,
                                                                                    d / 4);
@@ -213,6 +216,7 @@ int gather_window_rows(const float* vidproj, int64_t n_vid_rows, const int64_t* 
 int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, float* out, int64_t B, int Lv, int Lt,
                  int d, int table_lv, cudaStream_t s) {
     if (B == 0) return CONE_OK;
+    ProfScope ps(s, P_ROWOPS, 0.0, 8.0 * (double)B * (Lv + Lt) * d);
     add_pos_rows_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(src, pos_table, vlen, out, B, Lv, Lt,
                                                                              d / 4, table_lv);
     CONE_LAUNCH_CHECK("add_pos_rows");
@@ -221,6 +225,7 @@ int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, 
 
 int add_row_table(const float* x, const float* table, float* out, int64_t rows, int period, int d, cudaStream_t s) {
     if (rows == 0) return CONE_OK;
+    ProfScope ps(s, P_ROWOPS, 0.0, 8.0 * (double)rows * d);
     add_row_table_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, s>>>(x, table, out, rows, period, d / 4);
     CONE_LAUNCH_CHECK("add_row_table");
     return CONE_OK;

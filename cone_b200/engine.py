@@ -320,3 +320,14 @@ class ConeEngine:
         # stage 3
         nms, cnt, rows, rcnt = self.fuse_nms(spans, prob, match, wstart, wlen, want_rows=want_rows)
         return GroundingOutput(ranklist, wstart, wlen, spans, prob, match, nms, cnt, rows, rcnt)
+
+
+def read_profile() -> Dict[str, dict]:
+    """Per-category kernel time since profiling was enabled: {name: {ms, launches, flops, bytes}}."""
+    lib = _lib.load()
+    n = lib.cone_profile_categories()
+    ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+    la = (C.c_int64 * n)()
+    _lib.check(lib.cone_profile_read(ms, la, fl, by, n), "cone_profile_read")
+    return {lib.cone_profile_name(i).decode(): {"ms": ms[i], "launches": int(la[i]), "flops": fl[i], "bytes": by[i]}
+            for i in range(n)}

@@ -1,0 +1,57 @@
+"""Multi-GPU layer: whole videos (with all their queries) are independent units through every
+stage, so they are sharded across ranks with no data-path collective; the only exchange is one all-gather of
+the fixed-size per-query prediction blocks at the end (NCCL over NVLink on the GPU box, gloo in CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def video_cost(n_frames: int, n_queries: int, topk: int, alpha: float = 1.0, beta: float = 150.0) -> float:
+    """cost ~ alpha * L (stage 0/1 streams the video once) + beta * Nq * k (windows through Moment-DETR)."""
+    return alpha * n_frames + beta * n_queries * topk
+
+
+def lpt_assign(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Greedy longest-processing-time assignment of videos to ranks; deterministic (ties -> lower id)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * world_size
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda j: (load[j], j))
+        out[r].append(i)
+        load[r] += costs[i]
+    return [sorted(x) for x in out]
+
+
+def gather_predictions(nms: torch.Tensor, count: torch.Tensor, qid: torch.Tensor | None = None, group=None
+                       ) -> Tuple[torch.Tensor, ...]:
+    """All-gather per-query prediction blocks [Nq_local, 3, max_after, 5] (+ counts [Nq_local, 3], + optional
+    int64 query ordinals) from every rank.  Ranks may hold different numbers of queries: blocks are padded to the
+    largest shard, gathered with one collective per tensor and trimmed.  Returns tensors concatenated in rank
+    order."""
+    if not dist.is_available() or not dist.is_initialized():
+        return (nms, count) if qid is None else (nms, count, qid)
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([nms.shape[0]], dtype=torch.int64, device=nms.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    n_max = max(sizes)
+
+    def pad(t):
+        if t.shape[0] == n_max:
+            return t.contiguous()
+        p = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        p[: t.shape[0]] = t
+        return p
+
+    outs = []
+    for t in (nms, count) + ((qid,) if qid is not None else ()):
+        buf = torch.empty((world, n_max) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf.view(-1), pad(t).view(-1), group=group) if t.is_cuda else \
+            dist.all_gather(list(buf.unbind(0)), pad(t), group=group)
+        outs.append(torch.cat([buf[r, : sizes[r]] for r in range(world)], dim=0))
+    return tuple(outs)

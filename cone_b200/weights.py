@@ -74,7 +74,7 @@ def state_dict_shapes(cfg: ConeConfig) -> "OrderedDict[str, tuple]":
 
 
 def init_state_dict(cfg: ConeConfig, seed: int = 0, perturb: bool = True,
-                    head_gain: float = 12.0, attn_gain: float = 4.0) -> "OrderedDict[str, torch.Tensor]":
+                    head_gain: float = 12.0, attn_gain: float = 2.0) -> "OrderedDict[str, torch.Tensor]":
     """Random fp32 state dict, deterministic in (cfg, seed).
 
     Matrices follow the reference's initial distributions (xavier-uniform inside

@@ -164,6 +164,15 @@ int cone_fuse_nms(const float* pred_spans, const float* prob_fg, const float* ma
 int cone_temporal_nms(const double* st, const double* ed, const double* score, int32_t n, double nms_thd,
                       int32_t max_after_nms, int32_t* keep_out, int32_t* n_keep_out, void* stream);
 
+/* ---- measurement hooks (no reference counterpart) --------------------------------------------
+ * Per-kernel timing: when enabled, every launch of the calling thread is bracketed by CUDA events on
+ * its stream; cone_profile_read waits for them and returns, per category, the summed device time
+ * (ms), launch count and the algorithmic FLOPs / bytes the launches were given. */
+void cone_profile_enable(int on);
+int cone_profile_categories(void);
+const char* cone_profile_name(int category);
+int cone_profile_read(double* ms, int64_t* launches, double* flops, double* bytes, int n_categories);
+
 /* number of kernels launched by this library on the calling thread since the last reset */
 int64_t cone_launch_count(void);
 void cone_launch_count_reset(void);
