@@ -40,6 +40,7 @@ SIGNATURES = {
     "cone_l2_normalize": (C.c_int, [_p, _p, _i64, _i32, _f32, _p]),
     "cone_video_prepare": (C.c_int, [_p, _p, _i64, _p, _p, _p, _sz, C.c_int, _p]),
     "cone_adapter": (C.c_int, [_p, _p, _p, _i64, C.c_int, _p, _sz, C.c_int, _p]),
+    "cone_linear": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, C.c_int, _p, _p, _p, _sz, C.c_int, _p]),
     "cone_frame_scores": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _p, _p, C.c_int, _p]),
     "cone_window_ranklist": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _i32, _p]),
     "cone_ground_windows": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _i32,

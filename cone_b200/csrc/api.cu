@@ -590,6 +590,17 @@ extern "C" int cone_adapter(const cone_weights* w, const float* x, float* out, i
     return adapter_rows(c, x, rows, hid, out, residual);
 }
 
+extern "C" int cone_linear(const cone_weights* w, const float* x, const float* W, const float* bias, int64_t M, int32_t N,
+                           int32_t K, int relu, const float* residual, float* y, void* workspace, size_t workspace_bytes,
+                           int precision, void* stream) {
+    CONE_REQUIRE(w && x && W && y, "null argument");
+    CONE_TRY(check_prec(precision));
+    Ctx c{w, precision, (cudaStream_t)stream};
+    CONE_TRY(ensure_tc(w, precision, c.s));
+    tc_set_scratch(w->tc, workspace, workspace_bytes);
+    return linear(c, x, K, M, W, bias, N, K, y, N, relu, residual, N);
+}
+
 extern "C" int cone_frame_scores(const float* ctx, int32_t v_dim, const int64_t* video_offsets, const int32_t* q_first,
                                  int32_t n_videos, int32_t max_video_frames, int32_t max_video_queries,
                                  const float* cls_norm, float* score_out, const int64_t* score_offsets, int precision,

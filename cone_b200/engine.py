@@ -189,6 +189,20 @@ class ConeEngine:
                                          _stream()), "cone_adapter")
         return out
 
+    def linear(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+               residual: Optional[torch.Tensor] = None, precision: Optional[str] = None) -> torch.Tensor:
+        """`F.linear` (+ residual, + ReLU) on rows through the library's GEMM path of the given precision."""
+        x = _need(x, torch.float32, "x")
+        weight = _need(weight, torch.float32, "weight")
+        M, K = x.shape
+        N = weight.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        prec = self.precision if precision is None else {"fp32": _lib.PREC_FP32, "tc": _lib.PREC_TC}[precision]
+        ws, nb = self._wsargs(M * K * 2 + 4096)
+        _lib.check(self.lib.cone_linear(self._handle, _ptr(x), _ptr(weight), _ptr(bias), M, N, K, int(relu),
+                                        _ptr(residual), _ptr(y), ws, nb, prec, _stream()), "cone_linear")
+        return y
+
     def video_prepare(self, frames: torch.Tensor, want_ctx=True, want_vidproj=True):
         """Stage 0 + per-frame `input_vid_proj` over concatenated frames [n, Dv] (raw features)."""
         frames = _need(frames, torch.float32, "frames")

@@ -88,6 +88,14 @@ int cone_video_prepare(const cone_weights* w, const float* frames_raw, int64_t n
 int cone_adapter(const cone_weights* w, const float* x, float* out, int64_t rows, int residual, void* workspace,
                  size_t workspace_bytes, int precision, void* stream);
 
+/* `torch.nn.functional.linear` on rows, the primitive every projection of the reference reduces to
+ * (cone/model.py:437-440, 458-465; nn.MultiheadAttention in/out projections):
+ * y[M,N] = act(x[M,K] * W[N,K]^T + bias (+ residual[M,N])).  W is any fp32 device matrix; with
+ * CONE_PREC_TC its fp16 copy is cached inside the weights handle. */
+int cone_linear(const cone_weights* w, const float* x, const float* W, const float* bias, int64_t M, int32_t N,
+                int32_t K, int relu, const float* residual, float* y, void* workspace, size_t workspace_bytes,
+                int precision, void* stream);
+
 /* ---- A3  stage 1 (cone/inference.py:276-299).
  * Frame scores `einsum('db,b->d')` (inference.py:284) for all queries of a set of videos in one
  * grouped GEMM: queries must be grouped by video.  ctx [n_frames_total, Dv]; video_offsets
