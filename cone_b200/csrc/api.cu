@@ -336,7 +336,9 @@ ProjBuffers plan_proj(Arena& a, int64_t rows, int din, int d) {
     b.ln_h1 = a.get<float>(rows * d);
     return b;
 }
-int input_proj(const Ctx& c, const char* name, const float* x, int64_t rows, int din, float* out, ProjBuffers& b) {
+int input_proj(const Ctx& cin, const char* name, const float* x, int64_t rows, int din, float* out, ProjBuffers& b) {
+    // per-frame / per-query work, a few GFLOP per movie: kept in fp32 in every mode (error budget)
+    const Ctx c{cin.w, CONE_PREC_FP32, cin.s};
     const int d = c.w->dims.hidden;
     const std::string p0 = std::string(name) + ".0", p1 = std::string(name) + ".1";
     CONE_TRY(layernorm_rows(x, nullptr, c.w->p(p0 + ".LayerNorm.weight"), c.w->p(p0 + ".LayerNorm.bias"), b.ln_in, rows,
@@ -360,25 +362,35 @@ int adapter_rows(const Ctx& c, const float* x, int64_t rows, float* hid, float* 
 struct CoreBuffers {
     int64_t B;
     int Lv, Lt, hw;
-    float *src, *srcpos, *qk, *v, *att, *tmp, *h;                      // [R, .]
+    float *src, *srcpos, *qk, *v, *att, *tmp, *h;                      // [R, .] fp32 (srcpos..h: fp32 mode only)
+    uint16_t *src16, *srcpos16, *qk16, *v16, *att16, *h16;            // [R, .] fp16 (tensor-core mode only)
     float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
     int64_t *vid_base, *txt_base;
     int32_t *vlen, *tlen, *pad_len, *qidx;
 };
 
-CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt) {
-    CoreBuffers b;
+CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, int prec) {
+    CoreBuffers b{};
     b.B = B; b.Lv = Lv; b.Lt = Lt;
     const int64_t R = B * (Lv + Lt), Q = B * c.num_queries;
     const int d = c.hidden;
     b.hw = c.ffn > 2 * d * c.dec_layers ? c.ffn : 2 * d * c.dec_layers;
     b.src = a.get<float>(R * d);
-    b.srcpos = a.get<float>(R * d);
-    b.qk = a.get<float>(R * 2 * d);
-    b.v = a.get<float>(R * d);
-    b.att = a.get<float>(R * d);
-    b.tmp = a.get<float>(R * d);
-    b.h = a.get<float>(R * b.hw);
+    if (prec == CONE_PREC_TC) {
+        b.src16 = a.get<uint16_t>(R * d);
+        b.srcpos16 = a.get<uint16_t>(R * d);
+        b.qk16 = a.get<uint16_t>(R * 2 * d);
+        b.v16 = a.get<uint16_t>(R * d);
+        b.att16 = a.get<uint16_t>(R * d);
+        b.h16 = a.get<uint16_t>(R * b.hw);
+    } else {
+        b.srcpos = a.get<float>(R * d);
+        b.qk = a.get<float>(R * 2 * d);
+        b.v = a.get<float>(R * d);
+        b.att = a.get<float>(R * d);
+        b.tmp = a.get<float>(R * d);
+        b.h = a.get<float>(R * b.hw);
+    }
     b.tgt = a.get<float>(Q * d);
     b.t2 = a.get<float>(Q * d);
     b.dqkin = a.get<float>(Q * d);
@@ -401,7 +413,8 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt) {
 
 // heads on hs [Q, d]: class logits / foreground probability and sigmoid spans (cone/model.py:112-115,
 // cone/inference.py:47,52)
-int heads(const Ctx& c, CoreBuffers& b, const float* hs, int64_t Q, float* logits, float* prob_fg, float* spans) {
+int heads(const Ctx& cin, CoreBuffers& b, const float* hs, int64_t Q, float* logits, float* prob_fg, float* spans) {
+    const Ctx c{cin.w, CONE_PREC_FP32, cin.s};  // 5 rows per window: fp32 in every mode
     const int d = c.w->dims.hidden;
     if (logits) CONE_TRY(rowdot_small(hs, d, c.w->p("class_embed.weight"), c.w->p("class_embed.bias"), logits, Q, 2, d, 0, c.s));
     if (prob_fg) CONE_TRY(rowdot_small(hs, d, c.w->p("class_embed.weight"), c.w->p("class_embed.bias"), prob_fg, Q, 2, d, 2, c.s));
@@ -421,32 +434,62 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
     const int d = dm.hidden, ff = dm.ffn, nq = dm.num_queries, H = dm.nheads;
     const int S = b.Lv + b.Lt;
     const int64_t R = b.B * S, Q = b.B * nq;
-    // encoder (cone/transformer.py:233-246)
-    for (int l = 0; l < dm.enc_layers; ++l) {
-        const std::string p = "transformer.encoder.layers." + std::to_string(l);
-        const float* inw = c.w->p(p + ".self_attn.in_proj_weight");
-        const float* inb = c.w->p(p + ".self_attn.in_proj_bias");
-        CONE_TRY(add_pos_rows(b.src, c.w->pos_table, b.vlen, b.srcpos, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
-        CONE_TRY(linear(c, b.srcpos, d, R, inw, inb, 2 * d, d, b.qk, 2 * d, 0));                 // q | k
-        CONE_TRY(linear(c, b.src, d, R, inw + (size_t)2 * d * d, inb + 2 * d, d, d, b.v, d, 0));  // v
-        CONE_TRY(enc_self_attention(b.qk, 2 * d, b.v, d, b.att, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H, c.s));
-        CONE_TRY(linear_named(c, b.att, d, R, p + ".self_attn.out_proj", d, d, b.tmp, d, 0, b.src, d));
-        CONE_TRY(layernorm_rows(b.tmp, nullptr, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), b.src, R, d, 1e-5f, c.s));
-        CONE_TRY(linear_named(c, b.src, d, R, p + ".linear1", ff, d, b.h, b.hw, 1));
-        CONE_TRY(linear_named(c, b.h, b.hw, R, p + ".linear2", d, ff, b.tmp, d, 0, b.src, d));
-        CONE_TRY(layernorm_rows(b.tmp, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.src, R, d, 1e-5f, c.s));
+    const int DL = dm.dec_layers;
+    const bool tc = (c.prec == CONE_PREC_TC);
+    if (!tc) {
+        // encoder (cone/transformer.py:233-246), fp32
+        for (int l = 0; l < dm.enc_layers; ++l) {
+            const std::string p = "transformer.encoder.layers." + std::to_string(l);
+            const float* inw = c.w->p(p + ".self_attn.in_proj_weight");
+            const float* inb = c.w->p(p + ".self_attn.in_proj_bias");
+            CONE_TRY(add_pos_rows(b.src, c.w->pos_table, b.vlen, b.srcpos, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+            CONE_TRY(linear(c, b.srcpos, d, R, inw, inb, 2 * d, d, b.qk, 2 * d, 0));                 // q | k
+            CONE_TRY(linear(c, b.src, d, R, inw + (size_t)2 * d * d, inb + 2 * d, d, d, b.v, d, 0));  // v
+            CONE_TRY(enc_self_attention(b.qk, 2 * d, b.v, d, b.att, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H, c.s));
+            CONE_TRY(linear_named(c, b.att, d, R, p + ".self_attn.out_proj", d, d, b.tmp, d, 0, b.src, d));
+            CONE_TRY(layernorm_rows(b.tmp, nullptr, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), b.src, R, d, 1e-5f, c.s));
+            CONE_TRY(linear_named(c, b.src, d, R, p + ".linear1", ff, d, b.h, b.hw, 1));
+            CONE_TRY(linear_named(c, b.h, b.hw, R, p + ".linear2", d, ff, b.tmp, d, 0, b.src, d));
+            CONE_TRY(layernorm_rows(b.tmp, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.src, R, d, 1e-5f, c.s));
+        }
+    } else {
+        // encoder on the tensor cores: fp16 GEMM operands produced by the previous kernel's epilogue, fp32
+        // residual stream, LayerNorm fused into the out_proj / linear2 epilogues (N = 256 = one accumulator row)
+        TcWeights* t = c.w->tc;
+        CONE_TRY(add_pos_rows_f16(b.src, c.w->pos_table, b.vlen, b.src16, b.srcpos16, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+        for (int l = 0; l < dm.enc_layers; ++l) {
+            const std::string p = "transformer.encoder.layers." + std::to_string(l);
+            const float* inw = c.w->p(p + ".self_attn.in_proj_weight");
+            const float* inb = c.w->p(p + ".self_attn.in_proj_bias");
+            CONE_TRY(tc_gemm_f16(t, b.srcpos16, d, R, inw, inb, 2 * d, d, nullptr, 0, b.qk16, 2 * d, 0, nullptr, 0, nullptr, nullptr, c.s));
+            CONE_TRY(tc_gemm_f16(t, b.src16, d, R, inw + (size_t)2 * d * d, inb + 2 * d, d, d, nullptr, 0, b.v16, d, 0, nullptr, 0, nullptr, nullptr, c.s));
+            CONE_TRY(enc_self_attention_f16(b.qk16, 2 * d, b.v16, d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H, c.s));
+            CONE_TRY(tc_gemm_f16(t, b.att16, d, R, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"),
+                                 d, d, b.src, d, b.src16, d, 0, b.src, d, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), c.s));
+            CONE_TRY(tc_gemm_f16(t, b.src16, d, R, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d, nullptr, 0,
+                                 b.h16, b.hw, 1, nullptr, 0, nullptr, nullptr, c.s));
+            CONE_TRY(tc_gemm_f16(t, b.h16, b.hw, R, c.w->p(p + ".linear2.weight"), c.w->p(p + ".linear2.bias"), d, ff, b.src, d,
+                                 b.src16, d, 0, b.src, d, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), c.s));
+            CONE_TRY(add_pos_rows_f16(b.src, c.w->pos_table, b.vlen, nullptr, b.srcpos16, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+        }
     }
     if (saliency) {  // saliency_proj(vid_mem) (cone/model.py:119-122), video rows only
         CONE_TRY(rowdot_small(b.src, d, c.w->p("saliency_proj.weight"), c.w->p("saliency_proj.bias"), saliency, b.B * b.Lv,
                               1, d, 0, c.s, b.Lv, S));
     }
     // decoder (cone/transformer.py:296-317, 117-146): memory K/V projections of all layers in two GEMMs
-    const int DL = dm.dec_layers;
     float* kdec = b.h;
-    float* vdec = b.h + (size_t)DL * d;
-    CONE_TRY(add_pos_rows(b.src, c.w->pos_table, b.vlen, b.srcpos, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
-    CONE_TRY(linear(c, b.srcpos, d, R, c.w->dec_kw, c.w->dec_kb, DL * d, d, kdec, b.hw, 0));
-    CONE_TRY(linear(c, b.src, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, vdec, b.hw, 0));
+    float* vdec = b.h ? b.h + (size_t)DL * d : nullptr;
+    uint16_t* kdec16 = b.h16;
+    uint16_t* vdec16 = b.h16 ? b.h16 + (size_t)DL * d : nullptr;
+    if (!tc) {
+        CONE_TRY(add_pos_rows(b.src, c.w->pos_table, b.vlen, b.srcpos, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+        CONE_TRY(linear(c, b.srcpos, d, R, c.w->dec_kw, c.w->dec_kb, DL * d, d, kdec, b.hw, 0));
+        CONE_TRY(linear(c, b.src, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, vdec, b.hw, 0));
+    } else {
+        CONE_TRY(tc_gemm_f16(c.w->tc, b.srcpos16, d, R, c.w->dec_kw, c.w->dec_kb, DL * d, d, nullptr, 0, kdec16, b.hw, 0, nullptr, 0, nullptr, nullptr, c.s));
+        CONE_TRY(tc_gemm_f16(c.w->tc, b.src16, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, nullptr, 0, vdec16, b.hw, 0, nullptr, 0, nullptr, nullptr, c.s));
+    }
     CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * Q * d, c.s));
     const float* qpos = c.w->p("query_embed.weight");
     for (int l = 0; l < DL; ++l) {
@@ -463,8 +506,13 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
         const float* cb = c.w->p(p + ".multihead_attn.in_proj_bias");
         CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Q, nq, d, c.s));
         CONE_TRY(linear(c, b.dqkin, d, Q, cw, cb, d, d, b.dq, d, 0));
-        CONE_TRY(dec_cross_attention(b.dq, d, kdec + (size_t)l * d, b.hw, vdec + (size_t)l * d, b.hw, b.datt, d, b.vlen,
-                                     b.tlen, b.B, nq, b.Lv, b.Lt, H, c.s));
+        if (!tc) {
+            CONE_TRY(dec_cross_attention(b.dq, d, kdec + (size_t)l * d, b.hw, vdec + (size_t)l * d, b.hw, b.datt, d, b.vlen,
+                                         b.tlen, b.B, nq, b.Lv, b.Lt, H, 0, c.s));
+        } else {
+            CONE_TRY(dec_cross_attention(b.dq, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt, d,
+                                         b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.s));
+        }
         CONE_TRY(linear_named(c, b.datt, d, Q, p + ".multihead_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
         CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.tgt, Q, d, 1e-5f, c.s));
         CONE_TRY(linear_named(c, b.tgt, d, Q, p + ".linear1", ff, d, b.dh, ff, 1));
@@ -566,7 +614,8 @@ extern "C" int cone_video_prepare(const cone_weights* w, const float* frames_raw
         if (ctx_out) {
             // host-side L2 norm of the dataset (dataloader:459), adapter + residual, no-eps norm (inference.py:255-257)
             CONE_TRY(l2norm_rows(x, xn, n, dm.v_dim, 1e-5f, c.s));
-            CONE_TRY(adapter_rows(c, xn, n, hid, ad, 1));
+            const Ctx c32{w, CONE_PREC_FP32, c.s};  // the window ranking must be bit-stable across precisions
+            CONE_TRY(adapter_rows(c32, xn, n, hid, ad, 1));
             CONE_TRY(l2norm_rows(ad, ctx_out + f0 * dm.v_dim, n, dm.v_dim, 0.f, c.s));
         }
         if (vidproj_out) CONE_TRY(input_proj(c, "input_vid_proj", x, n, dm.v_dim, vidproj_out + f0 * dm.hidden, pb));
@@ -621,10 +670,10 @@ extern "C" int cone_window_ranklist(const float* frame_score, const int64_t* sco
 }
 
 namespace {
-size_t ground_chunk_bytes(const cone_dims& dm, int64_t nqc, int topk, int Lv, int Lt) {
+size_t ground_chunk_bytes(const cone_dims& dm, int64_t nqc, int topk, int Lv, int Lt, int prec) {
     Arena a(nullptr, 0);
     const int64_t B = nqc * topk;
-    plan_core(a, dm, B, Lv, Lt);
+    plan_core(a, dm, B, Lv, Lt, prec);
     plan_match(a, dm, B, nqc);
     a.get<float>(nqc * Lt * dm.hidden);  // txtproj
     plan_proj(a, nqc * Lt, dm.t_dim, dm.hidden);
@@ -636,7 +685,7 @@ extern "C" size_t cone_workspace_bytes(const cone_dims* dims, int64_t n_windows,
     if (check_dims(dims) != CONE_OK) return 0;
     // dense forward: vid/txt projections of every row + core + matching
     Arena a(nullptr, 0);
-    plan_core(a, *dims, n_windows, lv, lt);
+    plan_core(a, *dims, n_windows, lv, lt, CONE_PREC_FP32);  // the fp32 plan is the larger one
     plan_match(a, *dims, n_windows, n_windows);
     a.get<float>(n_windows * lv * dims->hidden);
     a.get<float>(n_windows * lt * dims->hidden);
@@ -675,17 +724,17 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
 
     const size_t avail = workspace_bytes - head.used;
     int64_t nqc = n_queries;
-    while (nqc > 1 && ground_chunk_bytes(dm, nqc, topk, Lv, Lt) > avail) nqc = (nqc + 1) / 2;
-    if (ground_chunk_bytes(dm, nqc, topk, Lv, Lt) > avail) {
+    while (nqc > 1 && ground_chunk_bytes(dm, nqc, topk, Lv, Lt, precision) > avail) nqc = (nqc + 1) / 2;
+    if (ground_chunk_bytes(dm, nqc, topk, Lv, Lt, precision) > avail) {
         set_error("cone_ground_windows: workspace of %zu bytes cannot hold one query (%zu needed)", workspace_bytes,
-                  ground_chunk_bytes(dm, 1, topk, Lv, Lt) + head.used);
+                  ground_chunk_bytes(dm, 1, topk, Lv, Lt, precision) + head.used);
         return CONE_ERR_WORKSPACE;
     }
     for (int64_t q0 = 0; q0 < n_queries; q0 += nqc) {
         const int64_t n = (n_queries - q0) < nqc ? (n_queries - q0) : nqc;
         const int64_t B = n * topk;
         Arena a((char*)workspace + head.used, avail);
-        CoreBuffers cb = plan_core(a, dm, B, Lv, Lt);
+        CoreBuffers cb = plan_core(a, dm, B, Lv, Lt, precision);
         MatchBuffers mb = plan_match(a, dm, B, n);
         float* txtproj = a.get<float>(n * Lt * dm.hidden);
         ProjBuffers pb = plan_proj(a, n * Lt, dm.t_dim, dm.hidden);
@@ -715,7 +764,7 @@ extern "C" int cone_forward(const cone_weights* w, const float* src_txt, const i
     Ctx c{w, precision, (cudaStream_t)stream};
     CONE_TRY(ensure_tc(w, precision, c.s));
     Arena a(workspace, workspace_bytes);
-    CoreBuffers cb = plan_core(a, dm, B, Lv, Lt);
+    CoreBuffers cb = plan_core(a, dm, B, Lv, Lt, precision);
     float* vidproj = a.get<float>((int64_t)B * Lv * dm.hidden);
     float* txtproj = a.get<float>((int64_t)B * Lt * dm.hidden);
     ProjBuffers pv = plan_proj(a, (int64_t)B * Lv, dm.v_dim, dm.hidden);

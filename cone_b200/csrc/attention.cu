@@ -2,6 +2,7 @@
 // Math follows torch.nn.functional.multi_head_attention_forward as called at cone/transformer.py:239,
 // 304, 308: q scaled by sqrt(1/head_dim) BEFORE the dot product, additive -inf key-padding mask,
 // softmax over keys, then P.V.  One CTA per (window, head); K and V of the head live in shared memory.
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "kernels.h"
@@ -125,9 +126,33 @@ __global__ void dec_self_attention_kernel(const float* __restrict__ qk, int64_t 
 }
 
 // decoder cross-attention: one warp per (window, head); nq <= 8 queries against S memory keys
+__device__ __forceinline__ void load_head_row(const float* p, float* out) {
+#pragma unroll
+    for (int c = 0; c < HD / 4; ++c) {
+        const float4 t = reinterpret_cast<const float4*>(p)[c];
+        out[4 * c] = t.x; out[4 * c + 1] = t.y; out[4 * c + 2] = t.z; out[4 * c + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void load_head_row(const __half* p, float* out) {
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+        const uint4 t = reinterpret_cast<const uint4*>(p)[c];
+        const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            out[8 * c + 2 * e] = f.x;
+            out[8 * c + 2 * e + 1] = f.y;
+        }
+    }
+}
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
+
+template <typename KV>
 __global__ void __launch_bounds__(128)
-dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
-                           const float* __restrict__ v, int64_t ldv, float* __restrict__ o, int64_t ldo,
+dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const KV* __restrict__ k, int64_t ldk,
+                           const KV* __restrict__ v, int64_t ldv, float* __restrict__ o, int64_t ldo,
                            const int32_t* __restrict__ vlen, const int32_t* __restrict__ tlen, int64_t B, int nq, int Lv,
                            int Lt, int nheads) {
     extern __shared__ float smem[];
@@ -150,12 +175,7 @@ dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const float
     for (int j = lane; j < S; j += 32) {
         const bool ok = key_valid(j, Lv, vl, tl);
         float kr[HD];
-        const float4* kp = reinterpret_cast<const float4*>(k + (b * S + j) * ldk + h * HD);
-#pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-            const float4 t = kp[c];
-            kr[4 * c] = t.x; kr[4 * c + 1] = t.y; kr[4 * c + 2] = t.z; kr[4 * c + 3] = t.w;
-        }
+        load_head_row(k + (b * S + j) * ldk + h * HD, kr);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (i < nq) {
@@ -192,7 +212,7 @@ dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const float
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     for (int j = 0; j < S; ++j) {
-        const float vj = v[(b * S + j) * ldv + h * HD + lane];
+        const float vj = to_f32(v[(b * S + j) * ldv + h * HD + lane]);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if (i < nq) acc[i] = fmaf(Ps[i * S + j], vj, acc[i]);
@@ -200,6 +220,159 @@ dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const float
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         if (i < nq) o[(b * nq + i) * ldo + h * HD + lane] = acc[i] / sum[i];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core encoder self-attention (CONE_PREC_TC): fp16 Q/K/V, fp32 scores and softmax, fp16 output.
+// One CTA per (window, head); Q, K and V^T of the head in shared memory (padded rows: conflict-free fragment
+// loads); each warp owns 16-query-row blocks and keeps the whole score row block (16 x S) in registers:
+// S = Q.K^T with mma.sync.m16n8k16, masked softmax on the accumulator fragments, P re-used in place as the
+// A operand of P.V (FlashAttention-2 register layout).  S <= 8*NB keys.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {
+    __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int ATT_WARPS = 5;
+constexpr int QK_PAD = 40;  // halves per Q/K row in smem (32 + 8): 20-word stride -> conflict-free 32-bit fragment loads
+
+template <int NB>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __half* __restrict__ v, int64_t ldv,
+                         __half* __restrict__ o, int64_t ldo, const int32_t* __restrict__ vlen,
+                         const int32_t* __restrict__ tlen, int Lv, int Lt, int d_model) {
+    extern __shared__ __align__(16) unsigned char att_smem[];
+    const int S = Lv + Lt;
+    const int Sp = (S + 15) & ~15;
+    const int vt_ld = Sp + 8;  // halves per V^T row
+    __half* Qs = reinterpret_cast<__half*>(att_smem);  // [Sp][QK_PAD]
+    __half* Ks = Qs + Sp * QK_PAD;                      // [Sp][QK_PAD]
+    __half* Vt = Ks + Sp * QK_PAD;                      // [HD][vt_ld]
+    const int64_t b = blockIdx.x;
+    const int h = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int vl = vlen[b], tl = tlen[b];
+    const int64_t row0 = b * S;
+
+    // cooperative load: 4 x 16-byte chunks per row for each of Q, K, V; V is transposed on the way in
+    for (int i = threadIdx.x; i < Sp * 4; i += blockDim.x) {
+        const int r = i >> 2, c = i & 3;
+        uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+        if (r < S) {
+            const __half* qrow = qk + (row0 + r) * ldqk + h * HD + c * 8;
+            q4 = *reinterpret_cast<const uint4*>(qrow);
+            k4 = *reinterpret_cast<const uint4*>(qrow + d_model);
+            v4 = *reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + h * HD + c * 8);
+        }
+        *reinterpret_cast<uint4*>(Qs + r * QK_PAD + c * 8) = q4;
+        *reinterpret_cast<uint4*>(Ks + r * QK_PAD + c * 8) = k4;
+        const __half* vh = reinterpret_cast<const __half*>(&v4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Vt[(c * 8 + e) * vt_ld + r] = vh[e];
+    }
+    __syncthreads();
+
+    const int nkb = Sp >> 3;  // key blocks of 8 (even)
+    const int nrb = Sp >> 4;  // query row blocks of 16
+    const int g = lane >> 2, t4 = lane & 3;
+    const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // softmax scale * log2(e)
+    for (int rb = warp; rb < nrb; rb += ATT_WARPS) {
+        const int r_lo = rb * 16 + g, r_hi = r_lo + 8;
+        uint32_t aq[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            aq[ks][0] = *reinterpret_cast<const uint32_t*>(Qs + r_lo * QK_PAD + ks * 16 + t4 * 2);
+            aq[ks][1] = *reinterpret_cast<const uint32_t*>(Qs + r_hi * QK_PAD + ks * 16 + t4 * 2);
+            aq[ks][2] = *reinterpret_cast<const uint32_t*>(Qs + r_lo * QK_PAD + ks * 16 + 8 + t4 * 2);
+            aq[ks][3] = *reinterpret_cast<const uint32_t*>(Qs + r_hi * QK_PAD + ks * 16 + 8 + t4 * 2);
+        }
+        float sc[NB][4];
+        float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F;
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            sc[jb][0] = sc[jb][1] = sc[jb][2] = sc[jb][3] = 0.f;
+            if (jb < nkb) {
+                const __half* krow = Ks + (jb * 8 + g) * QK_PAD + t4 * 2;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+                    mma_16816(sc[jb], aq[ks], b0, b1);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int key = jb * 8 + t4 * 2 + e;
+                    const bool ok = key < S && key_valid(key, Lv, vl, tl);
+                    sc[jb][e] = ok ? sc[jb][e] * sl2 : -CUDART_INF_F;
+                    sc[jb][2 + e] = ok ? sc[jb][2 + e] * sl2 : -CUDART_INF_F;
+                    m_lo = fmaxf(m_lo, sc[jb][e]);
+                    m_hi = fmaxf(m_hi, sc[jb][2 + e]);
+                }
+            }
+        }
+        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+        float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            if (jb < nkb) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float p0 = exp2f(sc[jb][e] - m_lo);      // exp2(-inf) = 0 for masked keys
+                    const float p1 = exp2f(sc[jb][2 + e] - m_hi);
+                    sc[jb][e] = p0;
+                    sc[jb][2 + e] = p1;
+                    s_lo += p0;
+                    s_hi += p1;
+                }
+            }
+        }
+        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+
+        float out[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) out[nb][0] = out[nb][1] = out[nb][2] = out[nb][3] = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < NB / 2; ++kb) {
+            if (kb * 2 < nkb) {
+                uint32_t ap[4];
+                ap[0] = pack_half2(sc[2 * kb][0], sc[2 * kb][1]);
+                ap[1] = pack_half2(sc[2 * kb][2], sc[2 * kb][3]);
+                ap[2] = pack_half2(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
+                ap[3] = pack_half2(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const __half* vrow = Vt + (nb * 8 + g) * vt_ld + kb * 16 + t4 * 2;
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + 8);
+                    mma_16816(out[nb], ap, b0, b1);
+                }
+            }
+        }
+        const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            if (r_lo < S)
+                *reinterpret_cast<uint32_t*>(o + (row0 + r_lo) * ldo + h * HD + nb * 8 + t4 * 2) =
+                    pack_half2(out[nb][0] * i_lo, out[nb][1] * i_lo);
+            if (r_hi < S)
+                *reinterpret_cast<uint32_t*>(o + (row0 + r_hi) * ldo + h * HD + nb * 8 + t4 * 2) =
+                    pack_half2(out[nb][2] * i_hi, out[nb][3] * i_hi);
+        }
+    }
 }
 
 }  // namespace
@@ -236,19 +409,56 @@ int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
     return CONE_OK;
 }
 
-int dec_cross_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
-                        int Lt, int nheads, cudaStream_t s) {
+                        int Lt, int nheads, int kv_f16, cudaStream_t s) {
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
     CONE_REQUIRE(nq <= 8 && S <= MAX_S, "dec_cross_attention: unsupported nq=%d S=%d", nq, S);
-    CONE_REQUIRE((ldk & 3) == 0, "dec_cross_attention: ldk must be a multiple of 4");
+    CONE_REQUIRE((ldk & 7) == 0, "dec_cross_attention: ldk must be a multiple of 8");
     const int warps = 4;
     const size_t smem = sizeof(float) * warps * (8 * HD + 8 * (size_t)S);
     ProfScope ps(s, P_DEC_ATTN, 4.0 * (double)B * nheads * nq * S * HD, 8.0 * (double)B * S * nheads * HD);
-    dec_cross_attention_kernel<<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
-        q, ldq, k, ldk, v, ldv, o, ldo, vlen, tlen, B, nq, Lv, Lt, nheads);
+    if (kv_f16) {
+        dec_cross_attention_kernel<__half><<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
+            q, ldq, static_cast<const __half*>(k), ldk, static_cast<const __half*>(v), ldv, o, ldo, vlen, tlen, B, nq, Lv,
+            Lt, nheads);
+    } else {
+        dec_cross_attention_kernel<float><<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
+            q, ldq, static_cast<const float*>(k), ldk, static_cast<const float*>(v), ldv, o, ldo, vlen, tlen, B, nq, Lv, Lt,
+            nheads);
+    }
     CONE_LAUNCH_CHECK("dec_cross_attention");
+    return CONE_OK;
+}
+
+int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                           const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
+                           cudaStream_t s) {
+    if (B == 0) return CONE_OK;
+    const int S = Lv + Lt;
+    CONE_REQUIRE(S <= MAX_S, "enc_self_attention_f16: window of %d rows exceeds %d", S, MAX_S);
+    CONE_REQUIRE((ldqk % 8) == 0 && (ldv % 8) == 0 && (ldo % 2) == 0, "enc_self_attention_f16: leading dims must keep 16-byte rows");
+    const int Sp = (S + 15) & ~15;
+    const size_t smem = sizeof(__half) * ((size_t)2 * Sp * QK_PAD + (size_t)HD * (Sp + 8));
+    dim3 grid((unsigned)B, (unsigned)nheads);
+    ProfScope ps(s, P_ENC_ATTN, 4.0 * (double)B * nheads * S * S * HD, 8.0 * (double)B * S * nheads * HD);
+    const __half* qk16 = static_cast<const __half*>(qk);
+    const __half* v16 = static_cast<const __half*>(v);
+    __half* o16 = static_cast<__half*>(o);
+    if (Sp <= 160) {
+        enc_attention_f16_kernel<20><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt,
+                                                                      nheads * HD);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            CONE_CUDA(cudaFuncSetAttribute(enc_attention_f16_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr = true;
+        }
+        enc_attention_f16_kernel<32><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt,
+                                                                      nheads * HD);
+    }
+    CONE_LAUNCH_CHECK("enc_self_attention_f16");
     return CONE_OK;
 }
 

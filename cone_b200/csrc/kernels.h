@@ -44,6 +44,9 @@ int gather_window_rows(const float* vidproj, int64_t n_vid_rows, const int64_t* 
 // out[b*S + r] = src[b*S + r] + (r < Lv ? pos[vlen[b]][r] : 0)
 int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, float* out, int64_t B, int Lv, int Lt,
                  int d, int table_lv, cudaStream_t s);
+// fp16 operands for the tensor-core path: plain16 = fp16(src), pos16 = fp16(src + pos); either may be null
+int add_pos_rows_f16(const float* src, const float* pos_table, const int32_t* vlen, uint16_t* plain16, uint16_t* pos16,
+                     int64_t B, int Lv, int Lt, int d, int table_lv, cudaStream_t s);
 // out[row] = x[row] + table[row % period]   (x may be null = zeros)
 int add_row_table(const float* x, const float* table, float* out, int64_t rows, int period, int d, cudaStream_t s);
 int fill_window_desc_dense(int64_t* vid_base, int64_t* txt_base, int32_t* qidx, int64_t B, int Lv, int Lt,
@@ -55,13 +58,18 @@ int fill_i32(int32_t* p, int64_t n, int32_t value, cudaStream_t s);
 int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo,
                        const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
                        cudaStream_t s);
+// tensor-core variant: fp16 q|k [R, ldqk], v, o (passed as void* to keep cuda_fp16.h out of this header)
+int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                           const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
+                           cudaStream_t s);
 // decoder self-attention over nq slots (no mask)
 int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo, int64_t B,
                        int nq, int nheads, cudaStream_t s);
 // decoder cross-attention: nq queries x S memory keys with key-padding mask
-int dec_cross_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+// k / v are fp32 (kv_f16 = 0) or fp16 (kv_f16 = 1) with leading dims in elements
+int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
-                        int Lt, int nheads, cudaStream_t s);
+                        int Lt, int nheads, int kv_f16, cudaStream_t s);
 
 // ---------------------------------------------------------------- prefilter.cu
 int window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count, int n_queries,

@@ -1,5 +1,7 @@
 // Row-wise fp32 kernels: LayerNorm (+residual), L2 normalisation, sine position table, window row gather.
 // All are HBM/L2-bound: one warp per row, float4 accesses, grid sized from the row count.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace cone {
@@ -140,6 +142,39 @@ __global__ void add_pos_rows_kernel(const float* __restrict__ src, const float* 
     }
 }
 
+// fp16 GEMM operands from the fp32 residual stream: plain16 = fp16(src), pos16 = fp16(src + pos) (either may be null)
+__global__ void add_pos_rows_f16_kernel(const float* __restrict__ src, const float* __restrict__ pos_table,
+                                        const int32_t* __restrict__ vlen, __half* __restrict__ plain16,
+                                        __half* __restrict__ pos16, int64_t B, int Lv, int Lt, int d4, int table_lv) {
+    const int S = Lv + Lt;
+    const int64_t total = B * S * d4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % d4);
+        const int64_t row = i / d4;
+        const int r = (int)(row % S);
+        const int64_t b = row / S;
+        float4 v = reinterpret_cast<const float4*>(src)[i];
+        if (plain16) {
+            __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            reinterpret_cast<uint2*>(plain16)[i] = u;
+        }
+        if (pos16) {
+            if (r < Lv) {
+                const float4 p = __ldg(reinterpret_cast<const float4*>(pos_table) + ((int64_t)vlen[b] * table_lv + r) * d4 + c);
+                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            }
+            __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            reinterpret_cast<uint2*>(pos16)[i] = u;
+        }
+    }
+}
+
 __global__ void add_row_table_kernel(const float* __restrict__ x, const float* __restrict__ table,
                                      float* __restrict__ out, int64_t rows, int period, int d4) {
     const int64_t total = rows * d4;
@@ -220,6 +255,16 @@ int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, 
     add_pos_rows_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(src, pos_table, vlen, out, B, Lv, Lt,
                                                                              d / 4, table_lv);
     CONE_LAUNCH_CHECK("add_pos_rows");
+    return CONE_OK;
+}
+
+int add_pos_rows_f16(const float* src, const float* pos_table, const int32_t* vlen, uint16_t* plain16, uint16_t* pos16,
+                     int64_t B, int Lv, int Lt, int d, int table_lv, cudaStream_t s) {
+    if (B == 0) return CONE_OK;
+    ProfScope ps(s, P_ROWOPS, 0.0, (4.0 + (plain16 ? 2.0 : 0.0) + (pos16 ? 2.0 : 0.0)) * (double)B * (Lv + Lt) * d);
+    add_pos_rows_f16_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(
+        src, pos_table, vlen, reinterpret_cast<__half*>(plain16), reinterpret_cast<__half*>(pos16), B, Lv, Lt, d / 4, table_lv);
+    CONE_LAUNCH_CHECK("add_pos_rows_f16");
     return CONE_OK;
 }
 

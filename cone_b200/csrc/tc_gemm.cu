@@ -440,7 +440,7 @@ static int get_w16(TcWeights* t, const float* W, int N, int K, cudaStream_t s, c
     return CONE_OK;
 }
 
-int tc_gemm_f16(TcWeights* t, const __half* A16, int64_t lda, int64_t M, const float* W, const float* b, int N, int K,
+static int tc_gemm_f16_impl(TcWeights* t, const __half* A16, int64_t lda, int64_t M, const float* W, const float* b, int N, int K,
                 float* C32, int64_t ldc32, __half* C16, int64_t ldc16, int relu, const float* R, int64_t ldr,
                 const float* ln_g, const float* ln_b, cudaStream_t s) {
     CONE_REQUIRE(t != nullptr, "tc_gemm: tensor-core weights not initialised");
@@ -488,7 +488,14 @@ int tc_gemm(TcWeights* t, const float* x, int64_t ldx, int64_t M, const float* W
                  "tc_gemm: operand staging needs %zu bytes of workspace, %zu available", need, t->scratch_bytes);
     __half* a16 = reinterpret_cast<__half*>(t->scratch);
     CONE_TRY(f32_to_f16(x, ldx, a16, M, K, s));
-    return tc_gemm_f16(t, a16, K, M, W, b, N, K, y, ldy, nullptr, 0, relu, R, ldr, nullptr, nullptr, s);
+    return tc_gemm_f16_impl(t, a16, K, M, W, b, N, K, y, ldy, nullptr, 0, relu, R, ldr, nullptr, nullptr, s);
+}
+
+int tc_gemm_f16(TcWeights* t, const uint16_t* A16, int64_t lda, int64_t M, const float* W, const float* b, int N, int K,
+                float* C32, int64_t ldc32, uint16_t* C16, int64_t ldc16, int relu, const float* R, int64_t ldr,
+                const float* ln_g, const float* ln_b, cudaStream_t s) {
+    return tc_gemm_f16_impl(t, reinterpret_cast<const __half*>(A16), lda, M, W, b, N, K, C32, ldc32,
+                            reinterpret_cast<__half*>(C16), ldc16, relu, R, ldr, ln_g, ln_b, s);
 }
 
 }  // namespace cone

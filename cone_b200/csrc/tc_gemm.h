@@ -16,4 +16,10 @@ bool tc_gemm_supported(int64_t M, int N, int K);
 int tc_gemm(TcWeights* t, const float* x, int64_t ldx, int64_t M, const float* W, const float* b, int N, int K, float* y,
             int64_t ldy, int relu, const float* R, int64_t ldr, cudaStream_t s);
 
+// fp16 operand already in memory (row pitch lda halves); optional fp32 (C32) and fp16 (C16) outputs; optional fused
+// residual (R fp32) and LayerNorm over the row (ln_g/ln_b non-null requires N == 256).  fp16 pointers as uint16_t*.
+int tc_gemm_f16(TcWeights* t, const uint16_t* A16, int64_t lda, int64_t M, const float* W, const float* b, int N, int K,
+                float* C32, int64_t ldc32, uint16_t* C16, int64_t ldc16, int relu, const float* R, int64_t ldr,
+                const float* ln_g, const float* ln_b, cudaStream_t s);
+
 }  // namespace cone
