@@ -97,7 +97,12 @@ struct cone_weights {
     std::map<std::string, size_t> off;
     float* derived = nullptr;  // dec_kw | dec_kb | dec_vw | dec_vb | pos_table
     float *dec_kw = nullptr, *dec_kb = nullptr, *dec_vw = nullptr, *dec_vb = nullptr, *pos_table = nullptr;
-    TcWeights* tc = nullptr;  // bf16 copies + TMA descriptors for the tensor-core path (lazy)
+    TcWeights* tc = nullptr;  // fp16 copies + TMA descriptors for the tensor-core path (lazy)
+    // tensor-core path only (lazy): position embedding pushed through the q|k projections of every encoder layer
+    // [enc_layers][(max_v_l+1)*max_v_l][2d] and through the decoder cross-attention K projections [..][DL*d]
+    float* pos_proj = nullptr;
+    std::vector<float*> pos_qk;
+    float* pos_kdec = nullptr;
     const float* p(const std::string& name) const { return blob + off.at(name); }
 };
 
@@ -194,6 +199,7 @@ extern "C" size_t cone_weights_expected_floats(const cone_dims* dims) {
 extern "C" void cone_weights_destroy(cone_weights* w) {
     if (!w) return;
     if (w->tc) tc_weights_destroy(w->tc);
+    if (w->pos_proj) cudaFree(w->pos_proj);
     if (w->blob) cudaFree(w->blob);
     if (w->derived) cudaFree(w->derived);
     delete w;
@@ -237,10 +243,10 @@ extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, cons
     const int DL = dims->dec_layers;
     // derived: concatenated cross-attention K / V projections of all decoder layers (memory is shared)
     std::vector<float> der((size_t)DL * d * d * 2 + (size_t)DL * d * 2);
-    float* kw = der.data();
-    float* kb = kw + (size_t)DL * d * d;
-    float* vw = kb + (size_t)DL * d;
-    float* vb = vw + (size_t)DL * d * d;
+    float* kw = der.data();  // layout kw | vw | kb | vb: [K-proj rows; V-proj rows] form one [2*DL*d, d] weight
+    float* vw = kw + (size_t)DL * d * d;
+    float* kb = vw + (size_t)DL * d * d;
+    float* vb = kb + (size_t)DL * d;
     for (int i = 0; i < DL; ++i) {
         const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".multihead_attn";
         const float* inw = staged.data() + w->off.at(p + ".in_proj_weight");
@@ -262,9 +268,9 @@ extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, cons
         return CONE_ERR_CUDA;
     }
     w->dec_kw = w->derived;
-    w->dec_kb = w->dec_kw + (size_t)DL * d * d;
-    w->dec_vw = w->dec_kb + (size_t)DL * d;
-    w->dec_vb = w->dec_vw + (size_t)DL * d * d;
+    w->dec_vw = w->dec_kw + (size_t)DL * d * d;
+    w->dec_kb = w->dec_vw + (size_t)DL * d * d;
+    w->dec_vb = w->dec_kb + (size_t)DL * d;
     w->pos_table = w->derived + der.size();
     int r = build_pos_table(w->pos_table, dims->max_v_l, (int)d, s);
     if (r != CONE_OK) {
@@ -363,7 +369,7 @@ struct CoreBuffers {
     int64_t B;
     int Lv, Lt, hw;
     float *src, *srcpos, *qk, *v, *att, *tmp, *h;                      // [R, .] fp32 (srcpos..h: fp32 mode only)
-    uint16_t *src16, *srcpos16, *qk16, *v16, *att16, *h16;            // [R, .] fp16 (tensor-core mode only)
+    uint16_t *src16, *qkv16, *att16, *h16;                             // [R, .] fp16 (tensor-core mode only)
     float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
     int64_t *vid_base, *txt_base;
     int32_t *vlen, *tlen, *pad_len, *qidx;
@@ -378,9 +384,7 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, i
     b.src = a.get<float>(R * d);
     if (prec == CONE_PREC_TC) {
         b.src16 = a.get<uint16_t>(R * d);
-        b.srcpos16 = a.get<uint16_t>(R * d);
-        b.qk16 = a.get<uint16_t>(R * 2 * d);
-        b.v16 = a.get<uint16_t>(R * d);
+        b.qkv16 = a.get<uint16_t>(R * 3 * d);
         b.att16 = a.get<uint16_t>(R * d);
         b.h16 = a.get<uint16_t>(R * b.hw);
     } else {
@@ -453,31 +457,46 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
             CONE_TRY(layernorm_rows(b.tmp, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.src, R, d, 1e-5f, c.s));
         }
     } else {
-        // encoder on the tensor cores: fp16 GEMM operands produced by the previous kernel's epilogue, fp32
-        // residual stream, LayerNorm fused into the out_proj / linear2 epilogues (N = 256 = one accumulator row)
+        // encoder on the tensor cores.  Everything between two GEMMs is fp16 and is produced by the previous
+        // kernel's epilogue: b.src16 was filled by the fp16 gather; the residual stream is the fp16 LayerNorm
+        // output (no accuracy cost); LayerNorm is fused into the out_proj / linear2 epilogues (N = 256
+        // = one accumulator row per thread); q, k and v come from ONE GEMM over the packed in_proj (N = 768)
+        // because the position term of q and k is added inside the attention kernel from a per-layer table.
         TcWeights* t = c.w->tc;
-        CONE_TRY(add_pos_rows_f16(b.src, c.w->pos_table, b.vlen, b.src16, b.srcpos16, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+        auto G = [&](const uint16_t* A, int64_t lda, const float* W, const float* bias, int N, int K) {
+            TcGemmArgs g;
+            g.A16 = A; g.lda = lda; g.M = R; g.W = W; g.bias = bias; g.N = N; g.K = K;
+            return g;
+        };
         for (int l = 0; l < dm.enc_layers; ++l) {
             const std::string p = "transformer.encoder.layers." + std::to_string(l);
-            const float* inw = c.w->p(p + ".self_attn.in_proj_weight");
-            const float* inb = c.w->p(p + ".self_attn.in_proj_bias");
-            CONE_TRY(tc_gemm_f16(t, b.srcpos16, d, R, inw, inb, 2 * d, d, nullptr, 0, b.qk16, 2 * d, 0, nullptr, 0, nullptr, nullptr, c.s));
-            CONE_TRY(tc_gemm_f16(t, b.src16, d, R, inw + (size_t)2 * d * d, inb + 2 * d, d, d, nullptr, 0, b.v16, d, 0, nullptr, 0, nullptr, nullptr, c.s));
-            CONE_TRY(enc_self_attention_f16(b.qk16, 2 * d, b.v16, d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H, c.s));
-            CONE_TRY(tc_gemm_f16(t, b.att16, d, R, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"),
-                                 d, d, b.src, d, b.src16, d, 0, b.src, d, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), c.s));
-            CONE_TRY(tc_gemm_f16(t, b.src16, d, R, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d, nullptr, 0,
-                                 b.h16, b.hw, 1, nullptr, 0, nullptr, nullptr, c.s));
-            CONE_TRY(tc_gemm_f16(t, b.h16, b.hw, R, c.w->p(p + ".linear2.weight"), c.w->p(p + ".linear2.bias"), d, ff, b.src, d,
-                                 b.src16, d, 0, b.src, d, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), c.s));
-            CONE_TRY(add_pos_rows_f16(b.src, c.w->pos_table, b.vlen, nullptr, b.srcpos16, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
+            TcGemmArgs g = G(b.src16, d, c.w->p(p + ".self_attn.in_proj_weight"), c.w->p(p + ".self_attn.in_proj_bias"), 3 * d, d);
+            g.C16 = b.qkv16; g.ldc16 = 3 * d;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            CONE_TRY(enc_self_attention_f16(b.qkv16, 3 * d, b.qkv16 + 2 * d, 3 * d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv,
+                                            b.Lt, H, c.w->pos_qk[l], dm.max_v_l, c.s));
+            g = G(b.att16, d, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"), d, d);
+            g.R16 = b.src16; g.ldr16 = d;
+            g.ln_g = c.w->p(p + ".norm1.weight"); g.ln_b = c.w->p(p + ".norm1.bias");
+            g.C16 = b.src16; g.ldc16 = d;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            g = G(b.src16, d, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d);
+            g.relu = 1; g.C16 = b.h16; g.ldc16 = b.hw;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            g = G(b.h16, b.hw, c.w->p(p + ".linear2.weight"), c.w->p(p + ".linear2.bias"), d, ff);
+            g.R16 = b.src16; g.ldr16 = d;
+            g.ln_g = c.w->p(p + ".norm2.weight"); g.ln_b = c.w->p(p + ".norm2.bias");
+            g.C16 = b.src16; g.ldc16 = d;
+            if (saliency && l == dm.enc_layers - 1) { g.C32 = b.src; g.ldc32 = d; }  // fp32 memory for saliency_proj
+            CONE_TRY(tc_gemm_run(t, g, c.s));
         }
     }
     if (saliency) {  // saliency_proj(vid_mem) (cone/model.py:119-122), video rows only
         CONE_TRY(rowdot_small(b.src, d, c.w->p("saliency_proj.weight"), c.w->p("saliency_proj.bias"), saliency, b.B * b.Lv,
                               1, d, 0, c.s, b.Lv, S));
     }
-    // decoder (cone/transformer.py:296-317, 117-146): memory K/V projections of all layers in two GEMMs
+    // decoder (cone/transformer.py:296-317, 117-146): the memory K and V projections of ALL layers in one GEMM
+    // (weights concatenated at load time: columns [0, DL*d) = K of layer 0.., [DL*d, 2*DL*d) = V of layer 0..)
     float* kdec = b.h;
     float* vdec = b.h ? b.h + (size_t)DL * d : nullptr;
     uint16_t* kdec16 = b.h16;
@@ -487,8 +506,10 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
         CONE_TRY(linear(c, b.srcpos, d, R, c.w->dec_kw, c.w->dec_kb, DL * d, d, kdec, b.hw, 0));
         CONE_TRY(linear(c, b.src, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, vdec, b.hw, 0));
     } else {
-        CONE_TRY(tc_gemm_f16(c.w->tc, b.srcpos16, d, R, c.w->dec_kw, c.w->dec_kb, DL * d, d, nullptr, 0, kdec16, b.hw, 0, nullptr, 0, nullptr, nullptr, c.s));
-        CONE_TRY(tc_gemm_f16(c.w->tc, b.src16, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, nullptr, 0, vdec16, b.hw, 0, nullptr, 0, nullptr, nullptr, c.s));
+        TcGemmArgs g;  // k (without its position term: added in the cross-attention kernel) | v
+        g.A16 = b.src16; g.lda = d; g.M = R; g.W = c.w->dec_kw; g.bias = c.w->dec_kb; g.N = 2 * DL * d; g.K = d;
+        g.C16 = b.h16; g.ldc16 = b.hw;
+        CONE_TRY(tc_gemm_run(c.w->tc, g, c.s));
     }
     CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * Q * d, c.s));
     const float* qpos = c.w->p("query_embed.weight");
@@ -508,10 +529,11 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
         CONE_TRY(linear(c, b.dqkin, d, Q, cw, cb, d, d, b.dq, d, 0));
         if (!tc) {
             CONE_TRY(dec_cross_attention(b.dq, d, kdec + (size_t)l * d, b.hw, vdec + (size_t)l * d, b.hw, b.datt, d, b.vlen,
-                                         b.tlen, b.B, nq, b.Lv, b.Lt, H, 0, c.s));
+                                         b.tlen, b.B, nq, b.Lv, b.Lt, H, 0, nullptr, 0, 0, c.s));
         } else {
             CONE_TRY(dec_cross_attention(b.dq, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt, d,
-                                         b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.s));
+                                         b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.w->pos_kdec + (size_t)l * d,
+                                         (int64_t)DL * d, dm.max_v_l, c.s));
         }
         CONE_TRY(linear_named(c, b.datt, d, Q, p + ".multihead_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
         CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.tgt, Q, d, 1e-5f, c.s));
@@ -560,6 +582,28 @@ int ensure_tc(const cone_weights* w, int prec, cudaStream_t s) {
     if (prec != CONE_PREC_TC) return CONE_OK;
     cone_weights* mw = const_cast<cone_weights*>(w);
     if (mw->tc == nullptr) CONE_TRY(tc_weights_create(&mw->tc, s));
+    if (mw->pos_proj == nullptr) {
+        // pos . [Wq; Wk]^T per encoder layer and pos . Wk^T per decoder layer, for every (valid length, row): fp32
+        const cone_dims& dm = w->dims;
+        const size_t d = dm.hidden, rows = (size_t)(dm.max_v_l + 1) * dm.max_v_l;
+        const size_t per_enc = rows * 2 * d, dec = rows * dm.dec_layers * d;
+        CONE_CUDA(cudaMalloc(&mw->pos_proj, sizeof(float) * (per_enc * dm.enc_layers + dec)));
+        mw->pos_qk.clear();
+        for (int l = 0; l < dm.enc_layers; ++l) {
+            float* out = mw->pos_proj + per_enc * l;
+            GemmParams g;
+            g.A = w->pos_table; g.lda = d;
+            g.W = w->p("transformer.encoder.layers." + std::to_string(l) + ".self_attn.in_proj_weight"); g.ldw = d;
+            g.C = out; g.ldc = 2 * d; g.M = rows; g.N = 2 * d; g.K = d;
+            CONE_TRY(sgemm_nt(g, s));
+            mw->pos_qk.push_back(out);
+        }
+        mw->pos_kdec = mw->pos_proj + per_enc * dm.enc_layers;
+        GemmParams g;
+        g.A = w->pos_table; g.lda = d; g.W = w->dec_kw; g.ldw = d;
+        g.C = mw->pos_kdec; g.ldc = dm.dec_layers * d; g.M = rows; g.N = dm.dec_layers * d; g.K = d;
+        CONE_TRY(sgemm_nt(g, s));
+    }
     return CONE_OK;
 }
 
@@ -743,7 +787,12 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         CONE_TRY(input_proj(c, "input_txt_proj", tok + q0 * Lt * dm.t_dim, n * Lt, dm.t_dim, txtproj, pb));
         CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
                                         topk, Lt, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
-        CONE_TRY(gather_window_rows(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));
+        if (precision == CONE_PREC_TC) {
+            CONE_TRY(gather_window_rows_f16(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src16, B, Lv, Lt,
+                                            dm.hidden, c.s));
+        } else {
+            CONE_TRY(gather_window_rows(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));
+        }
         float* spans_c = pred_spans + q0 * topk * nq * 2;
         CONE_TRY(transformer_core(c, cb, nullptr, prob_fg + q0 * topk * nq, spans_c, nullptr, nullptr, nullptr));
         CONE_TRY(match_core(c, frames_raw, n_frames, cb, spans_c, cls_norm + q0 * dm.v_dim, n, mb, match + q0 * topk * nq, nq));
@@ -779,7 +828,12 @@ extern "C" int cone_forward(const cone_weights* w, const float* src_txt, const i
     CONE_TRY(fill_window_desc_dense(cb.vid_base, cb.txt_base, cb.qidx, B, Lv, Lt, c.s));
     CONE_CUDA(cudaMemcpyAsync(cb.vlen, vid_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, c.s));
     CONE_CUDA(cudaMemcpyAsync(cb.tlen, txt_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, c.s));
-    CONE_TRY(gather_window_rows(vidproj, (int64_t)B * Lv, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));
+    if (precision == CONE_PREC_TC) {
+        CONE_TRY(gather_window_rows_f16(vidproj, (int64_t)B * Lv, cb.vid_base, txtproj, cb.txt_base, cb.src16, B, Lv, Lt,
+                                        dm.hidden, c.s));
+    } else {
+        CONE_TRY(gather_window_rows(vidproj, (int64_t)B * Lv, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));
+    }
     return transformer_core(c, cb, pred_logits, nullptr, pred_spans, saliency, aux_logits, aux_spans);
 }
 

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128)
 dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const KV* __restrict__ k, int64_t ldk,
                            const KV* __restrict__ v, int64_t ldv, float* __restrict__ o, int64_t ldo,
                            const int32_t* __restrict__ vlen, const int32_t* __restrict__ tlen, int64_t B, int nq, int Lv,
-                           int Lt, int nheads) {
+                           int Lt, int nheads, const float* __restrict__ posk, int64_t ldposk, int table_lv) {
     extern __shared__ float smem[];
     const int S = Lv + Lt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,6 +176,14 @@ dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const KV* _
         const bool ok = key_valid(j, Lv, vl, tl);
         float kr[HD];
         load_head_row(k + (b * S + j) * ldk + h * HD, kr);
+        if (posk != nullptr && j < Lv) {  // k = memory Wk^T + bk + pos Wk^T (table row of (valid length, j))
+            const float4* pr = reinterpret_cast<const float4*>(posk + ((int64_t)vl * table_lv + j) * ldposk + h * HD);
+#pragma unroll
+            for (int c = 0; c < HD / 4; ++c) {
+                const float4 p = __ldg(pr + c);
+                kr[4 * c] += p.x; kr[4 * c + 1] += p.y; kr[4 * c + 2] += p.z; kr[4 * c + 3] += p.w;
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (i < nq) {
@@ -248,7 +256,8 @@ template <int NB>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __half* __restrict__ v, int64_t ldv,
                          __half* __restrict__ o, int64_t ldo, const int32_t* __restrict__ vlen,
-                         const int32_t* __restrict__ tlen, int Lv, int Lt, int d_model) {
+                         const int32_t* __restrict__ tlen, int Lv, int Lt, int d_model,
+                         const float* __restrict__ posqk, int table_lv) {
     extern __shared__ __align__(16) unsigned char att_smem[];
     const int S = Lv + Lt;
     const int Sp = (S + 15) & ~15;
@@ -271,6 +280,21 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
             q4 = *reinterpret_cast<const uint4*>(qrow);
             k4 = *reinterpret_cast<const uint4*>(qrow + d_model);
             v4 = *reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + h * HD + c * 8);
+            if (posqk != nullptr && r < Lv) {
+                // q = (src + pos) Wq^T + bq = (src Wq^T + bq) + pos Wq^T: the position term comes from a per-layer
+                // table indexed by (valid length, row), so no position-added copy of the activations exists
+                const float* pr = posqk + ((int64_t)vl * table_lv + r) * (2 * d_model) + h * HD + c * 8;
+                __half2* qh = reinterpret_cast<__half2*>(&q4);
+                __half2* kh = reinterpret_cast<__half2*>(&k4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 pq = __ldg(reinterpret_cast<const float2*>(pr) + e);
+                    const float2 pk = __ldg(reinterpret_cast<const float2*>(pr + d_model) + e);
+                    float2 fq = __half22float2(qh[e]), fk = __half22float2(kh[e]);
+                    qh[e] = __floats2half2_rn(fq.x + pq.x, fq.y + pq.y);
+                    kh[e] = __floats2half2_rn(fk.x + pk.x, fk.y + pk.y);
+                }
+            }
         }
         *reinterpret_cast<uint4*>(Qs + r * QK_PAD + c * 8) = q4;
         *reinterpret_cast<uint4*>(Ks + r * QK_PAD + c * 8) = k4;
@@ -411,7 +435,8 @@ int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
 
 int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
-                        int Lt, int nheads, int kv_f16, cudaStream_t s) {
+                        int Lt, int nheads, int kv_f16, const float* posk, int64_t ldposk, int table_lv,
+                        cudaStream_t s) {
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
     CONE_REQUIRE(nq <= 8 && S <= MAX_S, "dec_cross_attention: unsupported nq=%d S=%d", nq, S);
@@ -422,11 +447,11 @@ int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk,
     if (kv_f16) {
         dec_cross_attention_kernel<__half><<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
             q, ldq, static_cast<const __half*>(k), ldk, static_cast<const __half*>(v), ldv, o, ldo, vlen, tlen, B, nq, Lv,
-            Lt, nheads);
+            Lt, nheads, posk, ldposk, table_lv);
     } else {
         dec_cross_attention_kernel<float><<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
             q, ldq, static_cast<const float*>(k), ldk, static_cast<const float*>(v), ldv, o, ldo, vlen, tlen, B, nq, Lv, Lt,
-            nheads);
+            nheads, posk, ldposk, table_lv);
     }
     CONE_LAUNCH_CHECK("dec_cross_attention");
     return CONE_OK;
@@ -434,7 +459,7 @@ int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk,
 
 int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
                            const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
-                           cudaStream_t s) {
+                           const float* posqk, int table_lv, cudaStream_t s) {
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
     CONE_REQUIRE(S <= MAX_S, "enc_self_attention_f16: window of %d rows exceeds %d", S, MAX_S);
@@ -448,7 +473,7 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
     __half* o16 = static_cast<__half*>(o);
     if (Sp <= 160) {
         enc_attention_f16_kernel<20><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt,
-                                                                      nheads * HD);
+                                                                      nheads * HD, posqk, table_lv);
     } else {
         static bool attr = false;
         if (!attr) {
@@ -456,7 +481,7 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
             attr = true;
         }
         enc_attention_f16_kernel<32><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt,
-                                                                      nheads * HD);
+                                                                      nheads * HD, posqk, table_lv);
     }
     CONE_LAUNCH_CHECK("enc_self_attention_f16");
     return CONE_OK;

@@ -44,6 +44,8 @@ int gather_window_rows(const float* vidproj, int64_t n_vid_rows, const int64_t* 
 // out[b*S + r] = src[b*S + r] + (r < Lv ? pos[vlen[b]][r] : 0)
 int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, float* out, int64_t B, int Lv, int Lt,
                  int d, int table_lv, cudaStream_t s);
+int gather_window_rows_f16(const float* vidproj, int64_t n_vid_rows, const int64_t* vid_base, const float* txtproj,
+                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s);
 // fp16 operands for the tensor-core path: plain16 = fp16(src), pos16 = fp16(src + pos); either may be null
 int add_pos_rows_f16(const float* src, const float* pos_table, const int32_t* vlen, uint16_t* plain16, uint16_t* pos16,
                      int64_t B, int Lv, int Lt, int d, int table_lv, cudaStream_t s);
@@ -59,9 +61,10 @@ int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
                        const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
                        cudaStream_t s);
 // tensor-core variant: fp16 q|k [R, ldqk], v, o (passed as void* to keep cuda_fp16.h out of this header)
+// posqk (nullable): per-layer table [(table_lv+1)*table_lv, 2*d] = pos . [Wq; Wk]^T added to q | k of video rows
 int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
                            const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
-                           cudaStream_t s);
+                           const float* posqk, int table_lv, cudaStream_t s);
 // decoder self-attention over nq slots (no mask)
 int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo, int64_t B,
                        int nq, int nheads, cudaStream_t s);
@@ -69,7 +72,8 @@ int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
 // k / v are fp32 (kv_f16 = 0) or fp16 (kv_f16 = 1) with leading dims in elements
 int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
-                        int Lt, int nheads, int kv_f16, cudaStream_t s);
+                        int Lt, int nheads, int kv_f16, const float* posk, int64_t ldposk, int table_lv,
+                        cudaStream_t s);
 
 // ---------------------------------------------------------------- prefilter.cu
 int window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count, int n_queries,

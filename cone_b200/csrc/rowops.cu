@@ -175,6 +175,34 @@ __global__ void add_pos_rows_f16_kernel(const float* __restrict__ src, const flo
     }
 }
 
+// gather straight into the fp16 operand of the first encoder layer: src16 = fp16(projected row)
+__global__ void gather_window_rows_f16_kernel(const float* __restrict__ vidproj, int64_t n_vid_rows,
+                                              const int64_t* __restrict__ vid_base, const float* __restrict__ txtproj,
+                                              const int64_t* __restrict__ txt_base, __half* __restrict__ src16, int64_t B,
+                                              int Lv, int Lt, int d4) {
+    const int S = Lv + Lt;
+    const int64_t total = B * S * d4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % d4);
+        const int64_t row = i / d4;
+        const int r = (int)(row % S);
+        const int64_t b = row / S;
+        float4 v;
+        if (r < Lv) {
+            int64_t fr = vid_base[b] + r;
+            fr = fr < n_vid_rows ? fr : n_vid_rows - 1;
+            v = __ldg(reinterpret_cast<const float4*>(vidproj) + fr * d4 + c);
+        } else {
+            v = __ldg(reinterpret_cast<const float4*>(txtproj) + (txt_base[b] + (r - Lv)) * d4 + c);
+        }
+        __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(src16)[i] = u;
+    }
+}
+
 __global__ void add_row_table_kernel(const float* __restrict__ x, const float* __restrict__ table,
                                      float* __restrict__ out, int64_t rows, int period, int d4) {
     const int64_t total = rows * d4;
@@ -265,6 +293,16 @@ int add_pos_rows_f16(const float* src, const float* pos_table, const int32_t* vl
     add_pos_rows_f16_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(
         src, pos_table, vlen, reinterpret_cast<__half*>(plain16), reinterpret_cast<__half*>(pos16), B, Lv, Lt, d / 4, table_lv);
     CONE_LAUNCH_CHECK("add_pos_rows_f16");
+    return CONE_OK;
+}
+
+int gather_window_rows_f16(const float* vidproj, int64_t n_vid_rows, const int64_t* vid_base, const float* txtproj,
+                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s) {
+    if (B == 0) return CONE_OK;
+    ProfScope ps(s, P_ROWOPS, 0.0, 6.0 * (double)B * (Lv + Lt) * d);
+    gather_window_rows_f16_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(
+        vidproj, n_vid_rows, vid_base, txtproj, txt_base, reinterpret_cast<__half*>(src16), B, Lv, Lt, d / 4);
+    CONE_LAUNCH_CHECK("gather_window_rows_f16");
     return CONE_OK;
 }
 

@@ -16,10 +16,27 @@ bool tc_gemm_supported(int64_t M, int N, int K);
 int tc_gemm(TcWeights* t, const float* x, int64_t ldx, int64_t M, const float* W, const float* b, int N, int K, float* y,
             int64_t ldy, int relu, const float* R, int64_t ldr, cudaStream_t s);
 
-// fp16 operand already in memory (row pitch lda halves); optional fp32 (C32) and fp16 (C16) outputs; optional fused
-// residual (R fp32) and LayerNorm over the row (ln_g/ln_b non-null requires N == 256).  fp16 pointers as uint16_t*.
-int tc_gemm_f16(TcWeights* t, const uint16_t* A16, int64_t lda, int64_t M, const float* W, const float* b, int N, int K,
-                float* C32, int64_t ldc32, uint16_t* C16, int64_t ldc16, int relu, const float* R, int64_t ldr,
-                const float* ln_g, const float* ln_b, cudaStream_t s);
+// General form: fp16 operand A already in memory; optional fp32 / fp16 outputs (written by TMA stores); fused bias,
+// residual (fp16 via TMA, or fp32), ReLU and LayerNorm over the row (needs N == 256).  fp16 pointers are
+// passed as uint16_t*.  The output may alias the fp16 residual (in-place residual stream).
+struct TcGemmArgs {
+    const uint16_t* A16 = nullptr;
+    int64_t lda = 0, M = 0;
+    const float* W = nullptr;     // fp32 master weight [N, K]; its fp16 copy is cached in TcWeights
+    const float* bias = nullptr;
+    int N = 0, K = 0;
+    float* C32 = nullptr;
+    int64_t ldc32 = 0;
+    uint16_t* C16 = nullptr;
+    int64_t ldc16 = 0;
+    int relu = 0;
+    const float* R32 = nullptr;
+    int64_t ldr32 = 0;
+    const uint16_t* R16 = nullptr;
+    int64_t ldr16 = 0;
+    const float* ln_g = nullptr;
+    const float* ln_b = nullptr;
+};
+int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s);
 
 }  // namespace cone
