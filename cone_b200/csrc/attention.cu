@@ -250,10 +250,26 @@ __device__ __forceinline__ uint32_t pack_half2(float x, float y) {
 }
 
 constexpr int ATT_WARPS = 5;
-constexpr int QK_PAD = 40;  // halves per Q/K row in smem (32 + 8): 20-word stride -> conflict-free 32-bit fragment loads
+constexpr int QK_PAD = 40;  // halves per Q/K/V row in smem (32 + 8): 80-byte stride -> conflict-free ldmatrix rows
+
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const __half* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int NB>
-__global__ void __launch_bounds__(ATT_WARPS * 32)
+__global__ void __launch_bounds__(ATT_WARPS * 32, 3)
 enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __half* __restrict__ v, int64_t ldv,
                          __half* __restrict__ o, int64_t ldo, const int32_t* __restrict__ vlen,
                          const int32_t* __restrict__ tlen, int Lv, int Lt, int d_model,
@@ -261,17 +277,16 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
     extern __shared__ __align__(16) unsigned char att_smem[];
     const int S = Lv + Lt;
     const int Sp = (S + 15) & ~15;
-    const int vt_ld = Sp + 8;  // halves per V^T row
     __half* Qs = reinterpret_cast<__half*>(att_smem);  // [Sp][QK_PAD]
     __half* Ks = Qs + Sp * QK_PAD;                      // [Sp][QK_PAD]
-    __half* Vt = Ks + Sp * QK_PAD;                      // [HD][vt_ld]
+    __half* Vs = Ks + Sp * QK_PAD;                      // [Sp][QK_PAD]  (row-major; P.V uses ldmatrix.trans)
     const int64_t b = blockIdx.x;
     const int h = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vl = vlen[b], tl = tlen[b];
     const int64_t row0 = b * S;
 
-    // cooperative load: 4 x 16-byte chunks per row for each of Q, K, V; V is transposed on the way in
+    // cooperative load: 4 x 16-byte chunks per row for each of Q, K, V
     for (int i = threadIdx.x; i < Sp * 4; i += blockDim.x) {
         const int r = i >> 2, c = i & 3;
         uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
@@ -284,53 +299,51 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 // q = (src + pos) Wq^T + bq = (src Wq^T + bq) + pos Wq^T: the position term comes from a per-layer
                 // table indexed by (valid length, row), so no position-added copy of the activations exists
                 const float* pr = posqk + ((int64_t)vl * table_lv + r) * (2 * d_model) + h * HD + c * 8;
+                const float4 pq0 = __ldg(reinterpret_cast<const float4*>(pr));
+                const float4 pq1 = __ldg(reinterpret_cast<const float4*>(pr) + 1);
+                const float4 pk0 = __ldg(reinterpret_cast<const float4*>(pr + d_model));
+                const float4 pk1 = __ldg(reinterpret_cast<const float4*>(pr + d_model) + 1);
                 __half2* qh = reinterpret_cast<__half2*>(&q4);
                 __half2* kh = reinterpret_cast<__half2*>(&k4);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 pq = __ldg(reinterpret_cast<const float2*>(pr) + e);
-                    const float2 pk = __ldg(reinterpret_cast<const float2*>(pr + d_model) + e);
-                    float2 fq = __half22float2(qh[e]), fk = __half22float2(kh[e]);
-                    qh[e] = __floats2half2_rn(fq.x + pq.x, fq.y + pq.y);
-                    kh[e] = __floats2half2_rn(fk.x + pk.x, fk.y + pk.y);
-                }
+                float2 f;
+                f = __half22float2(qh[0]); qh[0] = __floats2half2_rn(f.x + pq0.x, f.y + pq0.y);
+                f = __half22float2(qh[1]); qh[1] = __floats2half2_rn(f.x + pq0.z, f.y + pq0.w);
+                f = __half22float2(qh[2]); qh[2] = __floats2half2_rn(f.x + pq1.x, f.y + pq1.y);
+                f = __half22float2(qh[3]); qh[3] = __floats2half2_rn(f.x + pq1.z, f.y + pq1.w);
+                f = __half22float2(kh[0]); kh[0] = __floats2half2_rn(f.x + pk0.x, f.y + pk0.y);
+                f = __half22float2(kh[1]); kh[1] = __floats2half2_rn(f.x + pk0.z, f.y + pk0.w);
+                f = __half22float2(kh[2]); kh[2] = __floats2half2_rn(f.x + pk1.x, f.y + pk1.y);
+                f = __half22float2(kh[3]); kh[3] = __floats2half2_rn(f.x + pk1.z, f.y + pk1.w);
             }
         }
         *reinterpret_cast<uint4*>(Qs + r * QK_PAD + c * 8) = q4;
         *reinterpret_cast<uint4*>(Ks + r * QK_PAD + c * 8) = k4;
-        const __half* vh = reinterpret_cast<const __half*>(&v4);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) Vt[(c * 8 + e) * vt_ld + r] = vh[e];
+        *reinterpret_cast<uint4*>(Vs + r * QK_PAD + c * 8) = v4;
     }
     __syncthreads();
 
     const int nkb = Sp >> 3;  // key blocks of 8 (even)
     const int nrb = Sp >> 4;  // query row blocks of 16
     const int g = lane >> 2, t4 = lane & 3;
+    const int l8 = lane & 7, lq = lane >> 3;  // ldmatrix: lane -> (row in 8x8 matrix, matrix id)
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // softmax scale * log2(e)
     for (int rb = warp; rb < nrb; rb += ATT_WARPS) {
         const int r_lo = rb * 16 + g, r_hi = r_lo + 8;
         uint32_t aq[2][4];
+        // A fragments of Q: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15) for each 16-wide k step
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            aq[ks][0] = *reinterpret_cast<const uint32_t*>(Qs + r_lo * QK_PAD + ks * 16 + t4 * 2);
-            aq[ks][1] = *reinterpret_cast<const uint32_t*>(Qs + r_hi * QK_PAD + ks * 16 + t4 * 2);
-            aq[ks][2] = *reinterpret_cast<const uint32_t*>(Qs + r_lo * QK_PAD + ks * 16 + 8 + t4 * 2);
-            aq[ks][3] = *reinterpret_cast<const uint32_t*>(Qs + r_hi * QK_PAD + ks * 16 + 8 + t4 * 2);
-        }
+        for (int ks = 0; ks < 2; ++ks)
+            ldsm_x4(aq[ks], Qs + (rb * 16 + l8 + (lq & 1) * 8) * QK_PAD + ks * 16 + (lq >> 1) * 8);
         float sc[NB][4];
         float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F;
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             sc[jb][0] = sc[jb][1] = sc[jb][2] = sc[jb][3] = 0.f;
             if (jb < nkb) {
-                const __half* krow = Ks + (jb * 8 + g) * QK_PAD + t4 * 2;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
-                    mma_16816(sc[jb], aq[ks], b0, b1);
-                }
+                uint32_t bk[4];  // B fragments of K for keys jb*8..+7: dims 0-7, 8-15, 16-23, 24-31
+                ldsm_x4(bk, Ks + (jb * 8 + l8) * QK_PAD + lq * 8);
+                mma_16816(sc[jb], aq[0], bk[0], bk[1]);
+                mma_16816(sc[jb], aq[1], bk[2], bk[3]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int key = jb * 8 + t4 * 2 + e;
@@ -352,8 +365,8 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
             if (jb < nkb) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float p0 = exp2f(sc[jb][e] - m_lo);      // exp2(-inf) = 0 for masked keys
-                    const float p1 = exp2f(sc[jb][2 + e] - m_hi);
+                    const float p0 = fast_exp2(sc[jb][e] - m_lo);      // exp2(-inf) = 0 for masked keys
+                    const float p1 = fast_exp2(sc[jb][2 + e] - m_hi);
                     sc[jb][e] = p0;
                     sc[jb][2 + e] = p1;
                     s_lo += p0;
@@ -377,12 +390,14 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 ap[1] = pack_half2(sc[2 * kb][2], sc[2 * kb][3]);
                 ap[2] = pack_half2(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
                 ap[3] = pack_half2(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
+                // B fragments of V (k = key, n = dim) from row-major V via transposing ldmatrix:
+                // matrices (keys 0-7 | 8-15) x (dims nb*8 | (nb+1)*8)
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    const __half* vrow = Vt + (nb * 8 + g) * vt_ld + kb * 16 + t4 * 2;
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + 8);
-                    mma_16816(out[nb], ap, b0, b1);
+                for (int np = 0; np < 2; ++np) {
+                    uint32_t bv[4];
+                    ldsm_x4_trans(bv, Vs + (kb * 16 + l8 + (lq & 1) * 8) * QK_PAD + (np * 2 + (lq >> 1)) * 8);
+                    mma_16816(out[np * 2], ap, bv[0], bv[1]);
+                    mma_16816(out[np * 2 + 1], ap, bv[2], bv[3]);
                 }
             }
         }
@@ -465,7 +480,7 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
     CONE_REQUIRE(S <= MAX_S, "enc_self_attention_f16: window of %d rows exceeds %d", S, MAX_S);
     CONE_REQUIRE((ldqk % 8) == 0 && (ldv % 8) == 0 && (ldo % 2) == 0, "enc_self_attention_f16: leading dims must keep 16-byte rows");
     const int Sp = (S + 15) & ~15;
-    const size_t smem = sizeof(__half) * ((size_t)2 * Sp * QK_PAD + (size_t)HD * (Sp + 8));
+    const size_t smem = sizeof(__half) * (size_t)3 * Sp * QK_PAD;
     dim3 grid((unsigned)B, (unsigned)nheads);
     ProfScope ps(s, P_ENC_ATTN, 4.0 * (double)B * nheads * S * S * HD, 8.0 * (double)B * S * nheads * HD);
     const __half* qk16 = static_cast<const __half*>(qk);
