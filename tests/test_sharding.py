@@ -1,0 +1,62 @@
+"""Multi-GPU host logic on CPU: LPT sharding of videos and the prediction all-gather (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cone_b200.sharding import gather_predictions, lpt_assign, video_cost
+
+
+def test_lpt_assign_balances_and_is_deterministic():
+    rng = np.random.default_rng(0)
+    costs = [video_cost(int(rng.integers(36000, 54000)), int(rng.integers(300, 900)), 30) for _ in range(112)]
+    a = lpt_assign(costs, 8)
+    assert a == lpt_assign(costs, 8)
+    assert sorted(i for r in a for i in r) == list(range(112))
+    loads = [sum(costs[i] for i in r) for r in a]
+    assert max(loads) / (sum(loads) / 8) < 1.03  # within 3 % of perfect balance
+    assert lpt_assign([5.0, 1.0], 4) == [[0], [1], [], []]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 3 + 2 * rank  # ranks hold different numbers of queries
+    g = torch.Generator().manual_seed(rank)
+    nms = torch.rand((n, 3, 5, 5), dtype=torch.float64, generator=g)
+    cnt = torch.randint(0, 6, (n, 3), dtype=torch.int32, generator=g)
+    qid = torch.arange(n, dtype=torch.int64) + 1000 * rank
+    a, b, c = gather_predictions(nms, cnt, qid)
+    torch.save({"nms": a, "cnt": b, "qid": c, "local": (nms, cnt, qid)}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_predictions_gloo_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    want_nms = torch.cat([res[r]["local"][0] for r in range(world)])
+    want_cnt = torch.cat([res[r]["local"][1] for r in range(world)])
+    want_qid = torch.cat([res[r]["local"][2] for r in range(world)])
+    for r in range(world):  # every rank ends up with every rank's predictions, in rank order, padding trimmed
+        assert torch.equal(res[r]["nms"], want_nms)
+        assert torch.equal(res[r]["cnt"], want_cnt)
+        assert torch.equal(res[r]["qid"], want_qid)
+
+
+def test_gather_predictions_without_process_group_is_identity():
+    nms, cnt = torch.rand(4, 3, 5, 5, dtype=torch.float64), torch.ones(4, 3, dtype=torch.int32)
+    a, b = gather_predictions(nms, cnt)
+    assert a is nms and b is cnt
