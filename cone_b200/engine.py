@@ -62,6 +62,13 @@ class QueryBatch:
                        else getattr(self, f.name)) for f in dataclasses.fields(self)}
         return QueryBatch(**kw)
 
+    def record_stream(self, stream) -> None:
+        """Tell the caching allocator that `stream` uses these tensors (they were copied on a side stream)."""
+        for f in dataclasses.fields(self):
+            t = getattr(self, f.name)
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(stream)
+
     def h2d_bytes(self) -> int:
         return sum(getattr(self, f.name).numel() * getattr(self, f.name).element_size()
                    for f in dataclasses.fields(self) if isinstance(getattr(self, f.name), torch.Tensor))

@@ -26,19 +26,22 @@ def lpt_assign(costs: Sequence[float], world_size: int) -> List[List[int]]:
     return [sorted(x) for x in out]
 
 
-def gather_predictions(nms: torch.Tensor, count: torch.Tensor, qid: torch.Tensor | None = None, group=None
-                       ) -> Tuple[torch.Tensor, ...]:
+def gather_predictions(nms: torch.Tensor, count: torch.Tensor, qid: torch.Tensor | None = None, group=None,
+                       equal_shards: bool = False) -> Tuple[torch.Tensor, ...]:
     """All-gather per-query prediction blocks [Nq_local, 3, max_after, 5] (+ counts [Nq_local, 3], + optional
     int64 query ordinals) from every rank.  Ranks may hold different numbers of queries: blocks are padded to the
     largest shard, gathered with one collective per tensor and trimmed.  Returns tensors concatenated in rank
-    order."""
+    order.  `equal_shards=True` skips the size exchange when all ranks are known to hold equally many queries."""
     if not dist.is_available() or not dist.is_initialized():
         return (nms, count) if qid is None else (nms, count, qid)
     world = dist.get_world_size(group)
-    n_local = torch.tensor([nms.shape[0]], dtype=torch.int64, device=nms.device)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if equal_shards:  # every rank holds the same number of queries: no size exchange, no host sync
+        sizes = [nms.shape[0]] * world
+    else:
+        n_local = torch.tensor([nms.shape[0]], dtype=torch.int64, device=nms.device)
+        sizes = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(sizes, n_local, group=group)
+        sizes = [int(s.item()) for s in sizes]
     n_max = max(sizes)
 
     def pad(t):
