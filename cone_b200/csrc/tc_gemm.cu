@@ -6,7 +6,9 @@
 //   warp 1    MMA issuer    one thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) from
 //                           shared-memory descriptors; accumulators live in TMEM (2 x BN fp32 columns, double
 //                           buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2-5 epilogue      tcgen05.ld TMEM -> registers (one accumulator row per thread); bias / fp16 residual /
+//   warps 2-9 epilogue      tcgen05.ld TMEM -> registers (one accumulator row per thread, two warps per TMEM lane
+//                           quarter splitting the columns: 2 epilogue warps per scheduler hide each other's
+//                           latencies); bias / fp16 residual /
 //                           ReLU / LayerNorm(N = 256) in registers; results are written as 16-byte vectors into a
 //                           128-byte-swizzled shared-memory box and leave the SM as ONE TMA store per 32 x 64 box
 //                           (no per-row store instructions, out-of-range rows clipped by the tensor map); the
@@ -33,7 +35,7 @@ constexpr int BK = 64;           // fp16 elements per stage row = 128 bytes = on
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // producer warp + MMA warp + 8 epilogue warps
 constexpr int BOX_BYTES = 32 * 128;   // one epilogue box: 32 rows x 128 bytes (64 fp16 or 32 fp32 columns)
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -160,24 +162,28 @@ __device__ __forceinline__ void add_bias64(float* x, const float* bias) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quarter; each takes half of the tile's columns
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC16,
                const __grid_constant__ CUtensorMap tmC32, TcEpilogue ep, int64_t M, int N, int K) {
     constexpr int B_BYTES = BN * BK * 2;
+    constexpr int HALF = BN / 2;  // columns per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * A_BYTES;
-    uint8_t* sOut = sB + STAGES * B_BYTES;   // 4 warps x 2 boxes (double buffered TMA-store source)
-    uint8_t* sRes = sOut + 4 * 2 * BOX_BYTES;  // 4 warps x 1 box (TMA-loaded residual)
-    uint64_t* full = reinterpret_cast<uint64_t*>(sRes + 4 * BOX_BYTES);
+    uint8_t* sOut = sB + STAGES * B_BYTES;           // one TMA-store box per epilogue warp
+    uint8_t* sRes = sOut + EPI_WARPS * BOX_BYTES;    // one TMA-loaded residual box per epilogue warp
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRes + EPI_WARPS * BOX_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint64_t* rfull = tempty + 2;  // one per epilogue warp
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 4);
+    float2* ln_part = reinterpret_cast<float2*>(rfull + EPI_WARPS);  // [EPI_WARPS][32] partial (sum, sum of squares)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_part + EPI_WARPS * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_tiles = (M + BM - 1) / BM;
@@ -194,9 +200,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&tempty[i], EPI_WARPS * 32);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(&rfull[i], 1);
+        for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&rfull[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: 2 accumulators of BN fp32 columns (512 columns = the whole TMEM for BN = 256)
@@ -265,58 +271,52 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {  // ------------------------------------------------------------------------------- epilogue
-        const int ew = warp - 2;       // 0..3
+        const int ew = warp - 2;       // 0..7
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-        uint8_t* out_box = sOut + ew * 2 * BOX_BYTES;
+        const int half = ew >> 2;      // which half of the tile's columns
+        const int partner = ew ^ 4;    // the warp with the same rows and the other columns
+        uint8_t* out_box = sOut + ew * BOX_BYTES;
         uint8_t* res_box = sRes + ew * BOX_BYTES;
         uint64_t* rbar = &rfull[ew];
         uint32_t rphase = 0;
-        int obuf = 0;
         const bool ln = ep.ln_g != nullptr;
         int acc = 0;
         uint32_t acc_phase = 0;
 
-        // write 16-byte units of this lane's row into the swizzled box and hand the box to TMA
-        auto flush_box = [&](const CUtensorMap* map, uint8_t* box, int col, int row0) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_2d(map, box, col, row0);
-                tma_store_commit();
-            }
-        };
-        auto acquire_box = [&]() -> uint8_t* {
-            uint8_t* box = out_box + obuf * BOX_BYTES;
-            obuf ^= 1;
-            if (lane == 0) tma_store_wait_read<1>();  // the store issued two boxes ago has released this buffer
-            __syncwarp();
-            return box;
-        };
-
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int64_t m0 = (t / n_tiles) * BM;
-            const int n0 = (int)(t % n_tiles) * BN;
-            const int row0 = (int)m0 + quarter * 32;  // first row of this warp's 32 rows
+            const int n0 = (int)(t % n_tiles) * BN + half * HALF;  // first column of this warp's half
+            const int row0 = (int)m0 + quarter * 32;               // first row of this warp's 32 rows
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
 
-            // x = acc + bias (+ residual) for one 64-column chunk, one row per lane
-            auto load_chunk = [&](int c, float* x) {
-                if (ep.has_r16 && lane == 0) {  // residual box [32 rows x 64 cols] fp16 -> res_box
+            // x[0..31] = acc + bias (+ residual) for columns [c, c+32) of this warp's half, one row per lane.
+            // The fp16 residual arrives as a [32 x 64] box: requested at even 32-column steps, consumed in two halves.
+            auto load_sub = [&](int c, float* x) {
+                const int sub = (c >> 5) & 1;
+                if (ep.has_r16 && sub == 0 && lane == 0) {
+                    if (ep.has_c32) tma_store_wait_read<0>();  // res_box doubles as the fp32 store box (see below)
                     mbar_expect_tx(rbar, BOX_BYTES);
                     tma_load_2d(res_box, &tmR, rbar, n0 + c, row0);
                 }
                 tmem_ld_32x32(taddr + c, x);
-                tmem_ld_32x32(taddr + c + 32, x + 32);
                 tmem_ld_wait();
-                if (ep.bias) add_bias64(x, ep.bias + n0 + c);
-                if (ep.has_r16) {
-                    mbar_wait(rbar, rphase);
-                    rphase ^= 1;
+                if (ep.bias) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(res_box + sw128(lane, u));
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c) + q);
+                        x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+                    }
+                }
+                if (ep.has_r16) {
+                    if (sub == 0) {
+                        mbar_wait(rbar, rphase);
+                        rphase ^= 1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(res_box + sw128(lane, sub * 4 + u));
                         const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -325,14 +325,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             x[8 * u + 2 * e + 1] += f.y;
                         }
                     }
-                    __syncwarp();  // every lane has read the box before the next TMA load overwrites it
+                    if (sub == 1) __syncwarp();  // every lane has read the box before the next TMA load overwrites it
                 }
                 if (ep.R32) {  // small-M path: plain row loads
                     const int64_t row = (int64_t)row0 + lane;
                     if (row < M) {
                         const float4* r4 = reinterpret_cast<const float4*>(ep.R32 + row * ep.ldr32 + n0 + c);
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) {
+                        for (int q = 0; q < 8; ++q) {
                             const float4 b = r4[q];
                             x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
                         }
@@ -341,31 +341,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             };
 
             float mean = 0.f, rstd = 1.f;
-            if (ln) {  // pass 1: pre-LayerNorm values back into TMEM + row statistics
+            if (ln) {  // pass 1: pre-LayerNorm values back into TMEM + row statistics (two warps per row)
                 float s1 = 0.f, s2 = 0.f;
-                for (int c = 0; c < BN; c += 64) {
-                    float x[64];
-                    load_chunk(c, x);
+                for (int c = 0; c < HALF; c += 32) {
+                    float x[32];
+                    load_sub(c, x);
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) {
+                    for (int j = 0; j < 32; ++j) {
                         s1 += x[j];
                         s2 = fmaf(x[j], x[j], s2);
                     }
                     tmem_st_32x32(taddr + c, x);
-                    tmem_st_32x32(taddr + c + 32, x + 32);
                     tmem_st_wait();
                 }
+                ln_part[ew * 32 + lane] = make_float2(s1, s2);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // the two warps of this row quarter
+                const float2 o = ln_part[partner * 32 + lane];
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // partials consumed: slot reusable
+                s1 += o.x;
+                s2 += o.y;
                 mean = s1 * (1.f / BN);
                 rstd = rsqrtf(fmaxf(s2 * (1.f / BN) - mean * mean, 0.f) + ep.ln_eps);
             }
-            for (int c = 0; c < BN; c += 64) {
-                float x[64];
+            for (int c = 0; c < HALF; c += 32) {
+                float x[32];
                 if (ln) {
                     tmem_ld_32x32(taddr + c, x);
-                    tmem_ld_32x32(taddr + c + 32, x + 32);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
+                    for (int q = 0; q < 8; ++q) {
                         const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_g + n0 + c) + q);
                         const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_b + n0 + c) + q);
                         x[4 * q] = (x[4 * q] - mean) * rstd * g.x + b.x;
@@ -374,16 +378,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         x[4 * q + 3] = (x[4 * q + 3] - mean) * rstd * g.w + b.w;
                     }
                 } else {
-                    load_chunk(c, x);
+                    load_sub(c, x);
                     if (ep.relu) {
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) x[j] = fmaxf(x[j], 0.f);
+                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
                     }
                 }
-                if (ep.has_c16) {  // 32 rows x 64 fp16 columns = one 128-byte-swizzled box
-                    uint8_t* box = acquire_box();
+                if (ep.has_c16) {  // two 32-column steps fill one [32 rows x 64 fp16] 128-byte-swizzled box
+                    const int sub = (c >> 5) & 1;
+                    if (sub == 0) {
+                        if (lane == 0) tma_store_wait_read<0>();  // previous store has released the box
+                        __syncwarp();
+                    }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < 4; ++u) {
                         __half2 h0 = __floats2half2_rn(x[8 * u], x[8 * u + 1]);
                         __half2 h1 = __floats2half2_rn(x[8 * u + 2], x[8 * u + 3]);
                         __half2 h2 = __floats2half2_rn(x[8 * u + 4], x[8 * u + 5]);
@@ -393,20 +401,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v.y = *reinterpret_cast<uint32_t*>(&h1);
                         v.z = *reinterpret_cast<uint32_t*>(&h2);
                         v.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(box + sw128(lane, u)) = v;
+                        *reinterpret_cast<uint4*>(out_box + sw128(lane, sub * 4 + u)) = v;
                     }
-                    flush_box(&tmC16, box, n0 + c, row0);
+                    if (sub == 1) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC16, out_box, n0 + c - 32, row0);
+                            tma_store_commit();
+                        }
+                    }
                 }
-                if (ep.has_c32) {  // two boxes of 32 rows x 32 fp32 columns
+                if (ep.has_c32) {  // one box of 32 rows x 32 fp32 columns
+                    // with an fp16 output in flight the fp32 box is staged in res_box (free in this pass: the host
+                    // side only allows both outputs together with LayerNorm or without an fp16 residual)
+                    uint8_t* box32 = ep.has_c16 ? res_box : out_box;
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint8_t* box = acquire_box();
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            *reinterpret_cast<float4*>(box + sw128(lane, u)) =
-                                make_float4(x[hh * 32 + 4 * u], x[hh * 32 + 4 * u + 1], x[hh * 32 + 4 * u + 2],
-                                            x[hh * 32 + 4 * u + 3]);
-                        flush_box(&tmC32, box, n0 + c + hh * 32, row0);
+                    for (int u = 0; u < 8; ++u)
+                        *reinterpret_cast<float4*>(box32 + sw128(lane, u)) =
+                            make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC32, box32, n0 + c, row0);
+                        tma_store_commit();
                     }
                 }
             }
@@ -492,7 +512,7 @@ int make_map(CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t
 
 template <int BN>
 constexpr size_t tc_smem_bytes() {
-    return 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2) + 12 * BOX_BYTES + 32 * sizeof(uint64_t);
+    return 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2) + 16 * BOX_BYTES + 32 * sizeof(uint64_t) + 8 * 32 * 8 + 64;
 }
 
 }  // namespace
@@ -580,6 +600,8 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     const TcWeights::W16* w = nullptr;
     CONE_TRY(get_w16(t, g.W, g.N, g.K, s, &w));
     CONE_REQUIRE(g.ln_g == nullptr || g.N == w->BN, "tc_gemm: fused LayerNorm needs the whole row in one tile (N=%d)", g.N);
+    CONE_REQUIRE(!(g.C16 && g.C32 && g.R16 && g.ln_g == nullptr),
+                 "tc_gemm: fp16 + fp32 outputs with an fp16 residual need the LayerNorm epilogue");
     CUtensorMap mapA, mapR, mapC16, mapC32;
     CONE_TRY(make_map(&mapA, g.A16, false, g.M, g.K, g.lda, BK, BM));
     mapR = mapA;
