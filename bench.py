@@ -35,7 +35,8 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--config", default="mad768", choices=["mad768", "mad512", "ego4d"])
-    p.add_argument("--precision", default=os.environ.get("CONE_BENCH_PRECISION", "fp32"), choices=["fp32", "tc"])
+    p.add_argument("--precision", default=os.environ.get("CONE_BENCH_PRECISION", "tc"), choices=["fp32", "tc"],
+                   help="tc: tcgen05 fp16-operand / fp32-accumulate projections (1e-3 class); fp32: CUDA-core parity mode (1e-5)")
     p.add_argument("--movies", type=int, default=8, help="movies resident per GPU (cycled through by the steps)")
     p.add_argument("--queries-per-movie", type=int, default=640)
     p.add_argument("--frames", type=int, nargs=2, default=None, help="movie length range in frames")
@@ -240,9 +241,9 @@ def run_ours(args):
     def prefetch(i):
         s = host_steps[i % args.movies]
         with torch.cuda.stream(copy_stream):
-            fr = s.frames.to(dev, non_blocking=True)
+            frames_d = s.frames.to(dev, non_blocking=True)
             qb = s.qb.to(dev)
-        return s, fr, qb
+        return s, frames_d, qb
 
     host_out = []
     barrier()
@@ -250,13 +251,13 @@ def run_ours(args):
     h2d = d2h = 0
     nxt = prefetch(0)
     for i in range(args.steps):
-        s, fr, qb = nxt
+        s, frames_d, qb = nxt
         main.wait_stream(copy_stream)
-        fr.record_stream(main)
+        frames_d.record_stream(main)
         qb.record_stream(main)
         if i + 1 < args.steps:
             nxt = prefetch(i + 1)
-        out = eng.ground(fr, qb)
+        out = eng.ground(frames_d, qb)
         if world > 1:
             nms, cnt = gather_predictions(out.nms, out.nms_count, equal_shards=True)
         else:
@@ -277,14 +278,10 @@ def run_ours(args):
     e2e_value = nq_all / float(te.item())
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         line = {"metric": "grounding_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16",
                 "data": "synthetic",
                 "config": {"workload": workload_name(cfg, args, fr), "movies_per_gpu": args.movies,
                            "queries_per_step": args.queries_per_movie, "precision": args.precision,
@@ -297,7 +294,7 @@ def run_ours(args):
         flops_q = algorithmic_flops_per_query(cfg)
         line["roofline"] = roofline_entry(prof, peaks, flops_q, args, cfg)
         if prof:
-            line["stage_ms_per_step"] = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}
+            line["stages"] = stage_table(prof, peaks, args.steps)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             qps, dt, n = cpu_oracle_sample(cfg, sd, ds, args.cpu_sample_queries, threads)
@@ -310,23 +307,70 @@ def run_ours(args):
     return 0
 
 
+def load_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) or the fallback B200_PROFILING.md states."""
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pk, src = {}, "fallback (B200_PROFILING.md: 6.65 TB/s copy, 1.59 PFLOP/s burst / ~1.4 sustained)"
+    return {"hbm_gbs": float(pk.get("hbm_gbs", 6650.0)),
+            "tflops": float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))), "source": src}
+
+
+def load_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same
+    command (profiles/r01_traffic.json, written by profiles/summarize_ncu.py); None when not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return t.get(key)
+    except Exception:
+        return None
+
+
 def roofline_entry(prof, peaks, flops_per_query, args, cfg):
-    """Dominant kernel of the step: the dense-projection GEMM.  achieved = algorithmic GEMM FLOPs per launch /
-    average launch duration (CUDA events around every launch, on the launching stream)."""
+    """Dominant kernel of the step: the dense-projection GEMM (largest share of the step).  It sits at the
+    ridge: K = 256 / 1024 with N <= 1024 gives ~200 FLOP per activation byte against a machine balance of
+    ~210, so both rooflines are reported; `bound` names the one that is closer to its peak.
+    achieved = algorithmic FLOPs (bytes) of the launches / their summed duration (CUDA events around every
+    launch, on the launching stream, inside the timed region)."""
     key = "gemm_tc" if args.precision == "tc" else "gemm_fp32"
-    peak = peaks.get("bf16_tflops_sustained")
-    src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-    if peak is None:
-        peak, src = 1400.0, "fallback B200_PROFILING.md (~1.4 PFLOP/s sustained)"
     if not prof or key not in prof or not prof[key]["launches"]:
-        return {"bound": "tensor", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None, "traffic": None,
-                "note": "per-kernel profile unavailable"}
+        return {"bound": "tensor", "achieved": None, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": None,
+                "traffic": None, "note": "per-kernel profile unavailable"}
     p = prof[key]
-    achieved = p["flops"] / (p["ms"] * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": key, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "launches": p["launches"],
-            "avg_launch_ms": p["ms"] / p["launches"], "share_of_step": p["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
-            "peak_source": src}
+    sec = p["ms"] * 1e-3
+    tf = p["flops"] / sec / 1e12
+    gbs = p["bytes"] / sec / 1e9
+    total = max(sum(v["ms"] for v in prof.values()), 1e-9)
+    ent = {"kernel": key, "launches": p["launches"], "avg_launch_ms": p["ms"] / p["launches"],
+           "share_of_step": p["ms"] / total, "peak_source": peaks["source"],
+           "tensor": {"achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"]},
+           "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                   "algorithmic_bytes_per_launch": p["bytes"] / p["launches"]},
+           "traffic": load_traffic(key)}
+    if key == "gemm_tc" and gbs / peaks["hbm_gbs"] >= tf / peaks["tflops"]:
+        ent.update(bound="hbm", achieved=gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbs / peaks["hbm_gbs"])
+    else:
+        ent.update(bound="tensor", achieved=tf, peak=peaks["tflops"], unit="TFLOP/s", frac=tf / peaks["tflops"])
+    return ent
+
+
+def stage_table(prof, peaks, steps):
+    """Per kernel category: ms/step and achieved GB/s / TFLOP/s from the algorithmic work the launches declared."""
+    out = {}
+    for k, v in prof.items():
+        if not v["launches"]:
+            continue
+        sec = v["ms"] * 1e-3
+        e = {"ms": round(v["ms"] / steps, 3), "launches": v["launches"] // steps}
+        if v["bytes"]:
+            e["GBps"] = round(v["bytes"] / sec / 1e9, 1)
+            e["hbm_frac"] = round(v["bytes"] / sec / 1e9 / peaks["hbm_gbs"], 3)
+        if v["flops"]:
+            e["TFLOPs"] = round(v["flops"] / sec / 1e12, 2)
+        out[k] = e
+    return out
 
 
 if __name__ == "__main__":

@@ -149,30 +149,40 @@ __device__ __forceinline__ void load_head_row(const __half* p, float* out) {
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 
-template <typename KV>
-__global__ void __launch_bounds__(128)
+// One CTA per window, 8 warps.  Three phases, all reading K / V straight from global memory (no staging):
+//   1. scores: thread <-> (key j, head h) pairs, consecutive threads = the 8 heads of a key, so a warp reads 4 whole
+//      K rows (coalesced); the 32-wide dot products against the nq scaled queries of that head run from registers
+//      (K row chunk) x shared memory (queries, padded so the 8 heads hit distinct banks)
+//   2. masked softmax per (head, slot) row: one warp per row
+//   3. P.V: thread <-> output channel (warp = head), rows streamed 4 at a time, P read as broadcast float4
+// The previous version ran one warp per (window, head) end to end and was latency-bound at 5x its HBM time.
+constexpr int XQ_PAD = 36;  // floats per (slot, head) query row in smem: 16-byte aligned, heads 144 B apart
+
+template <typename KV, int NQ>
+__global__ void __launch_bounds__(256)
 dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const KV* __restrict__ k, int64_t ldk,
                            const KV* __restrict__ v, int64_t ldv, float* __restrict__ o, int64_t ldo,
-                           const int32_t* __restrict__ vlen, const int32_t* __restrict__ tlen, int64_t B, int nq, int Lv,
-                           int Lt, int nheads, const float* __restrict__ posk, int64_t ldposk, int table_lv) {
-    extern __shared__ float smem[];
+                           const int32_t* __restrict__ vlen, const int32_t* __restrict__ tlen, int nq, int Lv,
+                           int Lt, const float* __restrict__ posk, int64_t ldposk, int table_lv) {
+    constexpr int H = 8;
+    extern __shared__ __align__(16) float xsmem[];
     const int S = Lv + Lt;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (wid >= B * nheads) return;  // whole warp exits together
-    float* Qs = smem + warp * (8 * HD + 8 * S);  // [8][HD]
-    float* Ps = Qs + 8 * HD;                     // [8][S]
-    const int64_t b = wid / nheads;
-    const int h = (int)(wid % nheads);
+    const int Sp = (S + 3) & ~3;
+    float* Qs = xsmem;                   // [NQ][H][XQ_PAD]
+    float* Ps = Qs + NQ * H * XQ_PAD;    // [H][NQ][Sp]
+    float* inv = Ps + H * NQ * Sp;       // [H][NQ]
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int vl = vlen[b], tl = tlen[b];
     const float scale = 0.17677669529663687f;
-    for (int i = 0; i < nq; ++i) Qs[i * HD + lane] = q[(b * nq + i) * ldq + h * HD + lane] * scale;
-    __syncwarp();
-    float mx[8], sum[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { mx[i] = -CUDART_INF_F; sum[i] = 0.f; }
-    // pass 1: scores (each lane owns keys lane, lane+32, ...)
-    for (int j = lane; j < S; j += 32) {
+    for (int i = tid; i < NQ * H * HD; i += 256) {
+        const int c = i % HD, h = (i / HD) % H, s = i / (HD * H);
+        Qs[(s * H + h) * XQ_PAD + c] = s < nq ? q[(b * nq + s) * ldq + h * HD + c] * scale : 0.f;
+    }
+    __syncthreads();
+    // phase 1
+    for (int idx = tid; idx < S * H; idx += 256) {
+        const int j = idx >> 3, h = idx & 7;
         const bool ok = key_valid(j, Lv, vl, tl);
         float kr[HD];
         load_head_row(k + (b * S + j) * ldk + h * HD, kr);
@@ -185,49 +195,63 @@ dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const KV* _
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i < nq) {
-                float a = -CUDART_INF_F;
-                if (ok) {
-                    a = 0.f;
+        for (int s = 0; s < NQ; ++s) {
+            const float4* qr = reinterpret_cast<const float4*>(Qs + (s * H + h) * XQ_PAD);
+            float a = 0.f;
 #pragma unroll
-                    for (int c = 0; c < HD; ++c) a = fmaf(Qs[i * HD + c], kr[c], a);
-                }
-                Ps[i * S + j] = a;
-                mx[i] = fmaxf(mx[i], a);
+            for (int c = 0; c < HD / 4; ++c) {
+                const float4 qq = qr[c];
+                a = fmaf(qq.x, kr[4 * c], a);
+                a = fmaf(qq.y, kr[4 * c + 1], a);
+                a = fmaf(qq.z, kr[4 * c + 2], a);
+                a = fmaf(qq.w, kr[4 * c + 3], a);
             }
+            Ps[(h * NQ + s) * Sp + j] = ok ? a : -CUDART_INF_F;
+        }
+    }
+    __syncthreads();
+    // phase 2
+    for (int r = warp; r < H * NQ; r += 8) {
+        float* row = Ps + r * Sp;
+        float mx = -CUDART_INF_F;
+        for (int j = lane; j < S; j += 32) mx = fmaxf(mx, row[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < Sp; j += 32) {
+            float e = 0.f;
+            if (j < S) {
+                const float a = row[j];
+                e = (a == -CUDART_INF_F) ? 0.f : expf(a - mx);
+            }
+            row[j] = e;  // rows S..Sp-1 are zero: phase 3 reads float4
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) inv[r] = 1.f / sum;  // all keys masked -> inf * 0 = NaN, like torch's softmax of all -inf
+    }
+    __syncthreads();
+    // phase 3: warp = head, lane = channel
+    float acc[NQ];
+#pragma unroll
+    for (int s = 0; s < NQ; ++s) acc[s] = 0.f;
+    const KV* vp = v + (b * S) * ldv + tid;
+    const float* prow = Ps + (warp * NQ) * Sp;
+    for (int j = 0; j < Sp; j += 4) {
+        float vj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vj[u] = (j + u < S) ? to_f32(vp[(int64_t)(j + u) * ldv]) : 0.f;
+#pragma unroll
+        for (int s = 0; s < NQ; ++s) {
+            const float4 pp = *reinterpret_cast<const float4*>(prow + s * Sp + j);
+            acc[s] = fmaf(pp.x, vj[0], acc[s]);
+            acc[s] = fmaf(pp.y, vj[1], acc[s]);
+            acc[s] = fmaf(pp.z, vj[2], acc[s]);
+            acc[s] = fmaf(pp.w, vj[3], acc[s]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mx[i] = warp_max(mx[i]);
-    __syncwarp();
-    for (int j = lane; j < S; j += 32) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i < nq) {
-                const float a = Ps[i * S + j];
-                const float e = (a == -CUDART_INF_F) ? 0.f : expf(a - mx[i]);
-                Ps[i * S + j] = e;
-                sum[i] += e;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sum[i] = warp_sum(sum[i]);
-    __syncwarp();
-    // pass 2: P.V, lane = channel
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int j = 0; j < S; ++j) {
-        const float vj = to_f32(v[(b * S + j) * ldv + h * HD + lane]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i < nq) acc[i] = fmaf(Ps[i * S + j], vj, acc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (i < nq) o[(b * nq + i) * ldo + h * HD + lane] = acc[i] / sum[i];
+    for (int s = 0; s < NQ; ++s)
+        if (s < nq) o[(b * nq + s) * ldo + tid] = acc[s] * inv[warp * NQ + s];
 }
 
 
@@ -286,18 +310,34 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
     const int64_t b = blockIdx.x / nheads;
     const int h = blockIdx.x % nheads;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int vl = vlen[b], tl = tlen[b];
     const int64_t row0 = b * S;
 
-    // cooperative load: 4 x 16-byte chunks per row for each of Q, K, V
-    for (int i = threadIdx.x; i < Sp * 4; i += blockDim.x) {
+    // cooperative load: 4 x 16-byte chunks per row for each of Q, K, V.  The trip count is a compile-time constant
+    // and the loads of ALL iterations are issued before anything is consumed, so one round of global-memory
+    // latency covers the whole tile (the CTA is short-lived: ncu showed a third of its life in this phase when the
+    // loads of each iteration waited for the previous one)
+    constexpr int LOAD_ITERS = (NB * 8 * 4 + ATT_WARPS * 32 - 1) / (ATT_WARPS * 32);
+    uint4 q4[LOAD_ITERS], k4[LOAD_ITERS], v4[LOAD_ITERS];
+#pragma unroll
+    for (int it = 0; it < LOAD_ITERS; ++it) {
+        const int i = threadIdx.x + it * (ATT_WARPS * 32);
         const int r = i >> 2, c = i & 3;
-        uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+        q4[it] = make_uint4(0, 0, 0, 0);
+        k4[it] = q4[it];
+        v4[it] = q4[it];
         if (r < S) {
             const __half* qrow = qk + (row0 + r) * ldqk + h * HD + c * 8;
-            q4 = *reinterpret_cast<const uint4*>(qrow);
-            k4 = *reinterpret_cast<const uint4*>(qrow + d_model);
-            v4 = *reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + h * HD + c * 8);
+            q4[it] = *reinterpret_cast<const uint4*>(qrow);
+            k4[it] = *reinterpret_cast<const uint4*>(qrow + d_model);
+            v4[it] = *reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + h * HD + c * 8);
+        }
+    }
+    const int vl = vlen[b], tl = tlen[b];
+#pragma unroll
+    for (int it = 0; it < LOAD_ITERS; ++it) {
+        const int i = threadIdx.x + it * (ATT_WARPS * 32);
+        const int r = i >> 2, c = i & 3;
+        if (i < Sp * 4) {
             if (posqk != nullptr && r < Lv) {
                 // q = (src + pos) Wq^T + bq = (src Wq^T + bq) + pos Wq^T: the position term comes from a per-layer
                 // table indexed by (valid length, row), so no position-added copy of the activations exists
@@ -306,8 +346,8 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 const float4 pq1 = __ldg(reinterpret_cast<const float4*>(pr) + 1);
                 const float4 pk0 = __ldg(reinterpret_cast<const float4*>(pr + d_model));
                 const float4 pk1 = __ldg(reinterpret_cast<const float4*>(pr + d_model) + 1);
-                __half2* qh = reinterpret_cast<__half2*>(&q4);
-                __half2* kh = reinterpret_cast<__half2*>(&k4);
+                __half2* qh = reinterpret_cast<__half2*>(&q4[it]);
+                __half2* kh = reinterpret_cast<__half2*>(&k4[it]);
                 float2 f;
                 f = __half22float2(qh[0]); qh[0] = __floats2half2_rn(f.x + pq0.x, f.y + pq0.y);
                 f = __half22float2(qh[1]); qh[1] = __floats2half2_rn(f.x + pq0.z, f.y + pq0.w);
@@ -318,10 +358,10 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 f = __half22float2(kh[2]); kh[2] = __floats2half2_rn(f.x + pk1.x, f.y + pk1.y);
                 f = __half22float2(kh[3]); kh[3] = __floats2half2_rn(f.x + pk1.z, f.y + pk1.w);
             }
+            *reinterpret_cast<uint4*>(Qs + r * QK_PAD + c * 8) = q4[it];
+            *reinterpret_cast<uint4*>(Ks + r * QK_PAD + c * 8) = k4[it];
+            *reinterpret_cast<uint4*>(Vs + r * QK_PAD + c * 8) = v4[it];
         }
-        *reinterpret_cast<uint4*>(Qs + r * QK_PAD + c * 8) = q4;
-        *reinterpret_cast<uint4*>(Ks + r * QK_PAD + c * 8) = k4;
-        *reinterpret_cast<uint4*>(Vs + r * QK_PAD + c * 8) = v4;
     }
     __syncthreads();
 
@@ -347,29 +387,36 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 ldsm_x4(bk, Ks + (jb * 8 + l8) * QK_PAD + lq * 8);
                 mma_16816(sc[jb], aq[0], bk[0], bk[1]);
                 mma_16816(sc[jb], aq[1], bk[2], bk[3]);
+                // key-padding mask: only key blocks that touch a padded region pay for it (warp-uniform test)
+                const int k0 = jb * 8, k1 = k0 + 8;
+                const bool all_valid = (k1 <= vl) || (k1 <= Lv + tl && (vl == Lv || k0 >= Lv));
+                if (!all_valid) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int key = jb * 8 + t4 * 2 + e;
-                    const bool ok = key < S && key_valid(key, Lv, vl, tl);
-                    sc[jb][e] = ok ? sc[jb][e] * sl2 : -CUDART_INF_F;
-                    sc[jb][2 + e] = ok ? sc[jb][2 + e] * sl2 : -CUDART_INF_F;
-                    m_lo = fmaxf(m_lo, sc[jb][e]);
-                    m_hi = fmaxf(m_hi, sc[jb][2 + e]);
+                    for (int e = 0; e < 2; ++e) {
+                        const int key = k0 + t4 * 2 + e;
+                        const bool ok = key < S && key_valid(key, Lv, vl, tl);
+                        sc[jb][e] = ok ? sc[jb][e] : -CUDART_INF_F;
+                        sc[jb][2 + e] = ok ? sc[jb][2 + e] : -CUDART_INF_F;
+                    }
                 }
+                m_lo = fmaxf(m_lo, fmaxf(sc[jb][0], sc[jb][1]));
+                m_hi = fmaxf(m_hi, fmaxf(sc[jb][2], sc[jb][3]));
             }
         }
         m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
         m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
         m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
         m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+        // p = exp(scale * (s - max)) = exp2(s * sl2 - max * sl2): one FFMA + EX2 per score (exp2(-inf) = 0 for masked keys)
+        const float o_lo = -m_lo * sl2, o_hi = -m_hi * sl2;
         float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             if (jb < nkb) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float p0 = fast_exp2(sc[jb][e] - m_lo);      // exp2(-inf) = 0 for masked keys
-                    const float p1 = fast_exp2(sc[jb][2 + e] - m_hi);
+                    const float p0 = fast_exp2(fmaf(sc[jb][e], sl2, o_lo));
+                    const float p1 = fast_exp2(fmaf(sc[jb][2 + e], sl2, o_hi));
                     sc[jb][e] = p0;
                     sc[jb][2 + e] = p1;
                     s_lo += p0;
@@ -457,20 +504,32 @@ int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk,
                         cudaStream_t s) {
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
-    CONE_REQUIRE(nq <= 8 && S <= MAX_S, "dec_cross_attention: unsupported nq=%d S=%d", nq, S);
+    CONE_REQUIRE(nq >= 1 && nq <= 8 && S <= MAX_S && nheads == 8, "dec_cross_attention: unsupported nq=%d S=%d heads=%d", nq,
+                 S, nheads);
     CONE_REQUIRE((ldk & 7) == 0, "dec_cross_attention: ldk must be a multiple of 8");
-    const int warps = 4;
-    const size_t smem = sizeof(float) * warps * (8 * HD + 8 * (size_t)S);
-    ProfScope ps(s, P_DEC_ATTN, 4.0 * (double)B * nheads * nq * S * HD, 8.0 * (double)B * S * nheads * HD);
+    const int NQ = nq <= 5 ? 5 : 8;
+    const int Sp = (S + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)NQ * 8 * XQ_PAD + (size_t)8 * NQ * Sp + 8 * NQ);
+    ProfScope ps(s, P_DEC_ATTN, 4.0 * (double)B * nheads * nq * S * HD, (kv_f16 ? 4.0 : 8.0) * (double)B * S * nheads * HD);
+    const unsigned grid = (unsigned)B;
+#define CONE_XATT(KV, NQV)                                                                                              \
+    do {                                                                                                                \
+        static bool attr = false;                                                                                       \
+        if (!attr) {                                                                                                    \
+            CONE_CUDA(cudaFuncSetAttribute(dec_cross_attention_kernel<KV, NQV>,                                         \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                   \
+            attr = true;                                                                                                \
+        }                                                                                                               \
+        dec_cross_attention_kernel<KV, NQV><<<grid, 256, smem, s>>>(q, ldq, static_cast<const KV*>(k), ldk,             \
+                                                                    static_cast<const KV*>(v), ldv, o, ldo, vlen, tlen, \
+                                                                    nq, Lv, Lt, posk, ldposk, table_lv);                \
+    } while (0)
     if (kv_f16) {
-        dec_cross_attention_kernel<__half><<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
-            q, ldq, static_cast<const __half*>(k), ldk, static_cast<const __half*>(v), ldv, o, ldo, vlen, tlen, B, nq, Lv,
-            Lt, nheads, posk, ldposk, table_lv);
+        if (NQ == 5) CONE_XATT(__half, 5); else CONE_XATT(__half, 8);
     } else {
-        dec_cross_attention_kernel<float><<<(unsigned)cdiv64(B * nheads, warps), warps * 32, smem, s>>>(
-            q, ldq, static_cast<const float*>(k), ldk, static_cast<const float*>(v), ldv, o, ldo, vlen, tlen, B, nq, Lv, Lt,
-            nheads, posk, ldposk, table_lv);
+        if (NQ == 5) CONE_XATT(float, 5); else CONE_XATT(float, 8);
     }
+#undef CONE_XATT
     CONE_LAUNCH_CHECK("dec_cross_attention");
     return CONE_OK;
 }

@@ -164,25 +164,43 @@ __device__ __forceinline__ void add_bias64(float* x, const float* bias) {
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quarter; each takes half of the tile's columns
 
-template <int BN>
+// WRES ("weights resident", K = 4 k-blocks = 256): the CTA is bound to ONE n-tile, its whole [BN x 256] fp16 weight
+// tile (128 KB) is loaded once and stays in shared memory, and the ring carries only A (16 KB per k-block, 4 stages).
+// Why: ncu showed every K = 256 GEMM of the model stuck at ~1450 cycles per k-block against 512 cycles of MMA work,
+// whatever the epilogue did: with A + W in a 3-stage ring only 144 KB per SM were in flight against ~2 us of loaded
+// memory latency, and two thirds of those bytes were the same weight tile streamed again for every M tile.
+constexpr int WRES_KBLOCKS = 4;
+constexpr int WRES_STAGES = 4;
+
+template <int BN, bool WRES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC16,
                const __grid_constant__ CUtensorMap tmC32, TcEpilogue ep, int64_t M, int N, int K) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int HALF = BN / 2;  // columns per epilogue warp
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int NSTAGE = WRES ? WRES_STAGES : STAGES;
+    constexpr int B_RING = WRES ? WRES_KBLOCKS * B_BYTES : NSTAGE * B_BYTES;  // resident tile or ring
+    constexpr int N_BOX = WRES ? EPI_WARPS : 2 * EPI_WARPS;                  // WRES: residual and result share a box
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem;
+    if (WRES) {  // no room for alignment slack: the dynamic window must already be 1 KB aligned
+        smem = smem_raw;
+        if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    } else {
+        smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    }
     uint8_t* sA = smem;
-    uint8_t* sB = sA + STAGES * A_BYTES;
-    uint8_t* sOut = sB + STAGES * B_BYTES;           // one TMA-store box per epilogue warp
-    uint8_t* sRes = sOut + EPI_WARPS * BOX_BYTES;    // one TMA-loaded residual box per epilogue warp
-    uint64_t* full = reinterpret_cast<uint64_t*>(sRes + EPI_WARPS * BOX_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;
+    uint8_t* sB = sA + NSTAGE * A_BYTES;
+    uint8_t* sOut = sB + B_RING;                     // one TMA-store box per epilogue warp
+    uint8_t* sRes = WRES ? sOut : sOut + EPI_WARPS * BOX_BYTES;  // one TMA-loaded residual box per epilogue warp
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + N_BOX * BOX_BYTES);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* tfull = empty + NSTAGE;
     uint64_t* tempty = tfull + 2;
     uint64_t* rfull = tempty + 2;  // one per epilogue warp
-    float2* ln_part = reinterpret_cast<float2*>(rfull + EPI_WARPS);  // [EPI_WARPS][32] partial (sum, sum of squares)
+    uint64_t* wfull = rfull + EPI_WARPS;
+    float2* ln_part = reinterpret_cast<float2*>(wfull + 1);  // [EPI_WARPS][32] partial (sum, sum of squares)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_part + EPI_WARPS * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,14 +208,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_tiles = N / BN;
     const int64_t tiles = m_tiles * n_tiles;
     const int num_k = K / BK;
+    // tile walk: WRES -> this CTA's n-tile is fixed and t runs over M tiles; otherwise t runs over all (m, n) tiles
+    const int n_fixed = WRES ? (int)(blockIdx.x % n_tiles) : 0;
+    const int64_t t_begin = WRES ? (int64_t)(blockIdx.x / n_tiles) : (int64_t)blockIdx.x;
+    const int64_t t_step = WRES ? (int64_t)(gridDim.x / n_tiles) : (int64_t)gridDim.x;
+    const int64_t t_end = WRES ? m_tiles : tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
+        mbar_init(wfull, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], EPI_WARPS * 32);
@@ -220,14 +244,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {  // ---------------------------------------------------------------- TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * BN;
+            if (WRES) {  // the weight tile of this CTA's n-tile, once
+                mbar_expect_tx(wfull, WRES_KBLOCKS * B_BYTES);
+                for (int kb = 0; kb < WRES_KBLOCKS; ++kb) tma_load_2d(sB + kb * B_BYTES, &tmB, wfull, kb * BK, n_fixed * BN);
+            }
+            for (int64_t t = t_begin; t < t_end; t += t_step) {
+                const int m0 = (int)(WRES ? t : t / n_tiles) * BM, n0 = (WRES ? n_fixed : (int)(t % n_tiles)) * BN;
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+                    mbar_expect_tx(&full[stage], WRES ? A_BYTES : A_BYTES + B_BYTES);
                     tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], kb * BK, m0);
-                    tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], kb * BK, n0);
-                    if (++stage == STAGES) {
+                    if (!WRES) tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == NSTAGE) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -242,7 +270,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            if (WRES) mbar_wait(wfull, 0);
+            for (int64_t t = t_begin; t < t_end; t += t_step) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -250,7 +279,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + (WRES ? kb : stage) * B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = smem_desc_sw128(a_addr + k * UMMA_K * 2);
@@ -258,7 +287,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         umma_f16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
-                    if (++stage == STAGES) {
+                    if (++stage == NSTAGE) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -283,9 +312,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
 
-        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int64_t m0 = (t / n_tiles) * BM;
-            const int n0 = (int)(t % n_tiles) * BN + half * HALF;  // first column of this warp's half
+        for (int64_t t = t_begin; t < t_end; t += t_step) {
+            const int64_t m0 = (WRES ? t : t / n_tiles) * BM;
+            const int n0 = (WRES ? n_fixed : (int)(t % n_tiles)) * BN + half * HALF;  // first column of this warp's half
             const int row0 = (int)m0 + quarter * 32;               // first row of this warp's 32 rows
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -296,7 +325,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             auto load_sub = [&](int c, float* x) {
                 const int sub = (c >> 5) & 1;
                 if (ep.has_r16 && sub == 0 && lane == 0) {
-                    if (ep.has_c32) tma_store_wait_read<0>();  // res_box doubles as the fp32 store box (see below)
+                    // res_box doubles as the fp32 store box (see below) and, in WRES mode, as the result box
+                    if (WRES || ep.has_c32) tma_store_wait_read<0>();
                     mbar_expect_tx(rbar, BOX_BYTES);
                     tma_load_2d(res_box, &tmR, rbar, n0 + c, row0);
                 }
@@ -510,10 +540,13 @@ int make_map(CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t
     return CONE_OK;
 }
 
-template <int BN>
+template <int BN, bool WRES>
 constexpr size_t tc_smem_bytes() {
-    return 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2) + 16 * BOX_BYTES + 32 * sizeof(uint64_t) + 8 * 32 * 8 + 64;
+    constexpr size_t tail = 64 * sizeof(uint64_t) + 8 * 32 * 8 + 64;  // barriers, LayerNorm partials, TMEM slot
+    return WRES ? (size_t)WRES_STAGES * A_BYTES + (size_t)WRES_KBLOCKS * BN * BK * 2 + 8 * BOX_BYTES + tail
+                : 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2) + 16 * BOX_BYTES + tail;
 }
+static_assert(tc_smem_bytes<256, true>() <= 232448, "weights-resident layout exceeds 227 KB");
 
 }  // namespace
 
@@ -621,31 +654,39 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     ep.ln_g = g.ln_g;
     ep.ln_b = g.ln_b;
     ep.ln_eps = 1e-5f;
-    const int64_t tiles = cdiv64(g.M, BM) * (g.N / w->BN);
-    const unsigned grid = (unsigned)(tiles < t->num_sms ? tiles : t->num_sms);
+    const int64_t m_tiles = cdiv64(g.M, BM);
+    const int n_tiles = g.N / w->BN;
+    const int64_t tiles = m_tiles * n_tiles;
+    // weights-resident variant: K = 256, BN = 256, at most num_sms / n_tiles CTAs per n-tile
+    const bool wres = w->BN == 256 && g.K == WRES_KBLOCKS * BK && n_tiles <= t->num_sms && !(g.C16 && g.C32);
+    unsigned grid = (unsigned)(tiles < t->num_sms ? tiles : t->num_sms);
+    if (wres) {
+        const int64_t per_n = t->num_sms / n_tiles;
+        grid = (unsigned)((m_tiles < per_n ? m_tiles : per_n) * n_tiles);
+    }
     const double mn = (double)g.M * g.N;
     ProfScope ps(s, P_GEMM_TC, 2.0 * mn * g.K,
                  2.0 * ((double)g.M * g.K + (double)g.N * g.K) + (g.C32 ? 4.0 : 0.0) * mn + (g.C16 ? 2.0 : 0.0) * mn +
                      (g.R32 ? 4.0 : 0.0) * mn + (g.R16 ? 2.0 : 0.0) * mn);
-    if (w->BN == 256) {
-        static bool attr = false;
-        if (!attr) {
-            CONE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)tc_smem_bytes<256>()));
-            attr = true;
-        }
-        tc_gemm_kernel<256><<<grid, TC_THREADS, tc_smem_bytes<256>(), s>>>(mapA, w->map, mapR, mapC16, mapC32, ep, g.M,
-                                                                           g.N, g.K);
+#define CONE_TC_LAUNCH(BNV, WR)                                                                                         \
+    do {                                                                                                                \
+        static bool attr = false;                                                                                       \
+        if (!attr) {                                                                                                    \
+            CONE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BNV, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                           (int)tc_smem_bytes<BNV, WR>()));                                             \
+            attr = true;                                                                                                \
+        }                                                                                                               \
+        tc_gemm_kernel<BNV, WR><<<grid, TC_THREADS, tc_smem_bytes<BNV, WR>(), s>>>(mapA, w->map, mapR, mapC16, mapC32,  \
+                                                                                  ep, g.M, g.N, g.K);                   \
+    } while (0)
+    if (wres) {
+        CONE_TC_LAUNCH(256, true);
+    } else if (w->BN == 256) {
+        CONE_TC_LAUNCH(256, false);
     } else {
-        static bool attr = false;
-        if (!attr) {
-            CONE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)tc_smem_bytes<128>()));
-            attr = true;
-        }
-        tc_gemm_kernel<128><<<grid, TC_THREADS, tc_smem_bytes<128>(), s>>>(mapA, w->map, mapR, mapC16, mapC32, ep, g.M,
-                                                                           g.N, g.K);
+        CONE_TC_LAUNCH(128, false);
     }
+#undef CONE_TC_LAUNCH
     CONE_LAUNCH_CHECK("tc_gemm");
     return CONE_OK;
 }

@@ -26,7 +26,7 @@ def eng():
 
 
 @pytest.mark.parametrize("M,N,K", [(100, 256, 256), (128, 256, 64), (5000, 512, 256), (300, 1024, 256), (4097, 256, 1024),
-                                   (129, 768, 256), (33000, 256, 768), (257, 128, 128)])
+                                   (129, 768, 256), (33000, 256, 768), (257, 128, 128), (257, 256, 128), (128 * 148 * 3 + 5, 1024, 256), (128 * 300 + 77, 768, 256)])
 def test_tc_gemm_vs_torch_fp32(eng, M, N, K):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(DEV)
