@@ -18,6 +18,7 @@
 // fp16 (11 significant bits) rather than bf16: the reference comparison needs 1e-3 on spans and scores, which
 // bf16 operands miss by 3-5x (measured by emulation); conversions saturate.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include <map>
@@ -122,6 +123,25 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// 32 lanes x 64 columns
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -153,6 +173,11 @@ struct TcEpilogue {
 // Byte offset of 16-byte unit `u` of row `r` in a [rows x 128 B] box with the TMA 128-byte swizzle.
 __device__ __forceinline__ uint32_t sw128(int r, int u) { return (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)); }
 
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __device__ __forceinline__ void add_bias64(float* x, const float* bias) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -171,20 +196,55 @@ constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quarter; each takes hal
 // memory latency, and two thirds of those bytes were the same weight tile streamed again for every M tile.
 constexpr int WRES_KBLOCKS = 4;
 constexpr int WRES_STAGES = 4;
+constexpr int FAST_STAGES = 4;  // A + W ring depth of the streamlined epilogues when the weights are not resident
 
-template <int BN, bool WRES>
+// Epilogue variants.  The shape that carries most of the model's 2.9 M rows is compile-time specialised (no flag
+// tests, 64-column steps, accumulator released right after the second TMEM load, one staging box per warp):
+//   EPI_PLAIN16: bias (+ReLU) -> fp16                                         (QKV, FFN1, decoder K|V projections)
+//   EPI_GENERIC: every flag at run time: residual through TMA boxes, LayerNorm over the 256-wide row (out_proj,
+//                FFN2), fp32 in/out decoder-side GEMMs, cone_linear, BN = 128
+// (A specialised LayerNorm epilogue that read the residual with per-row global loads and kept the 128 columns of a
+// row in registers was measured 20-50 % SLOWER than the generic TMA-box one and was dropped: profiles/r01_notes.md.)
+// ncu on the generic epilogue at 2 warps per scheduler: ~9 issue cycles per instruction, a third of the stalls in
+// LDCU -> UISETP -> BRA chains of the run-time flags, another tenth on bias loads issued after the TMEM wait.
+enum { EPI_PLAIN16 = 0, EPI_GENERIC = 2 };
+
+// 64 fp32 values of one row -> fp16 -> this lane's row of a [32 x 64] 128-byte-swizzled box -> one TMA store
+__device__ __forceinline__ void store_box16(const float* x, uint8_t* box, const CUtensorMap* map, int col, int row0,
+                                            int lane) {
+    if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the box
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        uint4 v;
+        v.x = pack_h2(x[8 * u], x[8 * u + 1]);
+        v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
+        v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
+        v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
+        *reinterpret_cast<uint4*>(box + sw128(lane, u)) = v;
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map, box, col, row0);
+        tma_store_commit();
+    }
+}
+
+template <int BN, bool WRES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC16,
                const __grid_constant__ CUtensorMap tmC32, TcEpilogue ep, int64_t M, int N, int K) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int HALF = BN / 2;  // columns per epilogue warp
-    constexpr int NSTAGE = WRES ? WRES_STAGES : STAGES;
+    constexpr bool FAST = MODE != EPI_GENERIC;
+    constexpr int NSTAGE = WRES ? WRES_STAGES : (FAST ? FAST_STAGES : STAGES);
     constexpr int B_RING = WRES ? WRES_KBLOCKS * B_BYTES : NSTAGE * B_BYTES;  // resident tile or ring
-    constexpr int N_BOX = WRES ? EPI_WARPS : 2 * EPI_WARPS;                  // WRES: residual and result share a box
+    constexpr int N_BOX = (WRES || FAST) ? EPI_WARPS : 2 * EPI_WARPS;         // one box per warp unless generic + ring
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem;
-    if (WRES) {  // no room for alignment slack: the dynamic window must already be 1 KB aligned
+    if (WRES || FAST) {  // no room for alignment slack: the dynamic window must already be 1 KB aligned
         smem = smem_raw;
         if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     } else {
@@ -224,7 +284,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(wfull, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], EPI_WARPS * 32);
+            mbar_init(&tempty[i], FAST ? EPI_WARPS : EPI_WARPS * 32);
         }
         for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&rfull[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -299,7 +359,52 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else {  // ------------------------------------------------------------------------------- epilogue
+    } else if (FAST) {  // ------------------------------------------------- epilogue, specialised (see enum above)
+        const int ew = warp - 2;       // 0..7
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        const int half = ew >> 2;      // which half of the tile's columns
+        uint8_t* box = sOut + ew * BOX_BYTES;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t t = t_begin; t < t_end; t += t_step) {
+            const int64_t m0 = (WRES ? t : t / n_tiles) * BM;
+            const int n0 = (WRES ? n_fixed : (int)(t % n_tiles)) * BN + half * HALF;  // first of this warp's 128 columns
+            const int row0 = (int)m0 + quarter * 32;                                  // first of this warp's 32 rows
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
+            auto release_acc = [&]() {  // this warp's slice of the accumulator is in registers
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            };
+            auto add_bias = [&](float* x, int c) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c) + q);
+                    x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+                }
+            };
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float x[64];
+                tmem_ld_32x64(taddr + ch * 64, x);
+                tmem_ld_wait();
+                if (ch == 1) release_acc();
+                add_bias(x, ch * 64);
+                if (ep.relu) {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                store_box16(x, box, &tmC16, n0 + ch * 64, row0, lane);
+            }
+        }
+        if (lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last bulk stores
+    } else {  // ------------------------------------------------------------------- epilogue, generic (run-time flags)
         const int ew = warp - 2;       // 0..7
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
         const int half = ew >> 2;      // which half of the tile's columns
@@ -540,13 +645,16 @@ int make_map(CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t
     return CONE_OK;
 }
 
-template <int BN, bool WRES>
+template <int BN, bool WRES, int MODE>
 constexpr size_t tc_smem_bytes() {
     constexpr size_t tail = 64 * sizeof(uint64_t) + 8 * 32 * 8 + 64;  // barriers, LayerNorm partials, TMEM slot
-    return WRES ? (size_t)WRES_STAGES * A_BYTES + (size_t)WRES_KBLOCKS * BN * BK * 2 + 8 * BOX_BYTES + tail
-                : 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2) + 16 * BOX_BYTES + tail;
+    constexpr size_t b_bytes = (size_t)BN * BK * 2;
+    if (WRES) return (size_t)WRES_STAGES * A_BYTES + WRES_KBLOCKS * b_bytes + 8 * BOX_BYTES + tail;
+    if (MODE != EPI_GENERIC) return (size_t)FAST_STAGES * (A_BYTES + b_bytes) + 8 * BOX_BYTES + tail;
+    return 1024 + (size_t)STAGES * (A_BYTES + b_bytes) + 16 * BOX_BYTES + tail;
 }
-static_assert(tc_smem_bytes<256, true>() <= 232448, "weights-resident layout exceeds 227 KB");
+static_assert(tc_smem_bytes<256, true, EPI_GENERIC>() <= 232448, "weights-resident layout exceeds 227 KB");
+static_assert(tc_smem_bytes<256, false, EPI_PLAIN16>() <= 232448, "4-stage ring layout exceeds 227 KB");
 
 }  // namespace
 
@@ -668,23 +776,26 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     ProfScope ps(s, P_GEMM_TC, 2.0 * mn * g.K,
                  2.0 * ((double)g.M * g.K + (double)g.N * g.K) + (g.C32 ? 4.0 : 0.0) * mn + (g.C16 ? 2.0 : 0.0) * mn +
                      (g.R32 ? 4.0 : 0.0) * mn + (g.R16 ? 2.0 : 0.0) * mn);
-#define CONE_TC_LAUNCH(BNV, WR)                                                                                         \
+#define CONE_TC_LAUNCH(BNV, WR, MD)                                                                                 \
     do {                                                                                                                \
         static bool attr = false;                                                                                       \
         if (!attr) {                                                                                                    \
-            CONE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BNV, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                           (int)tc_smem_bytes<BNV, WR>()));                                             \
+            CONE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BNV, WR, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)tc_smem_bytes<BNV, WR, MD>()));                                         \
             attr = true;                                                                                                \
         }                                                                                                               \
-        tc_gemm_kernel<BNV, WR><<<grid, TC_THREADS, tc_smem_bytes<BNV, WR>(), s>>>(mapA, w->map, mapR, mapC16, mapC32,  \
-                                                                                  ep, g.M, g.N, g.K);                   \
+        tc_gemm_kernel<BNV, WR, MD><<<grid, TC_THREADS, tc_smem_bytes<BNV, WR, MD>(), s>>>(                             \
+            mapA, w->map, mapR, mapC16, mapC32, ep, g.M, g.N, g.K);                                                     \
     } while (0)
-    if (wres) {
-        CONE_TC_LAUNCH(256, true);
-    } else if (w->BN == 256) {
-        CONE_TC_LAUNCH(256, false);
+    const bool plain16 = w->BN == 256 && g.C16 && !g.C32 && !g.R16 && !g.R32 && !g.ln_g && g.bias;
+    if (w->BN != 256) {
+        CONE_TC_LAUNCH(128, false, EPI_GENERIC);
+    } else if (wres) {
+        if (plain16) CONE_TC_LAUNCH(256, true, EPI_PLAIN16);
+        else CONE_TC_LAUNCH(256, true, EPI_GENERIC);
     } else {
-        CONE_TC_LAUNCH(128, false);
+        if (plain16) CONE_TC_LAUNCH(256, false, EPI_PLAIN16);
+        else CONE_TC_LAUNCH(256, false, EPI_GENERIC);
     }
 #undef CONE_TC_LAUNCH
     CONE_LAUNCH_CHECK("tc_gemm");
