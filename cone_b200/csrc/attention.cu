@@ -15,6 +15,12 @@ constexpr int HD = 32;            // head dim (hidden 256 / 8 heads)
 constexpr int MAX_S = 256;        // max keys per window
 constexpr int ENC_WARPS = 4;
 
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ bool key_valid(int j, int Lv, int vl, int tl) { return j < Lv ? (j < vl) : ((j - Lv) < tl); }
 
 __global__ void __launch_bounds__(ENC_WARPS * 32)
@@ -149,109 +155,189 @@ __device__ __forceinline__ void load_head_row(const __half* p, float* out) {
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 
-// One CTA per window, 8 warps.  Three phases, all reading K / V straight from global memory (no staging):
-//   1. scores: thread <-> (key j, head h) pairs, consecutive threads = the 8 heads of a key, so a warp reads 4 whole
-//      K rows (coalesced); the 32-wide dot products against the nq scaled queries of that head run from registers
-//      (K row chunk) x shared memory (queries, padded so the 8 heads hit distinct banks)
-//   2. masked softmax per (head, slot) row: one warp per row
-//   3. P.V: thread <-> output channel (warp = head), rows streamed 4 at a time, P read as broadcast float4
-// The previous version ran one warp per (window, head) end to end and was latency-bound at 5x its HBM time.
-constexpr int XQ_PAD = 36;  // floats per (slot, head) query row in smem: 16-byte aligned, heads 144 B apart
+// One CTA per window, 8 warps, K / V read straight from global memory with every load of a batch of rows in flight
+// before the first is consumed (the earlier versions — one warp per (window, head), then one thread per (key, head) —
+// waited for one memory round trip per row and ran at 5x their HBM time).
+//   lane = (head h = lane / 4, part = lane % 4): the lane owns dims [8 part, 8 part + 8) of head h, so the 32 lanes of
+//   a warp read one whole 256-wide K (or V) row per instruction, fully coalesced; warp w takes rows w, w + 8, ...
+//   1. scores: the lane's slice of the nq scaled queries lives in registers; partial dot products are reduced over the
+//      4 lanes of a head with two shuffles; rows are processed XB at a time
+//   2. masked softmax per (head, slot) row: one warp per row of the score matrix in shared memory
+//   3. P.V: each lane accumulates its 8 channels over its warp's rows (VB rows in flight), then the 8 warps' partial
+//      sums are added through shared memory
+template <typename KV>
+struct XChunk;  // 8 consecutive elements of a K / V row
+template <>
+struct XChunk<__half> {
+    uint4 v;
+    __device__ __forceinline__ void load(const __half* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void to_float(float* o) const {
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            o[2 * e] = f.x;
+            o[2 * e + 1] = f.y;
+        }
+    }
+};
+template <>
+struct XChunk<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = reinterpret_cast<const float4*>(p)[0];
+        b = reinterpret_cast<const float4*>(p)[1];
+    }
+    __device__ __forceinline__ void to_float(float* o) const {
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+        o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+};
 
 template <typename KV, int NQ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dec_cross_attention_kernel(const float* __restrict__ q, int64_t ldq, const KV* __restrict__ k, int64_t ldk,
                            const KV* __restrict__ v, int64_t ldv, float* __restrict__ o, int64_t ldo,
                            const int32_t* __restrict__ vlen, const int32_t* __restrict__ tlen, int nq, int Lv,
                            int Lt, const float* __restrict__ posk, int64_t ldposk, int table_lv) {
     constexpr int H = 8;
+    constexpr int XB = sizeof(KV) == 2 ? 6 : 3;  // rows in flight per warp, phase 1 (K chunk + 2 position float4 each)
+    constexpr int VB = sizeof(KV) == 2 ? 10 : 5; // rows in flight per warp, phase 3
     extern __shared__ __align__(16) float xsmem[];
     const int S = Lv + Lt;
     const int Sp = (S + 3) & ~3;
-    float* Qs = xsmem;                   // [NQ][H][XQ_PAD]
-    float* Ps = Qs + NQ * H * XQ_PAD;    // [H][NQ][Sp]
+    float* Ps = xsmem;                   // [H][NQ][Sp]
     float* inv = Ps + H * NQ * Sp;       // [H][NQ]
+    float* red = inv + H * NQ;           // [8 warps][NQ * 8][32 lanes]
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int vl = vlen[b], tl = tlen[b];
+    const int h = lane >> 2, part = lane & 3;
+    const int col = h * HD + part * 8;   // this lane's 8 columns of a 256-wide row
     const float scale = 0.17677669529663687f;
-    for (int i = tid; i < NQ * H * HD; i += 256) {
-        const int c = i % HD, h = (i / HD) % H, s = i / (HD * H);
-        Qs[(s * H + h) * XQ_PAD + c] = s < nq ? q[(b * nq + s) * ldq + h * HD + c] * scale : 0.f;
+    float qv[NQ][8];
+#pragma unroll
+    for (int s = 0; s < NQ; ++s) {
+        if (s < nq) {
+            const float4 a = *reinterpret_cast<const float4*>(q + (b * nq + s) * ldq + col);
+            const float4 c = *reinterpret_cast<const float4*>(q + (b * nq + s) * ldq + col + 4);
+            qv[s][0] = a.x * scale; qv[s][1] = a.y * scale; qv[s][2] = a.z * scale; qv[s][3] = a.w * scale;
+            qv[s][4] = c.x * scale; qv[s][5] = c.y * scale; qv[s][6] = c.z * scale; qv[s][7] = c.w * scale;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) qv[s][e] = 0.f;
+        }
     }
-    __syncthreads();
+    const int vl = vlen[b], tl = tlen[b];
     // phase 1
-    for (int idx = tid; idx < S * H; idx += 256) {
-        const int j = idx >> 3, h = idx & 7;
-        const bool ok = key_valid(j, Lv, vl, tl);
-        float kr[HD];
-        load_head_row(k + (b * S + j) * ldk + h * HD, kr);
-        if (posk != nullptr && j < Lv) {  // k = memory Wk^T + bk + pos Wk^T (table row of (valid length, j))
-            const float4* pr = reinterpret_cast<const float4*>(posk + ((int64_t)vl * table_lv + j) * ldposk + h * HD);
+    for (int base = warp; base < S; base += 8 * XB) {
+        XChunk<KV> kc[XB];
+        float4 p0[XB], p1[XB];
 #pragma unroll
-            for (int c = 0; c < HD / 4; ++c) {
-                const float4 p = __ldg(pr + c);
-                kr[4 * c] += p.x; kr[4 * c + 1] += p.y; kr[4 * c + 2] += p.z; kr[4 * c + 3] += p.w;
+        for (int r = 0; r < XB; ++r) {
+            const int j = base + 8 * r;
+            p0[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            p1[r] = p0[r];
+            if (j < S) {
+                kc[r].load(k + (b * S + j) * ldk + col);
+                if (posk != nullptr && j < Lv) {  // k = memory Wk^T + bk + pos Wk^T (table row of (valid length, j))
+                    const float4* pr = reinterpret_cast<const float4*>(posk + ((int64_t)vl * table_lv + j) * ldposk + col);
+                    p0[r] = __ldg(pr);
+                    p1[r] = __ldg(pr + 1);
+                }
             }
         }
 #pragma unroll
-        for (int s = 0; s < NQ; ++s) {
-            const float4* qr = reinterpret_cast<const float4*>(Qs + (s * H + h) * XQ_PAD);
-            float a = 0.f;
+        for (int r = 0; r < XB; ++r) {
+            const int j = base + 8 * r;
+            if (j < S) {  // warp-uniform
+                float kr[8];
+                kc[r].to_float(kr);
+                kr[0] += p0[r].x; kr[1] += p0[r].y; kr[2] += p0[r].z; kr[3] += p0[r].w;
+                kr[4] += p1[r].x; kr[5] += p1[r].y; kr[6] += p1[r].z; kr[7] += p1[r].w;
+                const bool ok = key_valid(j, Lv, vl, tl);
 #pragma unroll
-            for (int c = 0; c < HD / 4; ++c) {
-                const float4 qq = qr[c];
-                a = fmaf(qq.x, kr[4 * c], a);
-                a = fmaf(qq.y, kr[4 * c + 1], a);
-                a = fmaf(qq.z, kr[4 * c + 2], a);
-                a = fmaf(qq.w, kr[4 * c + 3], a);
+                for (int s = 0; s < NQ; ++s) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) a = fmaf(qv[s][e], kr[e], a);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    if ((s & 3) == part) Ps[(h * NQ + s) * Sp + j] = ok ? a : -CUDART_INF_F;
+                }
             }
-            Ps[(h * NQ + s) * Sp + j] = ok ? a : -CUDART_INF_F;
         }
     }
     __syncthreads();
-    // phase 2
+    // phase 2: each lane keeps its (at most 8) scores of the row in registers
     for (int r = warp; r < H * NQ; r += 8) {
         float* row = Ps + r * Sp;
+        float a[MAX_S / 32];
         float mx = -CUDART_INF_F;
-        for (int j = lane; j < S; j += 32) mx = fmaxf(mx, row[j]);
+#pragma unroll
+        for (int t = 0; t < MAX_S / 32; ++t) {
+            const int j = lane + 32 * t;
+            a[t] = j < S ? row[j] : -CUDART_INF_F;
+            mx = fmaxf(mx, a[t]);
+        }
         mx = warp_max(mx);
         float sum = 0.f;
-        for (int j = lane; j < Sp; j += 32) {
-            float e = 0.f;
-            if (j < S) {
-                const float a = row[j];
-                e = (a == -CUDART_INF_F) ? 0.f : expf(a - mx);
+#pragma unroll
+        for (int t = 0; t < MAX_S / 32; ++t) {
+            const int j = lane + 32 * t;
+            float e;
+            if (sizeof(KV) == 2) {  // reduced-precision mode: exp2 with the hardware approximation (2^-22 relative)
+                e = fast_exp2((a[t] - mx) * 1.4426950408889634f);  // exp2(-inf) = 0 for masked keys
+            } else {
+                e = (a[t] == -CUDART_INF_F) ? 0.f : expf(a[t] - mx);
             }
-            row[j] = e;  // rows S..Sp-1 are zero: phase 3 reads float4
+            if (j < Sp) row[j] = e;  // columns S..Sp-1 become 0
             sum += e;
         }
         sum = warp_sum(sum);
-        if (lane == 0) inv[r] = 1.f / sum;  // all keys masked -> inf * 0 = NaN, like torch's softmax of all -inf
+        if (lane == 0) inv[r] = 1.f / sum;  // all keys masked -> NaN, like torch's softmax of all -inf
     }
     __syncthreads();
-    // phase 3: warp = head, lane = channel
-    float acc[NQ];
+    // phase 3
+    float acc[NQ][8];
 #pragma unroll
-    for (int s = 0; s < NQ; ++s) acc[s] = 0.f;
-    const KV* vp = v + (b * S) * ldv + tid;
-    const float* prow = Ps + (warp * NQ) * Sp;
-    for (int j = 0; j < Sp; j += 4) {
-        float vj[4];
+    for (int s = 0; s < NQ; ++s)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) vj[u] = (j + u < S) ? to_f32(vp[(int64_t)(j + u) * ldv]) : 0.f;
+        for (int e = 0; e < 8; ++e) acc[s][e] = 0.f;
+    for (int base = warp; base < S; base += 8 * VB) {
+        XChunk<KV> vc[VB];
 #pragma unroll
-        for (int s = 0; s < NQ; ++s) {
-            const float4 pp = *reinterpret_cast<const float4*>(prow + s * Sp + j);
-            acc[s] = fmaf(pp.x, vj[0], acc[s]);
-            acc[s] = fmaf(pp.y, vj[1], acc[s]);
-            acc[s] = fmaf(pp.z, vj[2], acc[s]);
-            acc[s] = fmaf(pp.w, vj[3], acc[s]);
+        for (int r = 0; r < VB; ++r) {
+            const int j = base + 8 * r;
+            if (j < S) vc[r].load(v + (b * S + j) * ldv + col);
+        }
+#pragma unroll
+        for (int r = 0; r < VB; ++r) {
+            const int j = base + 8 * r;
+            if (j < S) {
+                float vr[8];
+                vc[r].to_float(vr);
+#pragma unroll
+                for (int s = 0; s < NQ; ++s) {
+                    const float p = Ps[(h * NQ + s) * Sp + j];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[s][e] = fmaf(p, vr[e], acc[s][e]);
+                }
+            }
         }
     }
 #pragma unroll
     for (int s = 0; s < NQ; ++s)
-        if (s < nq) o[(b * nq + s) * ldo + tid] = acc[s] * inv[warp * NQ + s];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[(warp * NQ * 8 + s * 8 + e) * 32 + lane] = acc[s][e];
+    __syncthreads();
+    // each warp finishes NQ of the NQ * 8 (slot, element) pairs: lane-contiguous reads, no bank conflicts
+    for (int kk = warp * NQ; kk < (warp + 1) * NQ; ++kk) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[(w * NQ * 8 + kk) * 32 + lane];
+        const int s = kk >> 3, e = kk & 7;
+        if (s < nq) o[(b * nq + s) * ldo + col + e] = t * inv[h * NQ + s];
+    }
 }
 
 
@@ -285,11 +371,6 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ float fast_exp2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 
 template <int NB>
@@ -509,7 +590,7 @@ int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk,
     CONE_REQUIRE((ldk & 7) == 0, "dec_cross_attention: ldk must be a multiple of 8");
     const int NQ = nq <= 5 ? 5 : 8;
     const int Sp = (S + 3) & ~3;
-    const size_t smem = sizeof(float) * ((size_t)NQ * 8 * XQ_PAD + (size_t)8 * NQ * Sp + 8 * NQ);
+    const size_t smem = sizeof(float) * ((size_t)8 * NQ * Sp + 8 * NQ + (size_t)8 * NQ * 8 * 32);
     ProfScope ps(s, P_DEC_ATTN, 4.0 * (double)B * nheads * nq * S * HD, (kv_f16 ? 4.0 : 8.0) * (double)B * S * nheads * HD);
     const unsigned grid = (unsigned)B;
 #define CONE_XATT(KV, NQV)                                                                                              \
@@ -517,7 +598,7 @@ int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk,
         static bool attr = false;                                                                                       \
         if (!attr) {                                                                                                    \
             CONE_CUDA(cudaFuncSetAttribute(dec_cross_attention_kernel<KV, NQV>,                                         \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));                   \
             attr = true;                                                                                                \
         }                                                                                                               \
         dec_cross_attention_kernel<KV, NQV><<<grid, 256, smem, s>>>(q, ldq, static_cast<const KV*>(k), ldk,             \

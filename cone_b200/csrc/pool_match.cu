@@ -37,11 +37,21 @@ span_mean_pool_kernel(const float* __restrict__ frames, int64_t n_frames, const 
     const int nv = Dv >> 2;
     for (int c = threadIdx.x; c < nv; c += blockDim.x) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = start; r < vend; ++r) {
-            const int64_t fr = base + r;
-            if (fr >= n_frames) break;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(frames + fr * Dv) + c);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        // rows are summed in order (start, start+1, ...) as the reference's mean does; 8 loads are in flight at a
+        // time so the column is not one memory round trip per row
+        const int64_t last = (base + vend < n_frames ? base + vend : n_frames) - base;  // rows past the tensor end: none
+        for (int r = start; r < last; r += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = (r + u < last) ? __ldg(reinterpret_cast<const float4*>(frames + (base + r + u) * Dv) + c)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (r + u < last) {
+                    acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+                }
+            }
         }
         float4 o;
         if (n > 0) {
