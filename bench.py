@@ -180,6 +180,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = PRESETS[args.config]
