@@ -103,6 +103,7 @@ struct cone_weights {
     float* pos_proj = nullptr;
     std::vector<float*> pos_qk;
     float* pos_kdec = nullptr;
+    uint16_t* pos_kdec16 = nullptr;  // fp16 copy for the mma.sync cross-attention
     const float* p(const std::string& name) const { return blob + off.at(name); }
 };
 
@@ -200,6 +201,7 @@ extern "C" void cone_weights_destroy(cone_weights* w) {
     if (!w) return;
     if (w->tc) tc_weights_destroy(w->tc);
     if (w->pos_proj) cudaFree(w->pos_proj);
+    if (w->pos_kdec16) cudaFree(w->pos_kdec16);
     if (w->blob) cudaFree(w->blob);
     if (w->derived) cudaFree(w->derived);
     delete w;
@@ -532,7 +534,7 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
                                          b.tlen, b.B, nq, b.Lv, b.Lt, H, 0, nullptr, 0, 0, c.s));
         } else {
             CONE_TRY(dec_cross_attention(b.dq, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt, d,
-                                         b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.w->pos_kdec + (size_t)l * d,
+                                         b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.w->pos_kdec16 + (size_t)l * d,
                                          (int64_t)DL * d, dm.max_v_l, c.s));
         }
         CONE_TRY(linear_named(c, b.datt, d, Q, p + ".multihead_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
@@ -603,6 +605,8 @@ int ensure_tc(const cone_weights* w, int prec, cudaStream_t s) {
         g.A = w->pos_table; g.lda = d; g.W = w->dec_kw; g.ldw = d;
         g.C = mw->pos_kdec; g.ldc = dm.dec_layers * d; g.M = rows; g.N = dm.dec_layers * d; g.K = d;
         CONE_TRY(sgemm_nt(g, s));
+        CONE_CUDA(cudaMalloc(&mw->pos_kdec16, sizeof(uint16_t) * dec));
+        CONE_TRY(f32_to_f16_rows(mw->pos_kdec, dm.dec_layers * d, mw->pos_kdec16, rows, (int)(dm.dec_layers * d), s));
     }
     return CONE_OK;
 }

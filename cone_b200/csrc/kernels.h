@@ -72,8 +72,8 @@ int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
 // k / v are fp32 (kv_f16 = 0) or fp16 (kv_f16 = 1) with leading dims in elements
 int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
-                        int Lt, int nheads, int kv_f16, const float* posk, int64_t ldposk, int table_lv,
-                        cudaStream_t s);
+                        int Lt, int nheads, int kv_f16, const void* posk, int64_t ldposk, int table_lv,
+                        cudaStream_t s);  // posk: fp32 table (kv_f16 = 0) or fp16 table (kv_f16 = 1), or null
 
 // ---------------------------------------------------------------- prefilter.cu
 int window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count, int n_queries,

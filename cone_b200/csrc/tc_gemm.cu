@@ -711,6 +711,10 @@ int f32_to_f16(const float* x, int64_t ldx, __half* y, int64_t rows, int cols, c
     return CONE_OK;
 }
 
+int f32_to_f16_rows(const float* x, int64_t ldx, uint16_t* y, int64_t rows, int cols, cudaStream_t s) {
+    return f32_to_f16(x, ldx, reinterpret_cast<__half*>(y), rows, cols, s);
+}
+
 static int get_w16(TcWeights* t, const float* W, int N, int K, cudaStream_t s, const TcWeights::W16** out) {
     auto it = t->cache.find(W);
     if (it == t->cache.end() || it->second.N != N || it->second.K != K) {

@@ -39,4 +39,7 @@ struct TcGemmArgs {
 };
 int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s);
 
+// y[rows, cols] (fp16, dense) = saturating round-to-nearest of x[rows, ldx] (cols % 4 == 0)
+int f32_to_f16_rows(const float* x, int64_t ldx, uint16_t* y, int64_t rows, int cols, cudaStream_t s);
+
 }  // namespace cone
