@@ -374,7 +374,7 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
 }
 
 template <int NB>
-__global__ void __launch_bounds__(ATT_WARPS * 32, 3)
+__global__ void __launch_bounds__(ATT_WARPS * 32, NB <= 20 ? 4 : 2)
 enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __half* __restrict__ v, int64_t ldv,
                          __half* __restrict__ o, int64_t ldo, const int32_t* __restrict__ vlen,
                          const int32_t* __restrict__ tlen, int Lv, int Lt, int d_model,
@@ -458,50 +458,96 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
             ldsm_x4(aq[ks], Qs + (rb * 16 + l8 + (lq & 1) * 8) * QK_PAD + ks * 16 + (lq >> 1) * 8);
-        float sc[NB][4];
-        float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F;
+        // Keys are processed in two chunks of NB/2 blocks with a running (max, sum) per row (online softmax): only
+        // half of the score row block lives in registers at a time, which is what lets 4 CTAs share an SM.
+        constexpr int CH = NB / 2;  // key blocks per chunk (even: two blocks form one k-step of P.V)
+        float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F, s_lo = 0.f, s_hi = 0.f;
+        float out[4][4];
 #pragma unroll
-        for (int jb = 0; jb < NB; ++jb) {
-            sc[jb][0] = sc[jb][1] = sc[jb][2] = sc[jb][3] = 0.f;
-            if (jb < nkb) {
-                uint32_t bk[4];  // B fragments of K for keys jb*8..+7: dims 0-7, 8-15, 16-23, 24-31
-                ldsm_x4(bk, Ks + (jb * 8 + l8) * QK_PAD + lq * 8);
-                mma_16816(sc[jb], aq[0], bk[0], bk[1]);
-                mma_16816(sc[jb], aq[1], bk[2], bk[3]);
-                // key-padding mask: only key blocks that touch a padded region pay for it (warp-uniform test)
-                const int k0 = jb * 8, k1 = k0 + 8;
-                const bool all_valid = (k1 <= vl) || (k1 <= Lv + tl && (vl == Lv || k0 >= Lv));
-                if (!all_valid) {
+        for (int nb = 0; nb < 4; ++nb) out[nb][0] = out[nb][1] = out[nb][2] = out[nb][3] = 0.f;
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int key = k0 + t4 * 2 + e;
-                        const bool ok = key < S && key_valid(key, Lv, vl, tl);
-                        sc[jb][e] = ok ? sc[jb][e] : -CUDART_INF_F;
-                        sc[jb][2 + e] = ok ? sc[jb][2 + e] : -CUDART_INF_F;
+        for (int ch = 0; ch < 2; ++ch) {
+            if (ch * CH < nkb) {  // warp-uniform
+                float sc[CH][4];
+                float c_lo = -CUDART_INF_F, c_hi = -CUDART_INF_F;
+#pragma unroll
+                for (int jj = 0; jj < CH; ++jj) {
+                    const int jb = ch * CH + jj;
+                    sc[jj][0] = sc[jj][1] = sc[jj][2] = sc[jj][3] = -CUDART_INF_F;
+                    if (jb < nkb) {
+                        sc[jj][0] = sc[jj][1] = sc[jj][2] = sc[jj][3] = 0.f;
+                        uint32_t bk[4];  // B fragments of K for keys jb*8..+7: dims 0-7, 8-15, 16-23, 24-31
+                        ldsm_x4(bk, Ks + (jb * 8 + l8) * QK_PAD + lq * 8);
+                        mma_16816(sc[jj], aq[0], bk[0], bk[1]);
+                        mma_16816(sc[jj], aq[1], bk[2], bk[3]);
+                        // key-padding mask: only key blocks that touch a padded region pay for it (warp-uniform test)
+                        const int k0 = jb * 8, k1 = k0 + 8;
+                        const bool all_valid = (k1 <= vl) || (k1 <= Lv + tl && (vl == Lv || k0 >= Lv));
+                        if (!all_valid) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int key = k0 + t4 * 2 + e;
+                                const bool ok = key < S && key_valid(key, Lv, vl, tl);
+                                sc[jj][e] = ok ? sc[jj][e] : -CUDART_INF_F;
+                                sc[jj][2 + e] = ok ? sc[jj][2 + e] : -CUDART_INF_F;
+                            }
+                        }
+                        c_lo = fmaxf(c_lo, fmaxf(sc[jj][0], sc[jj][1]));
+                        c_hi = fmaxf(c_hi, fmaxf(sc[jj][2], sc[jj][3]));
                     }
                 }
-                m_lo = fmaxf(m_lo, fmaxf(sc[jb][0], sc[jb][1]));
-                m_hi = fmaxf(m_hi, fmaxf(sc[jb][2], sc[jb][3]));
-            }
-        }
-        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
-        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
-        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
-        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
-        // p = exp(scale * (s - max)) = exp2(s * sl2 - max * sl2): one FFMA + EX2 per score (exp2(-inf) = 0 for masked keys)
-        const float o_lo = -m_lo * sl2, o_hi = -m_hi * sl2;
-        float s_lo = 0.f, s_hi = 0.f;
+                c_lo = fmaxf(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, 1));
+                c_lo = fmaxf(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, 2));
+                c_hi = fmaxf(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, 1));
+                c_hi = fmaxf(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, 2));
+                const float n_lo = fmaxf(m_lo, c_lo), n_hi = fmaxf(m_hi, c_hi);
+                // p = exp(scale * (s - max)) = exp2(s * sl2 - max * sl2): one FFMA + EX2 per score; exp2(-inf) = 0 for
+                // masked keys.  A row whose keys are all masked so far keeps offset 0 (its p and its rescale factor are 0).
+                const float o_lo = n_lo == -CUDART_INF_F ? 0.f : -n_lo * sl2;
+                const float o_hi = n_hi == -CUDART_INF_F ? 0.f : -n_hi * sl2;
+                if (ch > 0) {  // rescale what the previous chunk accumulated against its own maximum
+                    const float f_lo = fast_exp2(fmaf(m_lo, sl2, o_lo)), f_hi = fast_exp2(fmaf(m_hi, sl2, o_hi));
+                    s_lo *= f_lo;
+                    s_hi *= f_hi;
 #pragma unroll
-        for (int jb = 0; jb < NB; ++jb) {
-            if (jb < nkb) {
+                    for (int nb = 0; nb < 4; ++nb) {
+                        out[nb][0] *= f_lo; out[nb][1] *= f_lo;
+                        out[nb][2] *= f_hi; out[nb][3] *= f_hi;
+                    }
+                }
+                m_lo = n_lo;
+                m_hi = n_hi;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float p0 = fast_exp2(fmaf(sc[jb][e], sl2, o_lo));
-                    const float p1 = fast_exp2(fmaf(sc[jb][2 + e], sl2, o_hi));
-                    sc[jb][e] = p0;
-                    sc[jb][2 + e] = p1;
-                    s_lo += p0;
-                    s_hi += p1;
+                for (int jj = 0; jj < CH; ++jj) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p0 = fast_exp2(fmaf(sc[jj][e], sl2, o_lo));
+                        const float p1 = fast_exp2(fmaf(sc[jj][2 + e], sl2, o_hi));
+                        sc[jj][e] = p0;
+                        sc[jj][2 + e] = p1;
+                        s_lo += p0;
+                        s_hi += p1;
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < CH / 2; ++kk) {
+                    const int kb = ch * (CH / 2) + kk;  // k-step of 16 keys
+                    if (kb * 2 < nkb) {
+                        uint32_t ap[4];
+                        ap[0] = pack_half2(sc[2 * kk][0], sc[2 * kk][1]);
+                        ap[1] = pack_half2(sc[2 * kk][2], sc[2 * kk][3]);
+                        ap[2] = pack_half2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+                        ap[3] = pack_half2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+                        // B fragments of V (k = key, n = dim) from row-major V via transposing ldmatrix:
+                        // matrices (keys 0-7 | 8-15) x (dims nb*8 | (nb+1)*8)
+#pragma unroll
+                        for (int np = 0; np < 2; ++np) {
+                            uint32_t bv[4];
+                            ldsm_x4_trans(bv, Vs + (kb * 16 + l8 + (lq & 1) * 8) * QK_PAD + (np * 2 + (lq >> 1)) * 8);
+                            mma_16816(out[np * 2], ap, bv[0], bv[1]);
+                            mma_16816(out[np * 2 + 1], ap, bv[2], bv[3]);
+                        }
+                    }
                 }
             }
         }
@@ -509,29 +555,6 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
         s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
         s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
         s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
-
-        float out[4][4];
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb) out[nb][0] = out[nb][1] = out[nb][2] = out[nb][3] = 0.f;
-#pragma unroll
-        for (int kb = 0; kb < NB / 2; ++kb) {
-            if (kb * 2 < nkb) {
-                uint32_t ap[4];
-                ap[0] = pack_half2(sc[2 * kb][0], sc[2 * kb][1]);
-                ap[1] = pack_half2(sc[2 * kb][2], sc[2 * kb][3]);
-                ap[2] = pack_half2(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
-                ap[3] = pack_half2(sc[2 * kb + 1][2], sc[2 * kb + 1][3]);
-                // B fragments of V (k = key, n = dim) from row-major V via transposing ldmatrix:
-                // matrices (keys 0-7 | 8-15) x (dims nb*8 | (nb+1)*8)
-#pragma unroll
-                for (int np = 0; np < 2; ++np) {
-                    uint32_t bv[4];
-                    ldsm_x4_trans(bv, Vs + (kb * 16 + l8 + (lq & 1) * 8) * QK_PAD + (np * 2 + (lq >> 1)) * 8);
-                    mma_16816(out[np * 2], ap, bv[0], bv[1]);
-                    mma_16816(out[np * 2 + 1], ap, bv[2], bv[3]);
-                }
-            }
-        }
         const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
