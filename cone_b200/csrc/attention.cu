@@ -373,7 +373,8 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
                  : "r"((uint32_t)__cvta_generic_to_shared(p)));
 }
 
-template <int NB>
+// EXACT: the window has exactly NB key blocks (Sp == 8 NB), so none of the per-block range guards is compiled.
+template <int NB, bool EXACT>
 __global__ void __launch_bounds__(ATT_WARPS * 32, NB <= 20 ? 4 : 2)
 enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __half* __restrict__ v, int64_t ldv,
                          __half* __restrict__ o, int64_t ldo, const int32_t* __restrict__ vlen,
@@ -385,6 +386,7 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
     __half* Qs = reinterpret_cast<__half*>(att_smem);  // [Sp][QK_PAD]
     __half* Ks = Qs + Sp * QK_PAD;                      // [Sp][QK_PAD]
     __half* Vs = Ks + Sp * QK_PAD;                      // [Sp][QK_PAD]  (row-major; P.V uses ldmatrix.trans)
+    float* mbias = reinterpret_cast<float*>(Vs + Sp * QK_PAD);  // [Sp] additive key-padding mask: 0 or -inf
     // heads are the fast grid index: the 8 heads of a window run together, so both 64-byte halves of every
     // 128-byte line of its q|k|v rows are consumed while the line is in L2 (halves the DRAM reads, ncu-measured)
     const int nheads = d_model / HD;
@@ -444,6 +446,8 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
             *reinterpret_cast<uint4*>(Vs + r * QK_PAD + c * 8) = v4[it];
         }
     }
+    for (int key = threadIdx.x; key < Sp; key += blockDim.x)
+        mbias[key] = (key < S && key_valid(key, Lv, vl, tl)) ? 0.f : -CUDART_INF_F;
     __syncthreads();
 
     const int nkb = Sp >> 3;  // key blocks of 8 (even)
@@ -451,6 +455,13 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
     const int g = lane >> 2, t4 = lane & 3;
     const int l8 = lane & 7, lq = lane >> 3;  // ldmatrix: lane -> (row in 8x8 matrix, matrix id)
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // softmax scale * log2(e)
+    // bit jb set = key block jb touches a padded key: only those blocks pay for the mask (one ballot per warp)
+    uint32_t blkflags;
+    {
+        const int k0 = lane * 8, k1 = k0 + 8;
+        const bool all_valid = (k1 <= vl) || (k1 <= Lv + tl && (vl == Lv || k0 >= Lv));
+        blkflags = __ballot_sync(0xffffffffu, !all_valid);
+    }
     for (int rb = warp; rb < nrb; rb += ATT_WARPS) {
         const int r_lo = rb * 16 + g, r_hi = r_lo + 8;
         uint32_t aq[2][4];
@@ -467,30 +478,23 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
         for (int nb = 0; nb < 4; ++nb) out[nb][0] = out[nb][1] = out[nb][2] = out[nb][3] = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-            if (ch * CH < nkb) {  // warp-uniform
+            if (EXACT || ch * CH < nkb) {  // warp-uniform
                 float sc[CH][4];
                 float c_lo = -CUDART_INF_F, c_hi = -CUDART_INF_F;
 #pragma unroll
                 for (int jj = 0; jj < CH; ++jj) {
                     const int jb = ch * CH + jj;
                     sc[jj][0] = sc[jj][1] = sc[jj][2] = sc[jj][3] = -CUDART_INF_F;
-                    if (jb < nkb) {
+                    if (EXACT || jb < nkb) {
                         sc[jj][0] = sc[jj][1] = sc[jj][2] = sc[jj][3] = 0.f;
                         uint32_t bk[4];  // B fragments of K for keys jb*8..+7: dims 0-7, 8-15, 16-23, 24-31
                         ldsm_x4(bk, Ks + (jb * 8 + l8) * QK_PAD + lq * 8);
                         mma_16816(sc[jj], aq[0], bk[0], bk[1]);
                         mma_16816(sc[jj], aq[1], bk[2], bk[3]);
-                        // key-padding mask: only key blocks that touch a padded region pay for it (warp-uniform test)
-                        const int k0 = jb * 8, k1 = k0 + 8;
-                        const bool all_valid = (k1 <= vl) || (k1 <= Lv + tl && (vl == Lv || k0 >= Lv));
-                        if (!all_valid) {
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int key = k0 + t4 * 2 + e;
-                                const bool ok = key < S && key_valid(key, Lv, vl, tl);
-                                sc[jj][e] = ok ? sc[jj][e] : -CUDART_INF_F;
-                                sc[jj][2 + e] = ok ? sc[jj][2 + e] : -CUDART_INF_F;
-                            }
+                        if (blkflags & (1u << jb)) {  // additive -inf for the padded keys of this block (warp-uniform)
+                            const float2 mb = *reinterpret_cast<const float2*>(mbias + jb * 8 + t4 * 2);
+                            sc[jj][0] += mb.x; sc[jj][1] += mb.y;
+                            sc[jj][2] += mb.x; sc[jj][3] += mb.y;
                         }
                         c_lo = fmaxf(c_lo, fmaxf(sc[jj][0], sc[jj][1]));
                         c_hi = fmaxf(c_hi, fmaxf(sc[jj][2], sc[jj][3]));
@@ -532,7 +536,7 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
 #pragma unroll
                 for (int kk = 0; kk < CH / 2; ++kk) {
                     const int kb = ch * (CH / 2) + kk;  // k-step of 16 keys
-                    if (kb * 2 < nkb) {
+                    if (EXACT || kb * 2 < nkb) {
                         uint32_t ap[4];
                         ap[0] = pack_half2(sc[2 * kk][0], sc[2 * kk][1]);
                         ap[1] = pack_half2(sc[2 * kk][2], sc[2 * kk][3]);
@@ -800,24 +804,28 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
     CONE_REQUIRE(S <= MAX_S, "enc_self_attention_f16: window of %d rows exceeds %d", S, MAX_S);
     CONE_REQUIRE((ldqk % 8) == 0 && (ldv % 8) == 0 && (ldo % 2) == 0, "enc_self_attention_f16: leading dims must keep 16-byte rows");
     const int Sp = (S + 15) & ~15;
-    const size_t smem = sizeof(__half) * (size_t)3 * Sp * QK_PAD;
+    const size_t smem = sizeof(__half) * (size_t)3 * Sp * QK_PAD + sizeof(float) * Sp;
     dim3 grid((unsigned)(B * nheads));
     ProfScope ps(s, P_ENC_ATTN, 4.0 * (double)B * nheads * S * S * HD, 8.0 * (double)B * S * nheads * HD);
     const __half* qk16 = static_cast<const __half*>(qk);
     const __half* v16 = static_cast<const __half*>(v);
     __half* o16 = static_cast<__half*>(o);
-    if (Sp <= 160) {
-        enc_attention_f16_kernel<20><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt,
-                                                                      nheads * HD, posqk, table_lv);
+#define CONE_ENC_ATT(NBV, EX)                                                                                      \
+    enc_attention_f16_kernel<NBV, EX><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt, \
+                                                                       nheads * HD, posqk, table_lv)
+    if (Sp == 160) {  // MAD windows: 125 frames + 25 tokens
+        CONE_ENC_ATT(20, true);
+    } else if (Sp <= 160) {
+        CONE_ENC_ATT(20, false);
     } else {
         static bool attr = false;
         if (!attr) {
-            CONE_CUDA(cudaFuncSetAttribute(enc_attention_f16_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CONE_CUDA(cudaFuncSetAttribute(enc_attention_f16_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr = true;
         }
-        enc_attention_f16_kernel<32><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt,
-                                                                      nheads * HD, posqk, table_lv);
+        CONE_ENC_ATT(32, false);
     }
+#undef CONE_ENC_ATT
     CONE_LAUNCH_CHECK("enc_self_attention_f16");
     return CONE_OK;
 }
