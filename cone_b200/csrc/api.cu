@@ -375,6 +375,11 @@ struct CoreBuffers {
     float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
     int64_t *vid_base, *txt_base;
     int32_t *vlen, *tlen, *pad_len, *qidx;
+    // tensor-core mode, optional: q|k|v of encoder layer 0 per FRAME and per TOKEN (the projection of a row does not
+    // depend on the window it is sliced into); when set, layer 0 runs no per-window QKV GEMM
+    const uint16_t* frame_qkv = nullptr;
+    const uint16_t* token_qkv = nullptr;
+    int64_t n_frames = 0;
 };
 
 CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, int prec) {
@@ -472,11 +477,18 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
         };
         for (int l = 0; l < dm.enc_layers; ++l) {
             const std::string p = "transformer.encoder.layers." + std::to_string(l);
-            TcGemmArgs g = G(b.src16, d, c.w->p(p + ".self_attn.in_proj_weight"), c.w->p(p + ".self_attn.in_proj_bias"), 3 * d, d);
-            g.C16 = b.qkv16; g.ldc16 = 3 * d;
-            CONE_TRY(tc_gemm_run(t, g, c.s));
-            CONE_TRY(enc_self_attention_f16(b.qkv16, 3 * d, b.qkv16 + 2 * d, 3 * d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv,
-                                            b.Lt, H, c.w->pos_qk[l], dm.max_v_l, c.s));
+            TcGemmArgs g;
+            if (l == 0 && b.frame_qkv != nullptr) {
+                CONE_TRY(enc_self_attention_f16(nullptr, 3 * d, nullptr, 3 * d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H,
+                                                c.w->pos_qk[l], dm.max_v_l, c.s, b.frame_qkv, b.token_qkv, b.vid_base,
+                                                b.txt_base, b.n_frames));
+            } else {
+                g = G(b.src16, d, c.w->p(p + ".self_attn.in_proj_weight"), c.w->p(p + ".self_attn.in_proj_bias"), 3 * d, d);
+                g.C16 = b.qkv16; g.ldc16 = 3 * d;
+                CONE_TRY(tc_gemm_run(t, g, c.s));
+                CONE_TRY(enc_self_attention_f16(b.qkv16, 3 * d, b.qkv16 + 2 * d, 3 * d, b.att16, d, b.vlen, b.tlen, b.B,
+                                                b.Lv, b.Lt, H, c.w->pos_qk[l], dm.max_v_l, c.s));
+            }
             g = G(b.att16, d, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"), d, d);
             g.R16 = b.src16; g.ldr16 = d;
             g.ln_g = c.w->p(p + ".norm1.weight"); g.ln_b = c.w->p(p + ".norm1.bias");
@@ -725,6 +737,10 @@ size_t ground_chunk_bytes(const cone_dims& dm, int64_t nqc, int topk, int Lv, in
     plan_match(a, dm, B, nqc);
     a.get<float>(nqc * Lt * dm.hidden);  // txtproj
     plan_proj(a, nqc * Lt, dm.t_dim, dm.hidden);
+    if (prec == CONE_PREC_TC) {
+        a.get<uint16_t>(nqc * Lt * dm.hidden);      // txtproj16
+        a.get<uint16_t>(nqc * Lt * 3 * dm.hidden);  // token q|k|v of encoder layer 0
+    }
     return a.used + tc_scratch_bytes(B * (Lv + Lt), dm.ffn);
 }
 }  // namespace
@@ -769,6 +785,24 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         return CONE_ERR_WORKSPACE;
     }
     CONE_TRY(batch_max_len(win_len, q_batch, n_queries, topk, batch_max, n_batches, c.s));
+    // tensor-core mode: q|k|v of encoder layer 0 once per frame (the reference, and a per-window GEMM, compute the
+    // same row once for every window that contains the frame: k * Nq * Lv rows against n_frames)
+    uint16_t* frame_qkv = nullptr;
+    const int d = dm.hidden;
+    const std::string l0 = "transformer.encoder.layers.0.self_attn";
+    if (precision == CONE_PREC_TC) {
+        uint16_t* vidproj16 = head.get<uint16_t>(n_frames * d);
+        frame_qkv = head.get<uint16_t>(n_frames * 3 * d);
+        if (!head.fits()) {
+            set_error("cone_ground_windows: workspace too small for the per-frame projections");
+            return CONE_ERR_WORKSPACE;
+        }
+        CONE_TRY(f32_to_f16_rows(vidproj, d, vidproj16, n_frames, d, c.s));
+        TcGemmArgs g;
+        g.A16 = vidproj16; g.lda = d; g.M = n_frames; g.W = w->p(l0 + ".in_proj_weight"); g.bias = w->p(l0 + ".in_proj_bias");
+        g.N = 3 * d; g.K = d; g.C16 = frame_qkv; g.ldc16 = 3 * d;
+        CONE_TRY(tc_gemm_run(w->tc, g, c.s));
+    }
 
     const size_t avail = workspace_bytes - head.used;
     int64_t nqc = n_queries;
@@ -789,6 +823,19 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         tc_set_scratch(w->tc, a.base + a.used, avail > a.used ? avail - a.used : 0);
         // text projection once per query (the reference recomputes it for each of the k windows)
         CONE_TRY(input_proj(c, "input_txt_proj", tok + q0 * Lt * dm.t_dim, n * Lt, dm.t_dim, txtproj, pb));
+        if (precision == CONE_PREC_TC) {  // token q|k|v of encoder layer 0, once per query token
+            uint16_t* txtproj16 = a.get<uint16_t>(n * Lt * d);
+            uint16_t* token_qkv = a.get<uint16_t>(n * Lt * 3 * d);
+            tc_set_scratch(w->tc, a.base + a.used, avail > a.used ? avail - a.used : 0);
+            CONE_TRY(f32_to_f16_rows(txtproj, d, txtproj16, n * Lt, d, c.s));
+            TcGemmArgs g;
+            g.A16 = txtproj16; g.lda = d; g.M = n * Lt; g.W = w->p(l0 + ".in_proj_weight"); g.bias = w->p(l0 + ".in_proj_bias");
+            g.N = 3 * d; g.K = d; g.C16 = token_qkv; g.ldc16 = 3 * d;
+            CONE_TRY(tc_gemm_run(w->tc, g, c.s));
+            cb.frame_qkv = frame_qkv;
+            cb.token_qkv = token_qkv;
+            cb.n_frames = n_frames;
+        }
         CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
                                         topk, Lt, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
         if (precision == CONE_PREC_TC) {

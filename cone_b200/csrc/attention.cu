@@ -373,13 +373,23 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
                  : "r"((uint32_t)__cvta_generic_to_shared(p)));
 }
 
+// Layer 0 reads q|k|v rows through the window descriptors (frame / token row tables) instead of a per-window copy:
+// the projection of a frame or a token does not depend on the window it is sliced into (see api.cu).
+struct EncRowSource {
+    const __half* frames;      // [n_frames, 3 d] q|k|v of every frame, or null = dense per-window rows
+    const __half* tokens;      // [n_tokens, 3 d]
+    const int64_t* vid_base;   // [B] first frame row of each window
+    const int64_t* txt_base;   // [B] first token row of each window
+    int64_t n_frames;
+};
+
 // EXACT: the window has exactly NB key blocks (Sp == 8 NB), so none of the per-block range guards is compiled.
 template <int NB, bool EXACT>
 __global__ void __launch_bounds__(ATT_WARPS * 32, NB <= 20 ? 4 : 2)
 enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __half* __restrict__ v, int64_t ldv,
                          __half* __restrict__ o, int64_t ldo, const int32_t* __restrict__ vlen,
                          const int32_t* __restrict__ tlen, int Lv, int Lt, int d_model,
-                         const float* __restrict__ posqk, int table_lv) {
+                         const float* __restrict__ posqk, int table_lv, EncRowSource src) {
     extern __shared__ __align__(16) unsigned char att_smem[];
     const int S = Lv + Lt;
     const int Sp = (S + 15) & ~15;
@@ -401,6 +411,8 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
     // loads of each iteration waited for the previous one)
     constexpr int LOAD_ITERS = (NB * 8 * 4 + ATT_WARPS * 32 - 1) / (ATT_WARPS * 32);
     uint4 q4[LOAD_ITERS], k4[LOAD_ITERS], v4[LOAD_ITERS];
+    const int64_t vbase = src.frames != nullptr ? src.vid_base[b] : 0;
+    const int64_t tbase = src.frames != nullptr ? src.txt_base[b] : 0;
 #pragma unroll
     for (int it = 0; it < LOAD_ITERS; ++it) {
         const int i = threadIdx.x + it * (ATT_WARPS * 32);
@@ -409,10 +421,25 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
         k4[it] = q4[it];
         v4[it] = q4[it];
         if (r < S) {
-            const __half* qrow = qk + (row0 + r) * ldqk + h * HD + c * 8;
-            q4[it] = *reinterpret_cast<const uint4*>(qrow);
-            k4[it] = *reinterpret_cast<const uint4*>(qrow + d_model);
-            v4[it] = *reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + h * HD + c * 8);
+            if (src.frames != nullptr) {
+                const __half* row;
+                if (r < Lv) {
+                    int64_t fr = vbase + r;  // rows past the tensor end belong to masked keys: never read out of bounds
+                    fr = fr < src.n_frames ? fr : src.n_frames - 1;
+                    row = src.frames + fr * (3 * d_model);
+                } else {
+                    row = src.tokens + (tbase + (r - Lv)) * (3 * d_model);
+                }
+                row += h * HD + c * 8;
+                q4[it] = *reinterpret_cast<const uint4*>(row);
+                k4[it] = *reinterpret_cast<const uint4*>(row + d_model);
+                v4[it] = *reinterpret_cast<const uint4*>(row + 2 * d_model);
+            } else {
+                const __half* qrow = qk + (row0 + r) * ldqk + h * HD + c * 8;
+                q4[it] = *reinterpret_cast<const uint4*>(qrow);
+                k4[it] = *reinterpret_cast<const uint4*>(qrow + d_model);
+                v4[it] = *reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + h * HD + c * 8);
+            }
         }
     }
     const int vl = vlen[b], tl = tlen[b];
@@ -798,7 +825,8 @@ int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk,
 
 int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
                            const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
-                           const float* posqk, int table_lv, cudaStream_t s) {
+                           const float* posqk, int table_lv, cudaStream_t s, const void* frame_qkv,
+                           const void* token_qkv, const int64_t* vid_base, const int64_t* txt_base, int64_t n_frames) {
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
     CONE_REQUIRE(S <= MAX_S, "enc_self_attention_f16: window of %d rows exceeds %d", S, MAX_S);
@@ -812,7 +840,10 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
     __half* o16 = static_cast<__half*>(o);
 #define CONE_ENC_ATT(NBV, EX)                                                                                      \
     enc_attention_f16_kernel<NBV, EX><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt, \
-                                                                       nheads * HD, posqk, table_lv)
+                                                                       nheads * HD, posqk, table_lv, rs)
+    EncRowSource rs{static_cast<const __half*>(frame_qkv), static_cast<const __half*>(token_qkv), vid_base, txt_base, n_frames};
+    CONE_REQUIRE(frame_qkv == nullptr || (token_qkv && vid_base && txt_base && n_frames > 0),
+                 "enc_self_attention_f16: incomplete row tables");
     if (Sp == 160) {  // MAD windows: 125 frames + 25 tokens
         CONE_ENC_ATT(20, true);
     } else if (Sp <= 160) {

@@ -64,7 +64,11 @@ int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
 // posqk (nullable): per-layer table [(table_lv+1)*table_lv, 2*d] = pos . [Wq; Wk]^T added to q | k of video rows
 int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
                            const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
-                           const float* posqk, int table_lv, cudaStream_t s);
+                           const float* posqk, int table_lv, cudaStream_t s, const void* frame_qkv = nullptr,
+                           const void* token_qkv = nullptr, const int64_t* vid_base = nullptr,
+                           const int64_t* txt_base = nullptr, int64_t n_frames = 0);
+// frame_qkv / token_qkv (nullable): fp16 q|k|v rows [n, 3 d] of every frame / token; window row r then reads
+// frame vid_base[b] + r (r < Lv) or token txt_base[b] + r - Lv instead of qk / v
 // decoder self-attention over nq slots (no mask)
 int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo, int64_t B,
                        int nq, int nheads, cudaStream_t s);
