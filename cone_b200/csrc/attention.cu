@@ -410,48 +410,54 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
     // latency covers the whole tile (the CTA is short-lived: ncu showed a third of its life in this phase when the
     // loads of each iteration waited for the previous one)
     constexpr int LOAD_ITERS = (NB * 8 * 4 + ATT_WARPS * 32 - 1) / (ATT_WARPS * 32);
+    constexpr int ROWS_PER_IT = ATT_WARPS * 32 / 4;  // 4 threads per row: the row of iteration `it` is r0 + it * 40
     uint4 q4[LOAD_ITERS], k4[LOAD_ITERS], v4[LOAD_ITERS];
-    const int64_t vbase = src.frames != nullptr ? src.vid_base[b] : 0;
-    const int64_t tbase = src.frames != nullptr ? src.txt_base[b] : 0;
+    const int r0 = threadIdx.x >> 2, c8 = (threadIdx.x & 3) * 8 + h * HD;
+    // per-thread base pointers, advanced by a constant per iteration (the 64-bit row arithmetic of the first version
+    // was a third of this phase's instructions)
+    const bool indirect = src.frames != nullptr;
+    const int64_t vbase = indirect ? src.vid_base[b] : 0;
+    const int64_t tbase = indirect ? src.txt_base[b] : 0;
+    const __half* qp = qk + (row0 + r0) * ldqk + c8;
+    const __half* vp = v + (row0 + r0) * ldv + c8;
 #pragma unroll
     for (int it = 0; it < LOAD_ITERS; ++it) {
-        const int i = threadIdx.x + it * (ATT_WARPS * 32);
-        const int r = i >> 2, c = i & 3;
+        const int r = r0 + it * ROWS_PER_IT;
         q4[it] = make_uint4(0, 0, 0, 0);
         k4[it] = q4[it];
         v4[it] = q4[it];
         if (r < S) {
-            if (src.frames != nullptr) {
+            if (indirect) {
                 const __half* row;
                 if (r < Lv) {
                     int64_t fr = vbase + r;  // rows past the tensor end belong to masked keys: never read out of bounds
                     fr = fr < src.n_frames ? fr : src.n_frames - 1;
-                    row = src.frames + fr * (3 * d_model);
+                    row = src.frames + fr * (3 * d_model) + c8;
                 } else {
-                    row = src.tokens + (tbase + (r - Lv)) * (3 * d_model);
+                    row = src.tokens + (tbase + (r - Lv)) * (3 * d_model) + c8;
                 }
-                row += h * HD + c * 8;
                 q4[it] = *reinterpret_cast<const uint4*>(row);
                 k4[it] = *reinterpret_cast<const uint4*>(row + d_model);
                 v4[it] = *reinterpret_cast<const uint4*>(row + 2 * d_model);
             } else {
-                const __half* qrow = qk + (row0 + r) * ldqk + h * HD + c * 8;
-                q4[it] = *reinterpret_cast<const uint4*>(qrow);
-                k4[it] = *reinterpret_cast<const uint4*>(qrow + d_model);
-                v4[it] = *reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + h * HD + c * 8);
+                q4[it] = *reinterpret_cast<const uint4*>(qp + (int64_t)it * ROWS_PER_IT * ldqk);
+                k4[it] = *reinterpret_cast<const uint4*>(qp + (int64_t)it * ROWS_PER_IT * ldqk + d_model);
+                v4[it] = *reinterpret_cast<const uint4*>(vp + (int64_t)it * ROWS_PER_IT * ldv);
             }
         }
     }
     const int vl = vlen[b], tl = tlen[b];
+    const float* pp = posqk + ((int64_t)vl * table_lv + r0) * (2 * d_model) + c8;
+    unsigned char* sbase = att_smem + (r0 * QK_PAD + (threadIdx.x & 3) * 8) * 2;  // this thread's chunk of row r0 in Qs
+    const int mat_bytes = Sp * QK_PAD * 2;
 #pragma unroll
     for (int it = 0; it < LOAD_ITERS; ++it) {
-        const int i = threadIdx.x + it * (ATT_WARPS * 32);
-        const int r = i >> 2, c = i & 3;
-        if (i < Sp * 4) {
+        const int r = r0 + it * ROWS_PER_IT;
+        if (r < Sp) {
             if (posqk != nullptr && r < Lv) {
                 // q = (src + pos) Wq^T + bq = (src Wq^T + bq) + pos Wq^T: the position term comes from a per-layer
                 // table indexed by (valid length, row), so no position-added copy of the activations exists
-                const float* pr = posqk + ((int64_t)vl * table_lv + r) * (2 * d_model) + h * HD + c * 8;
+                const float* pr = pp + it * ROWS_PER_IT * 2 * d_model;
                 const float4 pq0 = __ldg(reinterpret_cast<const float4*>(pr));
                 const float4 pq1 = __ldg(reinterpret_cast<const float4*>(pr) + 1);
                 const float4 pk0 = __ldg(reinterpret_cast<const float4*>(pr + d_model));
@@ -468,9 +474,10 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 f = __half22float2(kh[2]); kh[2] = __floats2half2_rn(f.x + pk1.x, f.y + pk1.y);
                 f = __half22float2(kh[3]); kh[3] = __floats2half2_rn(f.x + pk1.z, f.y + pk1.w);
             }
-            *reinterpret_cast<uint4*>(Qs + r * QK_PAD + c * 8) = q4[it];
-            *reinterpret_cast<uint4*>(Ks + r * QK_PAD + c * 8) = k4[it];
-            *reinterpret_cast<uint4*>(Vs + r * QK_PAD + c * 8) = v4[it];
+            unsigned char* sp = sbase + it * ROWS_PER_IT * QK_PAD * 2;
+            *reinterpret_cast<uint4*>(sp) = q4[it];
+            *reinterpret_cast<uint4*>(sp + mat_bytes) = k4[it];
+            *reinterpret_cast<uint4*>(sp + 2 * mat_bytes) = v4[it];
         }
     }
     for (int key = threadIdx.x; key < Sp; key += blockDim.x)
@@ -499,7 +506,9 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
         // Keys are processed in two chunks of NB/2 blocks with a running (max, sum) per row (online softmax): only
         // half of the score row block lives in registers at a time, which is what lets 4 CTAs share an SM.
         constexpr int CH = NB / 2;  // key blocks per chunk (even: two blocks form one k-step of P.V)
-        float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F, s_lo = 0.f, s_hi = 0.f;
+        float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F;
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};                // accumulator of the ones block (row sums)
+        const uint32_t ones = g == 0 ? 0x3C003C00u : 0u;  // B fragment: B[k][n = g] = 1 for n = 0
         float out[4][4];
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) out[nb][0] = out[nb][1] = out[nb][2] = out[nb][3] = 0.f;
@@ -538,8 +547,8 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 const float o_hi = n_hi == -CUDART_INF_F ? 0.f : -n_hi * sl2;
                 if (ch > 0) {  // rescale what the previous chunk accumulated against its own maximum
                     const float f_lo = fast_exp2(fmaf(m_lo, sl2, o_lo)), f_hi = fast_exp2(fmaf(m_hi, sl2, o_hi));
-                    s_lo *= f_lo;
-                    s_hi *= f_hi;
+                    rs[0] *= f_lo;
+                    rs[2] *= f_hi;
 #pragma unroll
                     for (int nb = 0; nb < 4; ++nb) {
                         out[nb][0] *= f_lo; out[nb][1] *= f_lo;
@@ -552,12 +561,8 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 for (int jj = 0; jj < CH; ++jj) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float p0 = fast_exp2(fmaf(sc[jj][e], sl2, o_lo));
-                        const float p1 = fast_exp2(fmaf(sc[jj][2 + e], sl2, o_hi));
-                        sc[jj][e] = p0;
-                        sc[jj][2 + e] = p1;
-                        s_lo += p0;
-                        s_hi += p1;
+                        sc[jj][e] = fast_exp2(fmaf(sc[jj][e], sl2, o_lo));
+                        sc[jj][2 + e] = fast_exp2(fmaf(sc[jj][2 + e], sl2, o_hi));
                     }
                 }
 #pragma unroll
@@ -578,14 +583,15 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                             mma_16816(out[np * 2], ap, bv[0], bv[1]);
                             mma_16816(out[np * 2 + 1], ap, bv[2], bv[3]);
                         }
+                        // row sums of P through the tensor pipe: a fifth n-block whose column 0 is all ones.  The sum
+                        // is taken over the fp16 values that multiply V, so the normalisation is exact for them.
+                        mma_16816(rs, ap, ones, ones);
                     }
                 }
             }
         }
-        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
-        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
-        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
-        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+        // column 0 of the ones block lives in the t4 = 0 lane of each quad: rs[0] = row g, rs[2] = row g + 8
+        const float s_lo = __shfl_sync(0xffffffffu, rs[0], lane & ~3), s_hi = __shfl_sync(0xffffffffu, rs[2], lane & ~3);
         const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
