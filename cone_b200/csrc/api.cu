@@ -373,6 +373,7 @@ struct CoreBuffers {
     float *src, *srcpos, *qk, *v, *att, *tmp, *h;                      // [R, .] fp32 (srcpos..h: fp32 mode only)
     uint16_t *src16, *qkv16, *att16, *h16;                             // [R, .] fp16 (tensor-core mode only)
     float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
+    uint16_t *tgt16, *dqkin16, *dqkv16, *datt16, *dq16, *dh16;               // [B*nq, .] fp16 (tensor-core mode only)
     int64_t *vid_base, *txt_base;
     int32_t *vlen, *tlen, *pad_len, *qidx;
     // tensor-core mode, optional: q|k|v of encoder layer 0 per FRAME and per TOKEN (the projection of a row does not
@@ -403,13 +404,22 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, i
         b.h = a.get<float>(R * b.hw);
     }
     b.tgt = a.get<float>(Q * d);
-    b.t2 = a.get<float>(Q * d);
-    b.dqkin = a.get<float>(Q * d);
-    b.dqk = a.get<float>(Q * 2 * d);
-    b.dv = a.get<float>(Q * d);
-    b.datt = a.get<float>(Q * d);
-    b.dq = a.get<float>(Q * d);
-    b.dh = a.get<float>(Q * c.ffn);
+    if (prec == CONE_PREC_TC) {  // the decoder chain keeps an fp32 residual stream and fp16 GEMM operands
+        b.tgt16 = a.get<uint16_t>(Q * d);
+        b.dqkin16 = a.get<uint16_t>(Q * d);
+        b.dqkv16 = a.get<uint16_t>(Q * 3 * d);
+        b.datt16 = a.get<uint16_t>(Q * d);
+        b.dq16 = a.get<uint16_t>(Q * d);
+        b.dh16 = a.get<uint16_t>(Q * c.ffn);
+    } else {
+        b.t2 = a.get<float>(Q * d);
+        b.dqkin = a.get<float>(Q * d);
+        b.dqk = a.get<float>(Q * 2 * d);
+        b.dv = a.get<float>(Q * d);
+        b.datt = a.get<float>(Q * d);
+        b.dq = a.get<float>(Q * d);
+        b.dh = a.get<float>(Q * c.ffn);
+    }
     b.hs = a.get<float>(Q * d);
     b.hid1 = a.get<float>(Q * d);
     b.hid2 = a.get<float>(Q * d);
@@ -526,34 +536,74 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
         CONE_TRY(tc_gemm_run(c.w->tc, g, c.s));
     }
     CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * Q * d, c.s));
+    if (tc) CONE_CUDA(cudaMemsetAsync(b.tgt16, 0, sizeof(uint16_t) * Q * d, c.s));
     const float* qpos = c.w->p("query_embed.weight");
     for (int l = 0; l < DL; ++l) {
         const std::string p = "transformer.decoder.layers." + std::to_string(l);
         const float* inw = c.w->p(p + ".self_attn.in_proj_weight");
         const float* inb = c.w->p(p + ".self_attn.in_proj_bias");
-        CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Q, nq, d, c.s));
-        CONE_TRY(linear(c, b.dqkin, d, Q, inw, inb, 2 * d, d, b.dqk, 2 * d, 0));
-        CONE_TRY(linear(c, b.tgt, d, Q, inw + (size_t)2 * d * d, inb + 2 * d, d, d, b.dv, d, 0));
-        CONE_TRY(dec_self_attention(b.dqk, 2 * d, b.dv, d, b.datt, d, b.B, nq, H, c.s));
-        CONE_TRY(linear_named(c, b.datt, d, Q, p + ".self_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
-        CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), b.tgt, Q, d, 1e-5f, c.s));
         const float* cw = c.w->p(p + ".multihead_attn.in_proj_weight");
         const float* cb = c.w->p(p + ".multihead_attn.in_proj_bias");
-        CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Q, nq, d, c.s));
-        CONE_TRY(linear(c, b.dqkin, d, Q, cw, cb, d, d, b.dq, d, 0));
         if (!tc) {
+            CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Q, nq, d, c.s));
+            CONE_TRY(linear(c, b.dqkin, d, Q, inw, inb, 2 * d, d, b.dqk, 2 * d, 0));
+            CONE_TRY(linear(c, b.tgt, d, Q, inw + (size_t)2 * d * d, inb + 2 * d, d, d, b.dv, d, 0));
+            CONE_TRY(dec_self_attention(b.dqk, 2 * d, b.dv, d, b.datt, d, b.B, nq, H, 0, c.s));
+            CONE_TRY(linear_named(c, b.datt, d, Q, p + ".self_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
+            CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm1.weight"), c.w->p(p + ".norm1.bias"), b.tgt, Q, d, 1e-5f, c.s));
+            CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Q, nq, d, c.s));
+            CONE_TRY(linear(c, b.dqkin, d, Q, cw, cb, d, d, b.dq, d, 0));
             CONE_TRY(dec_cross_attention(b.dq, d, kdec + (size_t)l * d, b.hw, vdec + (size_t)l * d, b.hw, b.datt, d, b.vlen,
                                          b.tlen, b.B, nq, b.Lv, b.Lt, H, 0, nullptr, 0, 0, c.s));
+            CONE_TRY(linear_named(c, b.datt, d, Q, p + ".multihead_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
+            CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.tgt, Q, d, 1e-5f, c.s));
+            CONE_TRY(linear_named(c, b.tgt, d, Q, p + ".linear1", ff, d, b.dh, ff, 1));
+            CONE_TRY(linear_named(c, b.dh, ff, Q, p + ".linear2", d, ff, b.t2, d, 0, b.tgt, d));
+            CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm3.weight"), c.w->p(p + ".norm3.bias"), b.tgt, Q, d, 1e-5f, c.s));
         } else {
-            CONE_TRY(dec_cross_attention(b.dq, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt, d,
+            // Tensor-core decoder chain: every GEMM operand is fp16 and is written by the kernel that produces it (no
+            // conversion passes); the residual stream stays fp32: the residual-adding GEMMs read it (R32), apply
+            // LayerNorm in their epilogue and write it back as fp32 (next residual) and fp16 (next operand).
+            TcWeights* t = c.w->tc;
+            auto G = [&](const uint16_t* A, int64_t lda, const float* W, const float* bias, int N, int K) {
+                TcGemmArgs g;
+                g.A16 = A; g.lda = lda; g.M = Q; g.W = W; g.bias = bias; g.N = N; g.K = K;
+                return g;
+            };
+            auto LN = [&](TcGemmArgs& g, const std::string& norm) {  // + residual, LayerNorm, dual output
+                g.R32 = b.tgt; g.ldr32 = d;
+                g.ln_g = c.w->p(norm + ".weight"); g.ln_b = c.w->p(norm + ".bias");
+                g.C32 = b.tgt; g.ldc32 = d;
+                g.C16 = b.tgt16; g.ldc16 = d;
+            };
+            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Q, nq, d, c.s));
+            TcGemmArgs g = G(b.dqkin16, d, inw, inb, 2 * d, d);  // q | k of the self-attention
+            g.C16 = b.dqkv16; g.ldc16 = 3 * d;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            g = G(b.tgt16, d, inw + (size_t)2 * d * d, inb + 2 * d, d, d);  // v
+            g.C16 = b.dqkv16 + 2 * d; g.ldc16 = 3 * d;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            CONE_TRY(dec_self_attention(b.dqkv16, 3 * d, b.dqkv16 + 2 * d, 3 * d, b.datt16, d, b.B, nq, H, 1, c.s));
+            g = G(b.datt16, d, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"), d, d);
+            LN(g, p + ".norm1");
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Q, nq, d, c.s));
+            g = G(b.dqkin16, d, cw, cb, d, d);  // q of the cross-attention
+            g.C16 = b.dq16; g.ldc16 = d;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            CONE_TRY(dec_cross_attention(b.dq16, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt16, d,
                                          b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.w->pos_kdec16 + (size_t)l * d,
                                          (int64_t)DL * d, dm.max_v_l, c.s));
+            g = G(b.datt16, d, c.w->p(p + ".multihead_attn.out_proj.weight"), c.w->p(p + ".multihead_attn.out_proj.bias"), d, d);
+            LN(g, p + ".norm2");
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            g = G(b.tgt16, d, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d);
+            g.relu = 1; g.C16 = b.dh16; g.ldc16 = ff;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            g = G(b.dh16, ff, c.w->p(p + ".linear2.weight"), c.w->p(p + ".linear2.bias"), d, ff);
+            LN(g, p + ".norm3");
+            CONE_TRY(tc_gemm_run(t, g, c.s));
         }
-        CONE_TRY(linear_named(c, b.datt, d, Q, p + ".multihead_attn.out_proj", d, d, b.t2, d, 0, b.tgt, d));
-        CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm2.weight"), c.w->p(p + ".norm2.bias"), b.tgt, Q, d, 1e-5f, c.s));
-        CONE_TRY(linear_named(c, b.tgt, d, Q, p + ".linear1", ff, d, b.dh, ff, 1));
-        CONE_TRY(linear_named(c, b.dh, ff, Q, p + ".linear2", d, ff, b.t2, d, 0, b.tgt, d));
-        CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm3.weight"), c.w->p(p + ".norm3.bias"), b.tgt, Q, d, 1e-5f, c.s));
         const bool last = (l == DL - 1);
         if (last || aux_logits || aux_spans) {
             CONE_TRY(layernorm_rows(b.tgt, nullptr, c.w->p("transformer.decoder.norm.weight"),

@@ -84,9 +84,16 @@ enc_self_attention_kernel(const float* __restrict__ qk, int64_t ldqk, const floa
     }
 }
 
-// decoder self-attention: nq <= 8 slots, one warp per (window, head), lane = channel
-__global__ void dec_self_attention_kernel(const float* __restrict__ qk, int64_t ldqk, const float* __restrict__ v,
-                                          int64_t ldv, float* __restrict__ o, int64_t ldo, int64_t B, int nq,
+// decoder self-attention: nq <= 8 slots, one warp per (window, head), lane = channel.  T = float (parity mode) or
+// __half (tensor-core mode: q|k|v come from fp16 GEMM outputs and the result feeds an fp16 GEMM operand)
+__device__ __forceinline__ float ld_f32(const float* p) { return *p; }
+__device__ __forceinline__ float ld_f32(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void st_f32(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_f32(__half* p, float v) { *p = __float2half_rn(v); }
+
+template <typename T>
+__global__ void dec_self_attention_kernel(const T* __restrict__ qk, int64_t ldqk, const T* __restrict__ v,
+                                          int64_t ldv, T* __restrict__ o, int64_t ldo, int64_t B, int nq,
                                           int nheads, int d_model) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -99,9 +106,9 @@ __global__ void dec_self_attention_kernel(const float* __restrict__ qk, int64_t 
     for (int i = 0; i < 8; ++i) {
         if (i < nq) {
             const int64_t row = b * nq + i;
-            q[i] = qk[row * ldqk + h * HD + lane] * scale;
-            k[i] = qk[row * ldqk + d_model + h * HD + lane];
-            vv[i] = v[row * ldv + h * HD + lane];
+            q[i] = ld_f32(qk + row * ldqk + h * HD + lane) * scale;
+            k[i] = ld_f32(qk + row * ldqk + d_model + h * HD + lane);
+            vv[i] = ld_f32(v + row * ldv + h * HD + lane);
         } else {
             q[i] = k[i] = vv[i] = 0.f;
         }
@@ -127,7 +134,7 @@ __global__ void dec_self_attention_kernel(const float* __restrict__ qk, int64_t 
                 acc = fmaf(e, vv[j], acc);
             }
         }
-        o[(b * nq + i) * ldo + h * HD + lane] = acc / sum;
+        st_f32(o + (b * nq + i) * ldo + h * HD + lane, acc / sum);
     }
 }
 
@@ -621,8 +628,8 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
 // The SIMT version of this kernel spent 54 k warp-instructions per window (ncu), this one ~6 k.
 template <int NB>
 __global__ void __launch_bounds__(256, 3)
-dec_cross_attention_mma_kernel(const float* __restrict__ q, int64_t ldq, const __half* __restrict__ k, int64_t ldk,
-                               const __half* __restrict__ v, int64_t ldv, float* __restrict__ o, int64_t ldo,
+dec_cross_attention_mma_kernel(const __half* __restrict__ q, int64_t ldq, const __half* __restrict__ k, int64_t ldk,
+                               const __half* __restrict__ v, int64_t ldv, __half* __restrict__ o, int64_t ldo,
                                const int32_t* __restrict__ vlen, const int32_t* __restrict__ tlen, int64_t B, int nq, int Lv,
                                int Lt, const __half* __restrict__ posk, int64_t ldposk, int table_lv) {
     constexpr int KB = 5;  // key blocks (of 8 keys) whose loads are in flight together
@@ -642,12 +649,13 @@ dec_cross_attention_mma_kernel(const float* __restrict__ q, int64_t ldq, const _
     uint32_t a0[4] = {0u, 0u, 0u, 0u}, a1[4] = {0u, 0u, 0u, 0u};
     if (g < nq) {
         const float sl2 = 0.17677669529663687f * 1.4426950408889634f;
-        const float4 x = *reinterpret_cast<const float4*>(q + (b * nq + g) * ldq + colq);
-        const float4 y = *reinterpret_cast<const float4*>(q + (b * nq + g) * ldq + colq + 4);
-        a0[0] = pack_half2(x.x * sl2, x.y * sl2);
-        a0[2] = pack_half2(x.z * sl2, x.w * sl2);
-        a1[0] = pack_half2(y.x * sl2, y.y * sl2);
-        a1[2] = pack_half2(y.z * sl2, y.w * sl2);
+        const uint4 qraw = *reinterpret_cast<const uint4*>(q + (b * nq + g) * ldq + colq);
+        const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
+        const float2 x0 = __half22float2(qh[0]), x1 = __half22float2(qh[1]), y0 = __half22float2(qh[2]), y1 = __half22float2(qh[3]);
+        a0[0] = pack_half2(x0.x * sl2, x0.y * sl2);
+        a0[2] = pack_half2(x1.x * sl2, x1.y * sl2);
+        a1[0] = pack_half2(y0.x * sl2, y0.y * sl2);
+        a1[2] = pack_half2(y1.x * sl2, y1.y * sl2);
     }
     float sc[NB][2];
     float mx = -CUDART_INF_F;
@@ -741,9 +749,12 @@ dec_cross_attention_mma_kernel(const float* __restrict__ q, int64_t ldq, const _
     if (g < nq) {
         const float is = 1.f / sum;
         // out[nb][e] = O[slot g][n = 2 t4 + e of n-block nb] <-> dim 4 (2 t4 + e) + nb: 8 consecutive channels
-        float* op = o + (b * nq + g) * ldo + h * HD + t4 * 8;
-        *reinterpret_cast<float4*>(op) = make_float4(out[0][0] * is, out[1][0] * is, out[2][0] * is, out[3][0] * is);
-        *reinterpret_cast<float4*>(op + 4) = make_float4(out[0][1] * is, out[1][1] * is, out[2][1] * is, out[3][1] * is);
+        uint4 ov;
+        ov.x = pack_half2(out[0][0] * is, out[1][0] * is);
+        ov.y = pack_half2(out[2][0] * is, out[3][0] * is);
+        ov.z = pack_half2(out[0][1] * is, out[1][1] * is);
+        ov.w = pack_half2(out[2][1] * is, out[3][1] * is);
+        *reinterpret_cast<uint4*>(o + (b * nq + g) * ldo + h * HD + t4 * 8) = ov;
     }
 }
 
@@ -769,23 +780,33 @@ int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
     return CONE_OK;
 }
 
-int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo, int64_t B,
-                       int nq, int nheads, cudaStream_t s) {
+int dec_self_attention(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo, int64_t B,
+                       int nq, int nheads, int f16, cudaStream_t s) {
     if (B == 0) return CONE_OK;
     CONE_REQUIRE(nq <= 8, "dec_self_attention: at most 8 moment slots");
     const int warps = 4;
     ProfScope ps(s, P_DEC_ATTN);
-    dec_self_attention_kernel<<<(unsigned)cdiv64(B * nheads, warps), warps * 32, 0, s>>>(qk, ldqk, v, ldv, o, ldo, B, nq,
-                                                                                       nheads, nheads * HD);
+    const unsigned grid = (unsigned)cdiv64(B * nheads, warps);
+    if (f16) {
+        dec_self_attention_kernel<__half><<<grid, warps * 32, 0, s>>>(static_cast<const __half*>(qk), ldqk,
+                                                                    static_cast<const __half*>(v), ldv,
+                                                                    static_cast<__half*>(o), ldo, B, nq, nheads, nheads * HD);
+    } else {
+        dec_self_attention_kernel<float><<<grid, warps * 32, 0, s>>>(static_cast<const float*>(qk), ldqk,
+                                                                   static_cast<const float*>(v), ldv,
+                                                                   static_cast<float*>(o), ldo, B, nq, nheads, nheads * HD);
+    }
     CONE_LAUNCH_CHECK("dec_self_attention");
     return CONE_OK;
 }
 
-int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                        float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
+int dec_cross_attention(const void* q_any, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                        void* o_any, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
                         int Lt, int nheads, int kv_f16, const void* posk_any, int64_t ldposk, int table_lv,
                         cudaStream_t s) {
     const float* posk = static_cast<const float*>(posk_any);
+    const float* q = static_cast<const float*>(q_any);  // fp32 mode; in fp16 mode q and o are fp16 as well
+    float* o = static_cast<float*>(o_any);
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
     CONE_REQUIRE(nq >= 1 && nq <= 8 && S <= MAX_S && nheads == 8, "dec_cross_attention: unsupported nq=%d S=%d heads=%d", nq,
@@ -813,12 +834,15 @@ int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk,
         const __half* k16 = static_cast<const __half*>(k);
         const __half* v16 = static_cast<const __half*>(v);
         const __half* p16 = static_cast<const __half*>(posk_any);
+        const __half* q16 = static_cast<const __half*>(q_any);
+        __half* o16 = static_cast<__half*>(o_any);
+        CONE_REQUIRE((ldq & 7) == 0 && (ldo & 7) == 0, "dec_cross_attention: fp16 q / o rows must be 16-byte aligned");
         const unsigned g8 = (unsigned)B;  // 8 warps = the 8 heads of one window
         if (S <= 160) {
-            dec_cross_attention_mma_kernel<20><<<g8, 256, 0, s>>>(q, ldq, k16, ldk, v16, ldv, o, ldo, vlen, tlen, B, nq, Lv, Lt,
+            dec_cross_attention_mma_kernel<20><<<g8, 256, 0, s>>>(q16, ldq, k16, ldk, v16, ldv, o16, ldo, vlen, tlen, B, nq, Lv, Lt,
                                                                  p16, ldposk, table_lv);
         } else {
-            dec_cross_attention_mma_kernel<32><<<g8, 256, 0, s>>>(q, ldq, k16, ldk, v16, ldv, o, ldo, vlen, tlen, B, nq, Lv, Lt,
+            dec_cross_attention_mma_kernel<32><<<g8, 256, 0, s>>>(q16, ldq, k16, ldk, v16, ldv, o16, ldo, vlen, tlen, B, nq, Lv, Lt,
                                                                  p16, ldposk, table_lv);
         }
     } else {

@@ -51,6 +51,8 @@ int add_pos_rows_f16(const float* src, const float* pos_table, const int32_t* vl
                      int64_t B, int Lv, int Lt, int d, int table_lv, cudaStream_t s);
 // out[row] = x[row] + table[row % period]   (x may be null = zeros)
 int add_row_table(const float* x, const float* table, float* out, int64_t rows, int period, int d, cudaStream_t s);
+// same, rounded to fp16 (GEMM operand of the tensor-core decoder chain)
+int add_row_table_f16(const float* x, const float* table, uint16_t* out16, int64_t rows, int period, int d, cudaStream_t s);
 int fill_window_desc_dense(int64_t* vid_base, int64_t* txt_base, int32_t* qidx, int64_t B, int Lv, int Lt,
                            cudaStream_t s);
 int fill_i32(int32_t* p, int64_t n, int32_t value, cudaStream_t s);
@@ -70,12 +72,14 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
 // frame_qkv / token_qkv (nullable): fp16 q|k|v rows [n, 3 d] of every frame / token; window row r then reads
 // frame vid_base[b] + r (r < Lv) or token txt_base[b] + r - Lv instead of qk / v
 // decoder self-attention over nq slots (no mask)
-int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo, int64_t B,
-                       int nq, int nheads, cudaStream_t s);
+// qk / v / o are fp32 (f16 = 0) or fp16 (f16 = 1)
+int dec_self_attention(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo, int64_t B,
+                       int nq, int nheads, int f16, cudaStream_t s);
 // decoder cross-attention: nq queries x S memory keys with key-padding mask
 // k / v are fp32 (kv_f16 = 0) or fp16 (kv_f16 = 1) with leading dims in elements
-int dec_cross_attention(const float* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                        float* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
+// with kv_f16 = 1 the queries q and the output o are fp16 as well (the tensor-core decoder chain)
+int dec_cross_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                        void* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
                         int Lt, int nheads, int kv_f16, const void* posk, int64_t ldposk, int table_lv,
                         cudaStream_t s);  // posk: fp32 table (kv_f16 = 0) or fp16 table (kv_f16 = 1), or null
 

@@ -216,6 +216,22 @@ __global__ void add_row_table_kernel(const float* __restrict__ x, const float* _
     }
 }
 
+__global__ void add_row_table_f16_kernel(const float* __restrict__ x, const float* __restrict__ table,
+                                         __half* __restrict__ out, int64_t rows, int period, int d4) {
+    const int64_t total = rows * d4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % d4);
+        const int64_t row = i / d4;
+        float4 v = x ? reinterpret_cast<const float4*>(x)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t = __ldg(reinterpret_cast<const float4*>(table) + (row % period) * d4 + c);
+        __half2 h0 = __floats2half2_rn(v.x + t.x, v.y + t.y), h1 = __floats2half2_rn(v.z + t.z, v.w + t.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(out)[i] = u;
+    }
+}
+
 __global__ void fill_window_desc_dense_kernel(int64_t* vid_base, int64_t* txt_base, int32_t* qidx, int64_t B, int Lv,
                                               int Lt) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,6 +327,15 @@ int add_row_table(const float* x, const float* table, float* out, int64_t rows, 
     ProfScope ps(s, P_ROWOPS, 0.0, 8.0 * (double)rows * d);
     add_row_table_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, s>>>(x, table, out, rows, period, d / 4);
     CONE_LAUNCH_CHECK("add_row_table");
+    return CONE_OK;
+}
+
+int add_row_table_f16(const float* x, const float* table, uint16_t* out16, int64_t rows, int period, int d, cudaStream_t s) {
+    if (rows == 0) return CONE_OK;
+    ProfScope ps(s, P_ROWOPS, 0.0, 6.0 * (double)rows * d);
+    add_row_table_f16_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, s>>>(x, table, reinterpret_cast<__half*>(out16), rows,
+                                                                          period, d / 4);
+    CONE_LAUNCH_CHECK("add_row_table_f16");
     return CONE_OK;
 }
 
