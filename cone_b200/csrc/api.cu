@@ -838,10 +838,11 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
     // tensor-core mode: q|k|v of encoder layer 0 once per frame (the reference, and a per-window GEMM, compute the
     // same row once for every window that contains the frame: k * Nq * Lv rows against n_frames)
     uint16_t* frame_qkv = nullptr;
+    uint16_t* vidproj16 = nullptr;
     const int d = dm.hidden;
     const std::string l0 = "transformer.encoder.layers.0.self_attn";
     if (precision == CONE_PREC_TC) {
-        uint16_t* vidproj16 = head.get<uint16_t>(n_frames * d);
+        vidproj16 = head.get<uint16_t>(n_frames * d);
         frame_qkv = head.get<uint16_t>(n_frames * 3 * d);
         if (!head.fits()) {
             set_error("cone_ground_windows: workspace too small for the per-frame projections");
@@ -873,8 +874,9 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         tc_set_scratch(w->tc, a.base + a.used, avail > a.used ? avail - a.used : 0);
         // text projection once per query (the reference recomputes it for each of the k windows)
         CONE_TRY(input_proj(c, "input_txt_proj", tok + q0 * Lt * dm.t_dim, n * Lt, dm.t_dim, txtproj, pb));
+        uint16_t* txtproj16 = nullptr;
         if (precision == CONE_PREC_TC) {  // token q|k|v of encoder layer 0, once per query token
-            uint16_t* txtproj16 = a.get<uint16_t>(n * Lt * d);
+            txtproj16 = a.get<uint16_t>(n * Lt * d);
             uint16_t* token_qkv = a.get<uint16_t>(n * Lt * 3 * d);
             tc_set_scratch(w->tc, a.base + a.used, avail > a.used ? avail - a.used : 0);
             CONE_TRY(f32_to_f16_rows(txtproj, d, txtproj16, n * Lt, d, c.s));
@@ -889,7 +891,7 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
                                         topk, Lt, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
         if (precision == CONE_PREC_TC) {
-            CONE_TRY(gather_window_rows_f16(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src16, B, Lv, Lt,
+            CONE_TRY(gather_window_rows_h2h(vidproj16, n_frames, cb.vid_base, txtproj16, cb.txt_base, cb.src16, B, Lv, Lt,
                                             dm.hidden, c.s));
         } else {
             CONE_TRY(gather_window_rows(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));

@@ -46,6 +46,9 @@ int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, 
                  int d, int table_lv, cudaStream_t s);
 int gather_window_rows_f16(const float* vidproj, int64_t n_vid_rows, const int64_t* vid_base, const float* txtproj,
                            const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s);
+// same gather from fp16 source rows (bit-identical to rounding the fp32 rows)
+int gather_window_rows_h2h(const uint16_t* vid16, int64_t n_vid_rows, const int64_t* vid_base, const uint16_t* txt16,
+                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s);
 // fp16 operands for the tensor-core path: plain16 = fp16(src), pos16 = fp16(src + pos); either may be null
 int add_pos_rows_f16(const float* src, const float* pos_table, const int32_t* vlen, uint16_t* plain16, uint16_t* pos16,
                      int64_t B, int Lv, int Lt, int d, int table_lv, cudaStream_t s);

@@ -203,6 +203,28 @@ __global__ void gather_window_rows_f16_kernel(const float* __restrict__ vidproj,
     }
 }
 
+// fp16 rows -> fp16 window rows, 16-byte chunks (the per-frame / per-token projections already exist in fp16)
+__global__ void gather_window_rows_h2h_kernel(const uint4* __restrict__ vid16, int64_t n_vid_rows,
+                                              const int64_t* __restrict__ vid_base, const uint4* __restrict__ txt16,
+                                              const int64_t* __restrict__ txt_base, uint4* __restrict__ src16, int64_t B,
+                                              int Lv, int Lt, int d8) {
+    const int S = Lv + Lt;
+    const int64_t total = B * S * d8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % d8);
+        const int64_t row = i / d8;
+        const int r = (int)(row % S);
+        const int64_t b = row / S;
+        if (r < Lv) {
+            int64_t fr = vid_base[b] + r;
+            fr = fr < n_vid_rows ? fr : n_vid_rows - 1;
+            src16[i] = __ldg(vid16 + fr * d8 + c);
+        } else {
+            src16[i] = __ldg(txt16 + (txt_base[b] + (r - Lv)) * d8 + c);
+        }
+    }
+}
+
 __global__ void add_row_table_kernel(const float* __restrict__ x, const float* __restrict__ table,
                                      float* __restrict__ out, int64_t rows, int period, int d4) {
     const int64_t total = rows * d4;
@@ -319,6 +341,18 @@ int gather_window_rows_f16(const float* vidproj, int64_t n_vid_rows, const int64
     gather_window_rows_f16_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(
         vidproj, n_vid_rows, vid_base, txtproj, txt_base, reinterpret_cast<__half*>(src16), B, Lv, Lt, d / 4);
     CONE_LAUNCH_CHECK("gather_window_rows_f16");
+    return CONE_OK;
+}
+
+int gather_window_rows_h2h(const uint16_t* vid16, int64_t n_vid_rows, const int64_t* vid_base, const uint16_t* txt16,
+                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s) {
+    if (B == 0) return CONE_OK;
+    CONE_REQUIRE((d & 7) == 0, "gather_window_rows_h2h: d must be a multiple of 8");
+    ProfScope ps(s, P_ROWOPS, 0.0, 4.0 * (double)B * (Lv + Lt) * d);
+    gather_window_rows_h2h_kernel<<<grid_for(B * (Lv + Lt) * (d / 8), 256), 256, 0, s>>>(
+        reinterpret_cast<const uint4*>(vid16), n_vid_rows, vid_base, reinterpret_cast<const uint4*>(txt16), txt_base,
+        reinterpret_cast<uint4*>(src16), B, Lv, Lt, d / 8);
+    CONE_LAUNCH_CHECK("gather_window_rows_h2h");
     return CONE_OK;
 }
 

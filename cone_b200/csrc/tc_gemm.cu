@@ -201,13 +201,15 @@ constexpr int FAST_STAGES = 4;  // A + W ring depth of the streamlined epilogues
 // Epilogue variants.  The shape that carries most of the model's 2.9 M rows is compile-time specialised (no flag
 // tests, 64-column steps, accumulator released right after the second TMEM load, one staging box per warp):
 //   EPI_PLAIN16: bias (+ReLU) -> fp16                                         (QKV, FFN1, decoder K|V projections)
+//   EPI_LN16:    the generic code below with its flags fixed at compile time to bias + fp16 residual (TMA boxes) ->
+//                LayerNorm -> fp16                                             (out_proj, FFN2)
 //   EPI_GENERIC: every flag at run time: residual through TMA boxes, LayerNorm over the 256-wide row (out_proj,
 //                FFN2), fp32 in/out decoder-side GEMMs, cone_linear, BN = 128
 // (A specialised LayerNorm epilogue that read the residual with per-row global loads and kept the 128 columns of a
 // row in registers was measured 20-50 % SLOWER than the generic TMA-box one and was dropped: profiles/r01_notes.md.)
 // ncu on the generic epilogue at 2 warps per scheduler: ~9 issue cycles per instruction, a third of the stalls in
 // LDCU -> UISETP -> BRA chains of the run-time flags, another tenth on bias loads issued after the TMEM wait.
-enum { EPI_PLAIN16 = 0, EPI_GENERIC = 2 };
+enum { EPI_PLAIN16 = 0, EPI_LN16 = 1, EPI_GENERIC = 2 };
 
 // 64 fp32 values of one row -> fp16 -> this lane's row of a [32 x 64] 128-byte-swizzled box -> one TMA store
 __device__ __forceinline__ void store_box16(const float* x, uint8_t* box, const CUtensorMap* map, int col, int row0,
@@ -238,7 +240,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmC32, TcEpilogue ep, int64_t M, int N, int K) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int HALF = BN / 2;  // columns per epilogue warp
-    constexpr bool FAST = MODE != EPI_GENERIC;
+    constexpr bool FAST = MODE == EPI_PLAIN16;
     constexpr int NSTAGE = WRES ? WRES_STAGES : (FAST ? FAST_STAGES : STAGES);
     constexpr int B_RING = WRES ? WRES_KBLOCKS * B_BYTES : NSTAGE * B_BYTES;  // resident tile or ring
     constexpr int N_BOX = (WRES || FAST) ? EPI_WARPS : 2 * EPI_WARPS;         // one box per warp unless generic + ring
@@ -413,7 +415,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* res_box = sRes + ew * BOX_BYTES;
         uint64_t* rbar = &rfull[ew];
         uint32_t rphase = 0;
-        const bool ln = ep.ln_g != nullptr;
+        // EPI_LN16 fixes the flags at compile time (the run-time tests were LDCU -> UISETP -> BRA chains in every chunk)
+        constexpr bool LNM = MODE == EPI_LN16;
+        const bool ln = LNM ? true : ep.ln_g != nullptr;
+        const bool f_r16 = LNM ? true : ep.has_r16 != 0;
+        const bool f_c16 = LNM ? true : ep.has_c16 != 0;
+        const bool f_c32 = LNM ? false : ep.has_c32 != 0;
+        const bool f_bias = LNM ? true : ep.bias != nullptr;
+        const float* f_R32 = LNM ? nullptr : ep.R32;
+        const bool f_relu = LNM ? false : ep.relu != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
 
@@ -429,22 +439,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // The fp16 residual arrives as a [32 x 64] box: requested at even 32-column steps, consumed in two halves.
             auto load_sub = [&](int c, float* x) {
                 const int sub = (c >> 5) & 1;
-                if (ep.has_r16 && sub == 0 && lane == 0) {
+                if (f_r16 && sub == 0 && lane == 0) {
                     // res_box doubles as the fp32 store box (see below) and, in WRES mode, as the result box
-                    if (WRES || ep.has_c32) tma_store_wait_read<0>();
+                    if (WRES || f_c32) tma_store_wait_read<0>();
                     mbar_expect_tx(rbar, BOX_BYTES);
                     tma_load_2d(res_box, &tmR, rbar, n0 + c, row0);
                 }
                 tmem_ld_32x32(taddr + c, x);
                 tmem_ld_wait();
-                if (ep.bias) {
+                if (f_bias) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c) + q);
                         x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
                     }
                 }
-                if (ep.has_r16) {
+                if (f_r16) {
                     if (sub == 0) {
                         mbar_wait(rbar, rphase);
                         rphase ^= 1;
@@ -462,10 +472,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (sub == 1) __syncwarp();  // every lane has read the box before the next TMA load overwrites it
                 }
-                if (ep.R32) {  // small-M path: plain row loads
+                if (f_R32) {  // small-M path: plain row loads
                     const int64_t row = (int64_t)row0 + lane;
                     if (row < M) {
-                        const float4* r4 = reinterpret_cast<const float4*>(ep.R32 + row * ep.ldr32 + n0 + c);
+                        const float4* r4 = reinterpret_cast<const float4*>(f_R32 + row * ep.ldr32 + n0 + c);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 b = r4[q];
@@ -514,12 +524,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else {
                     load_sub(c, x);
-                    if (ep.relu) {
+                    if (f_relu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
                     }
                 }
-                if (ep.has_c16) {  // two 32-column steps fill one [32 rows x 64 fp16] 128-byte-swizzled box
+                if (f_c16) {  // two 32-column steps fill one [32 rows x 64 fp16] 128-byte-swizzled box
                     const int sub = (c >> 5) & 1;
                     if (sub == 0) {
                         if (lane == 0) tma_store_wait_read<0>();  // previous store has released the box
@@ -547,10 +557,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (ep.has_c32) {  // one box of 32 rows x 32 fp32 columns
+                if (f_c32) {  // one box of 32 rows x 32 fp32 columns
                     // with an fp16 output in flight the fp32 box is staged in res_box (free in this pass: the host
                     // side only allows both outputs together with LayerNorm or without an fp16 residual)
-                    uint8_t* box32 = ep.has_c16 ? res_box : out_box;
+                    uint8_t* box32 = f_c16 ? res_box : out_box;
                     if (lane == 0) tma_store_wait_read<0>();
                     __syncwarp();
 #pragma unroll
@@ -650,7 +660,7 @@ constexpr size_t tc_smem_bytes() {
     constexpr size_t tail = 64 * sizeof(uint64_t) + 8 * 32 * 8 + 64;  // barriers, LayerNorm partials, TMEM slot
     constexpr size_t b_bytes = (size_t)BN * BK * 2;
     if (WRES) return (size_t)WRES_STAGES * A_BYTES + WRES_KBLOCKS * b_bytes + 8 * BOX_BYTES + tail;
-    if (MODE != EPI_GENERIC) return (size_t)FAST_STAGES * (A_BYTES + b_bytes) + 8 * BOX_BYTES + tail;
+    if (MODE == EPI_PLAIN16) return (size_t)FAST_STAGES * (A_BYTES + b_bytes) + 8 * BOX_BYTES + tail;
     return 1024 + (size_t)STAGES * (A_BYTES + b_bytes) + 16 * BOX_BYTES + tail;
 }
 static_assert(tc_smem_bytes<256, true, EPI_GENERIC>() <= 232448, "weights-resident layout exceeds 227 KB");
@@ -792,13 +802,16 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
             mapA, w->map, mapR, mapC16, mapC32, ep, g.M, g.N, g.K);                                                     \
     } while (0)
     const bool plain16 = w->BN == 256 && g.C16 && !g.C32 && !g.R16 && !g.R32 && !g.ln_g && g.bias;
+    const bool ln16 = w->BN == 256 && g.C16 && !g.C32 && g.R16 && !g.R32 && g.ln_g && g.bias && !g.relu;
     if (w->BN != 256) {
         CONE_TC_LAUNCH(128, false, EPI_GENERIC);
     } else if (wres) {
         if (plain16) CONE_TC_LAUNCH(256, true, EPI_PLAIN16);
+        else if (ln16) CONE_TC_LAUNCH(256, true, EPI_LN16);
         else CONE_TC_LAUNCH(256, true, EPI_GENERIC);
     } else {
         if (plain16) CONE_TC_LAUNCH(256, false, EPI_PLAIN16);
+        else if (ln16) CONE_TC_LAUNCH(256, false, EPI_LN16);
         else CONE_TC_LAUNCH(256, false, EPI_GENERIC);
     }
 #undef CONE_TC_LAUNCH
