@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcone_b200.so")
 SOURCES = ["api.cu", "gemm_simt.cu", "tc_gemm.cu", "rowops.cu", "attention.cu", "prefilter.cu", "pool_match.cu",
-           "fuse_nms.cu"]
+           "fuse_nms.cu", "eval.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -989,3 +989,22 @@ extern "C" int cone_temporal_nms(const double* st, const double* ed, const doubl
     CONE_REQUIRE(keep_out && n_keep_out && (n == 0 || (st && ed && score)), "null argument");
     return temporal_nms_single(st, ed, score, n, nms_thd, max_after_nms, keep_out, n_keep_out, (cudaStream_t)stream);
 }
+
+extern "C" int cone_eval_recall(const double* nms, const int32_t* nms_count, const double* gt, int32_t n_queries,
+                                int32_t max_after_nms, const int32_t* topk_host, int32_t n_topk,
+                                const double* thresholds_host, int32_t n_thresholds, int32_t flavour, int64_t* hits,
+                                double* top1_iou, void* stream) {
+    CONE_REQUIRE(n_queries == 0 || (nms && nms_count && gt), "null argument");
+    CONE_REQUIRE(hits && topk_host && thresholds_host && max_after_nms >= 1, "null argument");
+    return eval_recall(nms, nms_count, gt, n_queries, max_after_nms, topk_host, n_topk, thresholds_host, n_thresholds,
+                       flavour, hits, top1_iou, (cudaStream_t)stream);
+}
+
+extern "C" int cone_eval_window_recall(const int32_t* ranklist, int32_t ranklist_stride, const double* gt,
+                                       int32_t n_queries, double clip_length, int32_t max_v_l, const int32_t* topk_host,
+                                       int32_t n_topk, int64_t* hits, void* stream) {
+    CONE_REQUIRE(n_queries == 0 || (ranklist && gt), "null argument");
+    CONE_REQUIRE(hits && topk_host && ranklist_stride >= 1, "null argument");
+    return eval_window_recall(ranklist, ranklist_stride, gt, n_queries, clip_length, max_v_l, topk_host, n_topk, hits,
+                              (cudaStream_t)stream);
+}

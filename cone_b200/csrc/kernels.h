@@ -117,4 +117,15 @@ int fuse_nms(const float* pred_spans, const float* prob_fg, const float* match, 
 int temporal_nms_single(const double* st, const double* ed, const double* score, int n, double nms_thd,
                         int max_after_nms, int32_t* keep_out, int32_t* n_keep_out, cudaStream_t s);
 
+
+// ---------------------------------------------------------------- eval.cu
+// R@K / IoU hit counters from the stage-3 output (flavour 0: evaluate_mad.py, 1: evaluate_ego4d_nlq.py); topk / thr are
+// HOST arrays; hits [3, n_topk, n_thr] int64 is ACCUMULATED into; top1_iou (nullable) [n_queries, 3] fp64
+int eval_recall(const double* nms, const int32_t* nms_count, const double* gt, int n_queries, int max_after,
+                const int32_t* topk_host, int n_topk, const double* thr_host, int n_thr, int flavour, int64_t* hits,
+                double* top1_iou, cudaStream_t s);
+// window pre-filtering recall (evaluate_pre_filtered_window.py); hits [n_topk] int64 is accumulated into
+int eval_window_recall(const int32_t* ranklist, int ranklist_stride, const double* gt, int n_queries, double clip_length,
+                       int max_v_l, const int32_t* topk_host, int n_topk, int64_t* hits, cudaStream_t s);
+
 }  // namespace cone

@@ -306,6 +306,48 @@ class ConeEngine:
                    "cone_fuse_nms")
         return out, cnt, rows, rcnt
 
+    # ---- metric counters ---------------------------------------------------
+    def eval_recall(self, nms: torch.Tensor, nms_count: torch.Tensor, gt: torch.Tensor, topk=(1, 5),
+                    thresholds=(0.3, 0.5), flavour: str = "mad", hits: Optional[torch.Tensor] = None,
+                    want_top1: bool = False):
+        """R@K / IoU hit counters of `evaluate_mad.py:60-104` (flavour "mad") or `evaluate_ego4d_nlq.py:65-117`
+        ("ego4d") from the stage-3 output.  gt [Nq, 2] fp64 seconds, packed-query order.  Returns
+        (hits [3, len(topk), len(thresholds)] int64 on the device — accumulated into when passed in —, top-1 IoU
+        [Nq, 3] fp64 or None)."""
+        nms = _need(nms, torch.float64, "nms")
+        nms_count = _need(nms_count, torch.int32, "nms_count")
+        gt = _need(gt, torch.float64, "gt")
+        nq_ = nms.shape[0]
+        if gt.shape != (nq_, 2):
+            raise ValueError(f"gt must be [{nq_}, 2], got {tuple(gt.shape)}")
+        if hits is None:
+            hits = torch.zeros((3, len(topk), len(thresholds)), dtype=torch.int64, device=nms.device)
+        hits = _need(hits, torch.int64, "hits")
+        if hits.shape != (3, len(topk), len(thresholds)):
+            raise ValueError("hits must be [3, len(topk), len(thresholds)]")
+        top1 = torch.empty((nq_, 3), dtype=torch.float64, device=nms.device) if want_top1 else None
+        tk = (C.c_int32 * len(topk))(*[int(k) for k in topk])
+        th = (C.c_double * len(thresholds))(*[float(t) for t in thresholds])
+        _lib.check(self.lib.cone_eval_recall(_ptr(nms), _ptr(nms_count), _ptr(gt), nq_, nms.shape[2], tk, len(topk), th,
+                                             len(thresholds), {"mad": 0, "ego4d": 1}[flavour], _ptr(hits), _ptr(top1),
+                                             _stream()), "cone_eval_recall")
+        return hits, top1
+
+    def eval_window_recall(self, ranklist: torch.Tensor, gt: torch.Tensor, topk=(1, 5, 10, 30, 50),
+                           hits: Optional[torch.Tensor] = None, cfg: Optional[ConeConfig] = None) -> torch.Tensor:
+        """Window pre-filtering recall counters (`evaluate_pre_filtered_window.py:30-72`) from the rank-lists."""
+        cfg = cfg or self.cfg
+        ranklist = _need(ranklist, torch.int32, "ranklist")
+        gt = _need(gt, torch.float64, "gt")
+        if hits is None:
+            hits = torch.zeros((len(topk),), dtype=torch.int64, device=ranklist.device)
+        hits = _need(hits, torch.int64, "hits")
+        tk = (C.c_int32 * len(topk))(*[int(k) for k in topk])
+        _lib.check(self.lib.cone_eval_window_recall(_ptr(ranklist), ranklist.shape[1], _ptr(gt), ranklist.shape[0],
+                                                    float(cfg.clip_length), cfg.max_v_l, tk, len(topk), _ptr(hits),
+                                                    _stream()), "cone_eval_window_recall")
+        return hits
+
     # ---- the whole path -------------------------------------------------------------------------
     def ground(self, frames: torch.Tensor, qb: QueryBatch, want_rows: bool = False) -> GroundingOutput:
         """Stages 0-3 for concatenated raw `frames` [n_frames, Dv] and the packed queries `qb` (both on the

@@ -131,3 +131,72 @@ def recall_at_k(results: Dict[str, dict], gt: Dict[str, Sequence[float]], mode: 
         for i, k in enumerate(topk):
             rec[i] += hit[:k].any(axis=0)
     return rec / max(len(results), 1)
+
+
+@dataclasses.dataclass
+class MetricCounters:
+    """Device-side metric state accumulated over steps (and summed over ranks by `sharding.reduce_counters`)."""
+    topk: Sequence[int]
+    thresholds: Sequence[float]
+    window_topk: Sequence[int]
+    hits: torch.Tensor  # [3, len(topk), len(thresholds)] int64, rankings in MODES order
+    window_hits: torch.Tensor  # [len(window_topk)] int64
+    n_queries: torch.Tensor  # [1] int64
+    top1_iou: List[torch.Tensor] = dataclasses.field(default_factory=list)  # per step [Nq, 3] fp64 (Ego4D mIoU)
+
+    def recall_mad(self, mode: str = "fusion") -> np.ndarray:
+        """`evaluate_mad.evaluate_nlq_performance`'s table [len(topk), len(thresholds)]: float32 counters divided
+        by the number of queries in float32, as `recall_x_iou /= len(submission)` does."""
+        h = self.hits[MODES.index(mode)].cpu().numpy().astype(np.float32)
+        return h / np.float32(max(int(self.n_queries.item()), 1))
+
+    def recall_ego4d(self, mode: str = "fusion"):
+        """`evaluate_ego4d_nlq.evaluate_nlq_performance`: (recall [len(thresholds), len(topk)] float64, mIoU)."""
+        m = MODES.index(mode)
+        n = max(int(self.n_queries.item()), 1)
+        rec = self.hits[m].cpu().numpy().astype(np.float64).T / n
+        iou = torch.cat([t[:, m] for t in self.top1_iou]).cpu().numpy() if self.top1_iou else np.zeros(0)
+        with np.errstate(invalid="ignore"):
+            return rec, float(np.mean(iou)) if iou.size else float("nan")
+
+    def window_recall(self) -> np.ndarray:
+        return self.window_hits.cpu().numpy().astype(np.float32) / np.float32(max(int(self.n_queries.item()), 1))
+
+
+def new_counters(device, topk=(1, 5), thresholds=(0.3, 0.5), window_topk=(1, 5, 10, 30, 50)) -> MetricCounters:
+    return MetricCounters(tuple(topk), tuple(thresholds), tuple(window_topk),
+                          torch.zeros((3, len(topk), len(thresholds)), dtype=torch.int64, device=device),
+                          torch.zeros((len(window_topk),), dtype=torch.int64, device=device),
+                          torch.zeros((1,), dtype=torch.int64, device=device))
+
+
+def accumulate_metrics(engine: ConeEngine, counters: MetricCounters, step: HostStep, out: GroundingOutput,
+                       gt: Dict[str, Sequence[float]], flavour: str = "mad") -> None:
+    """Adds one step's hits to `counters` on the device: no prediction leaves the GPU."""
+    g = torch.tensor([[float(gt[q][0]), float(gt[q][1])] for q in step.qb.query_ids], dtype=torch.float64)
+    g = g.reshape(-1, 2).to(engine.device, non_blocking=True)
+    _, top1 = engine.eval_recall(out.nms, out.nms_count, g, counters.topk, counters.thresholds, flavour,
+                                 hits=counters.hits, want_top1=(flavour == "ego4d"))
+    if top1 is not None:
+        counters.top1_iou.append(top1)
+    engine.eval_window_recall(out.ranklist, g, counters.window_topk, hits=counters.window_hits)
+    counters.n_queries += g.shape[0]
+
+
+def evaluate_dataset(engine: ConeEngine, videos: Sequence[np.ndarray], queries, gt: Dict[str, Sequence[float]],
+                     flavour: str = "mad", topk=(1, 5), thresholds=(0.3, 0.5), window_topk=(1, 5, 10, 30, 50),
+                     max_frames_per_step: int = 1 << 20, video_ids: Optional[Sequence[int]] = None) -> MetricCounters:
+    """Stages 0-3 + metric counters over (this rank's share of) a dataset; only the counters are read back."""
+    counters = new_counters(engine.device, topk, thresholds, window_topk)
+    lens = [len(v) for v in videos]
+    mine = None if video_ids is None else set(video_ids)
+    for ids in plan_steps(lens, queries, max_frames_per_step):
+        ids = [v for v in ids if mine is None or v in mine]
+        if not ids:
+            continue
+        step = stage_step(engine.cfg, videos, queries, ids)
+        if step.qb.tok_len.numel() == 0:
+            continue
+        out = run_step(engine, step)
+        accumulate_metrics(engine, counters, step, out, gt, flavour)
+    return counters

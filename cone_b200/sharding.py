@@ -58,3 +58,17 @@ def gather_predictions(nms: torch.Tensor, count: torch.Tensor, qid: torch.Tensor
             dist.all_gather(list(buf.unbind(0)), pad(t), group=group)
         outs.append(torch.cat([buf[r, : sizes[r]] for r in range(world)], dim=0))
     return tuple(outs)
+
+
+def reduce_counters(counters, group=None):
+    """Sum the device-side metric counters of `inference.MetricCounters` over ranks (one all-reduce per tensor:
+    integer hit counts simply add up) and all-gather the per-query top-1 IoUs (Ego4D mIoU)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return counters
+    for t in (counters.hits, counters.window_hits, counters.n_queries):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if counters.top1_iou:
+        local = torch.cat(counters.top1_iou)
+        gathered = gather_predictions(local, local.new_zeros((local.shape[0], 1)), group=group)[0]
+        counters.top1_iou = [gathered]
+    return counters

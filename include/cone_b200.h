@@ -35,7 +35,7 @@ extern "C" {
 
 /* compute precision of the dense projections */
 #define CONE_PREC_FP32 0 /* fp32 CUDA-core GEMMs: parity mode, 1e-5 vs the reference */
-#define CONE_PREC_TC 1   /* tcgen05 tensor-core GEMMs (bf16 operands, fp32 accumulate): 1e-3 */
+#define CONE_PREC_TC 1   /* tcgen05 tensor-core GEMMs (fp16 operands, fp32 accumulate): 1e-3 */
 
 /* Model / window hyper-parameters (cone/config.py:73-125; values per dataset in
  * cone/scripts/train_{ego4d,mad}.sh). */
@@ -171,6 +171,28 @@ int cone_fuse_nms(const float* pred_spans, const float* prob_fg, const float* ma
  * output order; n_keep_out [1]. */
 int cone_temporal_nms(const double* st, const double* ed, const double* score, int32_t n, double nms_thd,
                       int32_t max_after_nms, int32_t* keep_out, int32_t* n_keep_out, void* stream);
+
+/* ---- A14 / SURVEY.md §8(f)1  metric counters on the device, straight from cone_fuse_nms' output.
+ * cone_eval_recall: for each query and each of the 3 rankings, IoU of its first max(topk) predictions
+ * with the ground truth gt [n_queries, 2] fp64 (seconds) and, per (rank K, threshold), whether any of
+ * the first K exceeds it (strict >).  flavour 0 = standalone_eval/evaluate_mad.py:32-37, 60-104
+ * (float32 hull IoU against float32 thresholds), flavour 1 =
+ * standalone_eval/evaluate_ego4d_nlq.py:41-62, 65-117 (float64).  topk_host / thresholds_host are
+ * HOST arrays (at most CONE_EVAL_MAX_TOPK / CONE_EVAL_MAX_THRESHOLDS entries).  hits
+ * [3, n_topk, n_thr] int64 is ADDED to (zero it first; counters of several steps or ranks simply
+ * add up; recall = hits / #queries); top1_iou (nullable) [n_queries, 3] fp64 = IoU of the first
+ * prediction (Ego4D's mIoU is its mean).
+ * cone_eval_window_recall: standalone_eval/evaluate_pre_filtered_window.py:30-72: whether any of the
+ * first K ranked windows lies in range(floor(st/clip_length/stride), ceil(ed/clip_length/stride)+1),
+ * stride = int(max_v_l / 2).  hits [n_topk] int64 is added to. */
+#define CONE_EVAL_MAX_TOPK 8
+#define CONE_EVAL_MAX_THRESHOLDS 8
+int cone_eval_recall(const double* nms, const int32_t* nms_count, const double* gt, int32_t n_queries,
+                     int32_t max_after_nms, const int32_t* topk_host, int32_t n_topk, const double* thresholds_host,
+                     int32_t n_thresholds, int32_t flavour, int64_t* hits, double* top1_iou, void* stream);
+int cone_eval_window_recall(const int32_t* ranklist, int32_t ranklist_stride, const double* gt, int32_t n_queries,
+                            double clip_length, int32_t max_v_l, const int32_t* topk_host, int32_t n_topk,
+                            int64_t* hits, void* stream);
 
 /* ---- measurement hooks (no reference counterpart) --------------------------------------------
  * Per-kernel timing: when enabled, every launch of the calling thread is bracketed by CUDA events on

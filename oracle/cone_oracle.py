@@ -412,6 +412,44 @@ def recall_at_k_iou(pred: Dict[str, List[List[float]]], gt: Dict[str, Sequence[f
     return rec / max(len(pred), 1)
 
 
+def recall_ego4d(pred: Dict[str, List[List[float]]], gt: Dict[str, Sequence[float]],
+                 thresholds=(0.3, 0.5), topk=(1, 5)):
+    """standalone_eval/evaluate_ego4d_nlq.py:41-62, 65-117: float64 IoU (intersection and hull both clamped at 0),
+    results[thr][k] = mean over queries of any(IoU[:k] > thr); mIoU = mean IoU of the FIRST prediction.
+    Returns (recall [len(thresholds), len(topk)] float64, mIoU)."""
+    hits = [[[] for _ in topk] for _ in thresholds]
+    top1 = []
+    for qid, rows in pred.items():
+        p = np.array([r[:2] for r in rows], dtype=np.float64)
+        g = np.array([list(gt[qid])], dtype=np.float64)
+        inter = np.maximum(0.0, np.minimum(p[:, 1, None], g[None, :, 1]) - np.maximum(p[:, 0, None], g[None, :, 0]))
+        hull = np.maximum(0.0, np.maximum(p[:, 1, None], g[None, :, 1]) - np.minimum(p[:, 0, None], g[None, :, 0]))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            overlap = 1.0 * inter / hull
+        top1.append(overlap[0])
+        for t, thr in enumerate(thresholds):
+            for r, k in enumerate(topk):
+                hits[t][r].append((overlap > thr)[:k].any())
+    return np.array(hits).mean(axis=-1), float(np.mean(top1))
+
+
+def window_recall(ranklists: Dict[str, List[int]], gt: Dict[str, Sequence[float]], clip_length: float, max_v_l: int,
+                  topk=(1, 5, 10, 30, 50)) -> np.ndarray:
+    """standalone_eval/evaluate_pre_filtered_window.py:30-72: a query is recalled at K when one of its first K ranked
+    window ids lies in range(floor(start / sws), ceil(end / sws) + 1), start / end = timestamps / clip_length in
+    frames, sws = int(max_v_l / 2).  float32 result, as the reference's torch.zeros accumulator."""
+    sws = int(max_v_l / 2)
+    rec = torch.zeros(len(topk))
+    for qid, wl in ranklists.items():
+        start, end = gt[qid][0] / clip_length, gt[qid][1] / clip_length
+        true = set(range(math.floor(start / sws), math.ceil(end / sws) + 1))
+        bools = [w in true for w in wl[: max(topk)]]
+        for i, k in enumerate(topk):
+            rec[i] += float(any(bools[:k]))
+    rec /= max(len(ranklists), 1)
+    return rec.numpy()
+
+
 # --------------------------------------------------------------------------------------
 # the whole path: eval_epoch stages 0-3                        cone/inference.py:227-322
 # --------------------------------------------------------------------------------------
