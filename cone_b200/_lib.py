@@ -34,6 +34,7 @@ SIGNATURES = {
     "cone_version": (C.c_int, []),
     "cone_weights_create": (C.c_int, [_p, _sz, C.POINTER(ConeDims), _p, C.POINTER(_p)]),
     "cone_weights_destroy": (None, [_p]),
+    "cone_weights_update": (C.c_int, [_p, _p, _sz, _p]),
     "cone_weights_expected_floats": (_sz, [C.POINTER(ConeDims)]),
     "cone_workspace_bytes": (_sz, [C.POINTER(ConeDims), _i64, _i32, _i32]),
     "cone_prepare_workspace_bytes": (_sz, [C.POINTER(ConeDims), _i64]),
@@ -48,6 +49,8 @@ SIGNATURES = {
     "cone_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, C.c_int, _p]),
     "cone_clip_matching": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _sz, C.c_int, _p]),
     "cone_fuse_nms": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _f32, _f64, _i32, _i32, _p, _p, _p, _p, _p]),
+    "cone_fuse_nms_ex": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _f32, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p,
+                                   _p]),
     "cone_temporal_nms": (C.c_int, [_p, _p, _p, _i32, _f64, _i32, _p, _p, _p]),
     "cone_eval_recall": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _p, _i32, _i32, _p, _p, _p]),
     "cone_eval_window_recall": (C.c_int, [_p, _i32, _p, _i32, _f64, _i32, _p, _i32, _p, _p]),

@@ -207,44 +207,32 @@ extern "C" void cone_weights_destroy(cone_weights* w) {
     delete w;
 }
 
-extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, const cone_dims* dims, void* stream,
-                                   cone_weights** out) {
-    CONE_TRY(check_dims(dims));
-    CONE_REQUIRE(blob_host != nullptr && out != nullptr, "null argument");
-    cudaStream_t s = (cudaStream_t)stream;
+// Host staging shared by create / update: the state dict padded per tensor to a multiple of 4 floats (float4 loads are
+// always aligned) and the derived [K-proj rows; V-proj rows] cross-attention weights of all decoder layers.
+static int stage_blob(cone_weights* w, const float* blob_host, size_t n_floats, std::vector<float>& staged,
+                      std::vector<float>& der) {
+    const cone_dims* dims = &w->dims;
     std::vector<std::pair<std::string, size_t>> l;
     layout(*dims, l);
-    cone_weights* w = new cone_weights();
-    w->dims = *dims;
     size_t n = 0;
-    for (auto& e : l) {
-        // keep every tensor 16-byte aligned on the device: all sizes are multiples of 4 floats except the
-        // 2- and 1-element head biases, which come last in their groups; pad offsets instead of assuming
-        w->off[e.first] = n;
-        n += e.second;
-    }
+    for (auto& e : l) n += e.second;
     if (n != n_floats) {
         set_error("state dict has %zu floats, expected %zu for these dims", n_floats, n);
-        delete w;
         return CONE_ERR_INVALID;
     }
-    // device layout: each tensor padded to a multiple of 4 floats so float4 loads are always aligned
-    std::vector<float> staged;
+    staged.clear();
     staged.reserve(n + 4 * l.size());
-    {
-        size_t src = 0;
-        for (auto& e : l) {
-            w->off[e.first] = staged.size();
-            staged.insert(staged.end(), blob_host + src, blob_host + src + e.second);
-            while (staged.size() & 3) staged.push_back(0.f);
-            src += e.second;
-        }
+    size_t src = 0;
+    for (auto& e : l) {
+        w->off[e.first] = staged.size();
+        staged.insert(staged.end(), blob_host + src, blob_host + src + e.second);
+        while (staged.size() & 3) staged.push_back(0.f);
+        src += e.second;
     }
-    w->n_floats = staged.size();
     const size_t d = dims->hidden;
     const int DL = dims->dec_layers;
     // derived: concatenated cross-attention K / V projections of all decoder layers (memory is shared)
-    std::vector<float> der((size_t)DL * d * d * 2 + (size_t)DL * d * 2);
+    der.assign((size_t)DL * d * d * 2 + (size_t)DL * d * 2, 0.f);
     float* kw = der.data();  // layout kw | vw | kb | vb: [K-proj rows; V-proj rows] form one [2*DL*d, d] weight
     float* vw = kw + (size_t)DL * d * d;
     float* kb = vw + (size_t)DL * d * d;
@@ -258,6 +246,25 @@ extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, cons
         memcpy(kb + (size_t)i * d, inb + d, sizeof(float) * d);
         memcpy(vb + (size_t)i * d, inb + 2 * d, sizeof(float) * d);
     }
+    return CONE_OK;
+}
+
+extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, const cone_dims* dims, void* stream,
+                                   cone_weights** out) {
+    CONE_TRY(check_dims(dims));
+    CONE_REQUIRE(blob_host != nullptr && out != nullptr, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    cone_weights* w = new cone_weights();
+    w->dims = *dims;
+    std::vector<float> staged, der;
+    int r = stage_blob(w, blob_host, n_floats, staged, der);
+    if (r != CONE_OK) {
+        delete w;
+        return r;
+    }
+    w->n_floats = staged.size();
+    const size_t d = dims->hidden;
+    const int DL = dims->dec_layers;
     const size_t pos_floats = (size_t)(dims->max_v_l + 1) * dims->max_v_l * d;
     cudaError_t e = cudaMalloc(&w->blob, sizeof(float) * w->n_floats);
     if (e == cudaSuccess) e = cudaMalloc(&w->derived, sizeof(float) * (der.size() + pos_floats));
@@ -274,12 +281,33 @@ extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, cons
     w->dec_kb = w->dec_vw + (size_t)DL * d * d;
     w->dec_vb = w->dec_kb + (size_t)DL * d;
     w->pos_table = w->derived + der.size();
-    int r = build_pos_table(w->pos_table, dims->max_v_l, (int)d, s);
+    r = build_pos_table(w->pos_table, dims->max_v_l, (int)d, s);
     if (r != CONE_OK) {
         cone_weights_destroy(w);
         return r;
     }
     *out = w;
+    return CONE_OK;
+}
+
+// Forward declaration: defined with the tensor-core helpers below.
+namespace { int fill_pos_proj(cone_weights* mw, cudaStream_t s); }
+
+// Live weights (cone/train.py:164-168 evaluates every few epochs on the weights being trained): the
+// new state dict is written INTO the existing device buffers and every derived tensor (decoder K|V concatenation, fp16
+// copies, position-projection tables) is recomputed in place, so the handle, all device pointers, TMA descriptors and
+// captured CUDA graphs stay valid.  Ordered on `stream` after the work already queued there.
+extern "C" int cone_weights_update(cone_weights* w, const float* blob_host, size_t n_floats, void* stream) {
+    CONE_REQUIRE(w != nullptr && blob_host != nullptr, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<float> staged, der;
+    CONE_TRY(stage_blob(w, blob_host, n_floats, staged, der));
+    CONE_REQUIRE(staged.size() == w->n_floats, "cone_weights_update: layout changed");
+    CONE_CUDA(cudaMemcpyAsync(w->blob, staged.data(), sizeof(float) * w->n_floats, cudaMemcpyHostToDevice, s));
+    CONE_CUDA(cudaMemcpyAsync(w->derived, der.data(), sizeof(float) * der.size(), cudaMemcpyHostToDevice, s));
+    CONE_CUDA(cudaStreamSynchronize(s));  // staging vectors die at return
+    CONE_TRY(tc_weights_refresh(w->tc, s));
+    if (w->pos_proj) CONE_TRY(fill_pos_proj(w, s));
     return CONE_OK;
 }
 
@@ -642,33 +670,42 @@ int match_core(const Ctx& c, const float* frames, int64_t n_frames, const CoreBu
     return CONE_OK;
 }
 
+// pos . [Wq; Wk]^T per encoder layer and pos . Wk^T per decoder layer, for every (valid length, row): fp32 tables (and
+// the fp16 copy the mma.sync cross-attention reads), recomputed whenever the weights change
+int fill_pos_proj(cone_weights* mw, cudaStream_t s) {
+    const cone_dims& dm = mw->dims;
+    const size_t d = dm.hidden, rows = (size_t)(dm.max_v_l + 1) * dm.max_v_l;
+    const size_t per_enc = rows * 2 * d, dec = rows * dm.dec_layers * d;
+    mw->pos_qk.clear();
+    for (int l = 0; l < dm.enc_layers; ++l) {
+        float* out = mw->pos_proj + per_enc * l;
+        GemmParams g;
+        g.A = mw->pos_table; g.lda = d;
+        g.W = mw->p("transformer.encoder.layers." + std::to_string(l) + ".self_attn.in_proj_weight"); g.ldw = d;
+        g.C = out; g.ldc = 2 * d; g.M = rows; g.N = 2 * d; g.K = d;
+        CONE_TRY(sgemm_nt(g, s));
+        mw->pos_qk.push_back(out);
+    }
+    mw->pos_kdec = mw->pos_proj + per_enc * dm.enc_layers;
+    GemmParams g;
+    g.A = mw->pos_table; g.lda = d; g.W = mw->dec_kw; g.ldw = d;
+    g.C = mw->pos_kdec; g.ldc = dm.dec_layers * d; g.M = rows; g.N = dm.dec_layers * d; g.K = d;
+    CONE_TRY(sgemm_nt(g, s));
+    CONE_TRY(f32_to_f16_rows(mw->pos_kdec, dm.dec_layers * d, mw->pos_kdec16, rows, (int)(dm.dec_layers * d), s));
+    (void)dec;
+    return CONE_OK;
+}
+
 int ensure_tc(const cone_weights* w, int prec, cudaStream_t s) {
     if (prec != CONE_PREC_TC) return CONE_OK;
     cone_weights* mw = const_cast<cone_weights*>(w);
     if (mw->tc == nullptr) CONE_TRY(tc_weights_create(&mw->tc, s));
     if (mw->pos_proj == nullptr) {
-        // pos . [Wq; Wk]^T per encoder layer and pos . Wk^T per decoder layer, for every (valid length, row): fp32
         const cone_dims& dm = w->dims;
         const size_t d = dm.hidden, rows = (size_t)(dm.max_v_l + 1) * dm.max_v_l;
-        const size_t per_enc = rows * 2 * d, dec = rows * dm.dec_layers * d;
-        CONE_CUDA(cudaMalloc(&mw->pos_proj, sizeof(float) * (per_enc * dm.enc_layers + dec)));
-        mw->pos_qk.clear();
-        for (int l = 0; l < dm.enc_layers; ++l) {
-            float* out = mw->pos_proj + per_enc * l;
-            GemmParams g;
-            g.A = w->pos_table; g.lda = d;
-            g.W = w->p("transformer.encoder.layers." + std::to_string(l) + ".self_attn.in_proj_weight"); g.ldw = d;
-            g.C = out; g.ldc = 2 * d; g.M = rows; g.N = 2 * d; g.K = d;
-            CONE_TRY(sgemm_nt(g, s));
-            mw->pos_qk.push_back(out);
-        }
-        mw->pos_kdec = mw->pos_proj + per_enc * dm.enc_layers;
-        GemmParams g;
-        g.A = w->pos_table; g.lda = d; g.W = w->dec_kw; g.ldw = d;
-        g.C = mw->pos_kdec; g.ldc = dm.dec_layers * d; g.M = rows; g.N = dm.dec_layers * d; g.K = d;
-        CONE_TRY(sgemm_nt(g, s));
-        CONE_CUDA(cudaMalloc(&mw->pos_kdec16, sizeof(uint16_t) * dec));
-        CONE_TRY(f32_to_f16_rows(mw->pos_kdec, dm.dec_layers * d, mw->pos_kdec16, rows, (int)(dm.dec_layers * d), s));
+        CONE_CUDA(cudaMalloc(&mw->pos_proj, sizeof(float) * (rows * 2 * d * dm.enc_layers + rows * dm.dec_layers * d)));
+        CONE_CUDA(cudaMalloc(&mw->pos_kdec16, sizeof(uint16_t) * rows * dm.dec_layers * d));
+        CONE_TRY(fill_pos_proj(mw, s));
     }
     return CONE_OK;
 }
@@ -816,7 +853,7 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
                                    float* prob_fg, float* match, int32_t* win_start, int32_t* win_len, void* workspace,
                                    size_t workspace_bytes, int precision, void* stream) {
     CONE_REQUIRE(w && frames_raw && vidproj && q_video_start && q_video_len && ranklist && tok && tok_len && cls_norm &&
-                     q_batch && pred_spans && prob_fg && match && win_start && win_len && workspace,
+                     pred_spans && prob_fg && match && win_start && win_len && workspace,
                  "null argument");
     CONE_REQUIRE(topk >= 1 && n_batches >= 1 && n_queries >= 0, "bad sizes");
     CONE_TRY(check_prec(precision));
@@ -834,7 +871,7 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         set_error("cone_ground_windows: workspace too small");
         return CONE_ERR_WORKSPACE;
     }
-    CONE_TRY(batch_max_len(win_len, q_batch, n_queries, topk, batch_max, n_batches, c.s));
+    if (q_batch) CONE_TRY(batch_max_len(win_len, q_batch, n_queries, topk, batch_max, n_batches, c.s));
     // tensor-core mode: q|k|v of encoder layer 0 once per frame (the reference, and a per-window GEMM, compute the
     // same row once for every window that contains the frame: k * Nq * Lv rows against n_frames)
     uint16_t* frame_qkv = nullptr;
@@ -889,7 +926,7 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
             cb.n_frames = n_frames;
         }
         CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
-                                        topk, Lt, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
+                                        topk, Lt, Lv, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
         if (precision == CONE_PREC_TC) {
             CONE_TRY(gather_window_rows_h2h(vidproj16, n_frames, cb.vid_base, txtproj16, cb.txt_base, cb.src16, B, Lv, Lt,
                                             dm.hidden, c.s));
@@ -982,6 +1019,18 @@ extern "C" int cone_fuse_nms(const float* pred_spans, const float* prob_fg, cons
     CONE_REQUIRE(pred_spans && prob_fg && match && win_start && win_len && out && out_count, "null argument");
     return fuse_nms(pred_spans, prob_fg, match, win_start, win_len, n_queries, topk, nq, clip_length, nms_thd,
                     max_before_nms, max_after_nms, out, out_count, rows_out, rows_count, (cudaStream_t)stream);
+}
+
+extern "C" int cone_fuse_nms_ex(const float* pred_spans, const float* prob_fg, const float* match,
+                                const int32_t* win_start, const int32_t* win_len, int32_t n_queries, int32_t topk, int32_t nq,
+                                float clip_length, double nms_thd, int32_t max_before_nms, int32_t max_after_nms,
+                                int32_t fixed_duration, int32_t sort_within_window, double* out, int32_t* out_count,
+                                double* rows_out, int32_t* rows_count, void* stream) {
+    CONE_REQUIRE(pred_spans && prob_fg && match && win_start && win_len && out && out_count, "null argument");
+    CONE_REQUIRE(fixed_duration >= 0, "cone_fuse_nms_ex: fixed_duration must be >= 0");
+    return fuse_nms(pred_spans, prob_fg, match, win_start, win_len, n_queries, topk, nq, clip_length, nms_thd,
+                    max_before_nms, max_after_nms, out, out_count, rows_out, rows_count, (cudaStream_t)stream,
+                    fixed_duration, sort_within_window != 0);
 }
 
 extern "C" int cone_temporal_nms(const double* st, const double* ed, const double* score, int32_t n, double nms_thd,

@@ -102,8 +102,9 @@ __host__ __device__ inline size_t smem_bytes(int N) { return (size_t)N * (10 * 8
 __global__ void __launch_bounds__(NMS_THREADS)
 fuse_nms_kernel(const float* __restrict__ pred_spans, const float* __restrict__ prob_fg, const float* __restrict__ match,
                 const int32_t* __restrict__ win_start, const int32_t* __restrict__ win_len, int topk, int nq,
-                float clip_length, double nms_thd, int max_before, int max_after, double* __restrict__ out,
-                int32_t* __restrict__ out_count, double* __restrict__ rows_out, int32_t* __restrict__ rows_count) {
+                float clip_length, double nms_thd, int max_before, int max_after, int fixed_duration, int sort_windows,
+                double* __restrict__ out, int32_t* __restrict__ out_count, double* __restrict__ rows_out,
+                int32_t* __restrict__ rows_count) {
     extern __shared__ __align__(16) unsigned char raw[];
     __shared__ int sh_head, sh_M, sh_cnt;
     __shared__ double sh_mm[4];
@@ -124,13 +125,15 @@ fuse_nms_kernel(const float* __restrict__ pred_spans, const float* __restrict__ 
     // A10: per window, seconds in fp32 (no FMA contraction), stable sort by fp32 score, 4-decimal rounding
     for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
         const int64_t g = (int64_t)q * topk + j;
-        const float dur = (float)win_len[g], vs = (float)win_start[g];
+        // eval_epoch scales by the window's own length (inference.py:75-78), the demo by max_v_l (cone_localizator.py:188)
+        const float dur = fixed_duration > 0 ? (float)fixed_duration : (float)win_len[g], vs = (float)win_start[g];
         int idx[MAX_NQ];
         float key[MAX_NQ];
         for (int a = 0; a < nq; ++a) {
             const float k = prob_fg[g * nq + a];
             int pos = a;
-            while (pos > 0 && key[pos - 1] < k) {  // strict: equal scores keep slot order
+            // the demo keeps slot order (cone_localizator.py:186-197): no per-window sort
+            while (sort_windows && pos > 0 && key[pos - 1] < k) {  // strict: equal scores keep slot order
                 key[pos] = key[pos - 1];
                 idx[pos] = idx[pos - 1];
                 --pos;
@@ -258,7 +261,7 @@ temporal_nms_single_kernel(const double* __restrict__ st, const double* __restri
 int fuse_nms(const float* pred_spans, const float* prob_fg, const float* match, const int32_t* win_start,
              const int32_t* win_len, int n_queries, int topk, int nq, float clip_length, double nms_thd,
              int max_before_nms, int max_after_nms, double* out, int32_t* out_count, double* rows_out,
-             int32_t* rows_count, cudaStream_t s) {
+             int32_t* rows_count, cudaStream_t s, int fixed_duration, int sort_windows) {
     if (n_queries == 0) return CONE_OK;
     CONE_REQUIRE(nq >= 1 && nq <= MAX_NQ, "fuse_nms: 1..%d moment slots supported", MAX_NQ);
     CONE_REQUIRE(max_after_nms >= 1 && max_before_nms >= 1, "fuse_nms: max_before/after_nms must be >= 1");
@@ -268,8 +271,9 @@ int fuse_nms(const float* pred_spans, const float* prob_fg, const float* match, 
         CONE_CUDA(cudaFuncSetAttribute(fuse_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(s, P_NMS);
     fuse_nms_kernel<<<n_queries, NMS_THREADS, smem, s>>>(pred_spans, prob_fg, match, win_start, win_len, topk, nq,
-                                                         clip_length, nms_thd, max_before_nms, max_after_nms, out,
-                                                         out_count, rows_out, rows_count);
+                                                         clip_length, nms_thd, max_before_nms, max_after_nms,
+                                                         fixed_duration, sort_windows, out, out_count, rows_out,
+                                                         rows_count);
     CONE_LAUNCH_CHECK("fuse_nms");
     return CONE_OK;
 }

@@ -97,8 +97,8 @@ int batch_max_len(const int32_t* win_len, const int32_t* q_batch, int n_queries,
 // per-chunk descriptors for queries [q0, q0+nq)
 int fill_window_desc_chunk(const int64_t* q_video_start, const int32_t* win_start, const int32_t* win_len,
                            const int32_t* tok_len, const int32_t* q_batch, const int32_t* batch_max, int q0, int nqc,
-                           int topk, int Lt, int64_t* vid_base, int32_t* vlen, int64_t* txt_base, int32_t* tlen,
-                           int32_t* pad_len, int32_t* qidx, cudaStream_t s);
+                           int topk, int Lt, int fixed_pad, int64_t* vid_base, int32_t* vlen, int64_t* txt_base,
+                           int32_t* tlen, int32_t* pad_len, int32_t* qidx, cudaStream_t s);  // q_batch null: pad_len = fixed_pad
 
 // ---------------------------------------------------------------- pool_match.cu
 // pooled[(b*nq+j), :] = mean of zero-padded window rows [start, min(end, pad_len)) (model.py:186-200)
@@ -113,7 +113,7 @@ int norm_dot(const float* p, const float* t, const int32_t* qidx, float* out, in
 int fuse_nms(const float* pred_spans, const float* prob_fg, const float* match, const int32_t* win_start,
              const int32_t* win_len, int n_queries, int topk, int nq, float clip_length, double nms_thd,
              int max_before_nms, int max_after_nms, double* out, int32_t* out_count, double* rows_out,
-             int32_t* rows_count, cudaStream_t s);
+             int32_t* rows_count, cudaStream_t s, int fixed_duration = 0, int sort_windows = 1);
 int temporal_nms_single(const double* st, const double* ed, const double* score, int n, double nms_thd,
                         int max_after_nms, int32_t* keep_out, int32_t* n_keep_out, cudaStream_t s);
 

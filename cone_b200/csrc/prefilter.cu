@@ -100,7 +100,7 @@ __global__ void fill_window_desc_chunk_kernel(const int64_t* __restrict__ q_vide
                                               const int32_t* __restrict__ win_start, const int32_t* __restrict__ win_len,
                                               const int32_t* __restrict__ tok_len, const int32_t* __restrict__ q_batch,
                                               const int32_t* __restrict__ batch_max, int q0, int nqc, int topk, int Lt,
-                                              int64_t* vid_base, int32_t* vlen, int64_t* txt_base, int32_t* tlen,
+                                              int fixed_pad, int64_t* vid_base, int32_t* vlen, int64_t* txt_base, int32_t* tlen,
                                               int32_t* pad_len, int32_t* qidx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nqc * topk) return;
@@ -111,7 +111,8 @@ __global__ void fill_window_desc_chunk_kernel(const int64_t* __restrict__ q_vide
     vlen[i] = win_len[g];
     txt_base[i] = (int64_t)ql * Lt;
     tlen[i] = tok_len[q];
-    pad_len[i] = batch_max[q_batch[q]];
+    // q_batch == null: every window is padded to `fixed_pad` rows (run_on_video/cone_localizator.py:141-165)
+    pad_len[i] = q_batch ? batch_max[q_batch[q]] : fixed_pad;
     qidx[i] = ql;
 }
 
@@ -155,11 +156,11 @@ int batch_max_len(const int32_t* win_len, const int32_t* q_batch, int n_queries,
 
 int fill_window_desc_chunk(const int64_t* q_video_start, const int32_t* win_start, const int32_t* win_len,
                            const int32_t* tok_len, const int32_t* q_batch, const int32_t* batch_max, int q0, int nqc,
-                           int topk, int Lt, int64_t* vid_base, int32_t* vlen, int64_t* txt_base, int32_t* tlen,
-                           int32_t* pad_len, int32_t* qidx, cudaStream_t s) {
+                           int topk, int Lt, int fixed_pad, int64_t* vid_base, int32_t* vlen, int64_t* txt_base,
+                           int32_t* tlen, int32_t* pad_len, int32_t* qidx, cudaStream_t s) {
     if (nqc == 0) return CONE_OK;
     fill_window_desc_chunk_kernel<<<cdiv(nqc * topk, 256), 256, 0, s>>>(q_video_start, win_start, win_len, tok_len,
-                                                                       q_batch, batch_max, q0, nqc, topk, Lt, vid_base,
+                                                                       q_batch, batch_max, q0, nqc, topk, Lt, fixed_pad, vid_base,
                                                                        vlen, txt_base, tlen, pad_len, qidx);
     CONE_LAUNCH_CHECK("fill_window_desc_chunk");
     return CONE_OK;

@@ -71,7 +71,10 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restric
         const float4 v = xr[i];
         sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
-    const float denom = sqrtf(warp_sum(sq)) + eps;
+    // eps >= 0: x / (||x|| + eps) (utils/basic_utils.py:97-99); eps < 0: x / max(||x||, -eps) = torch F.normalize
+    // (run_on_video/cone_localizator.py:127, 131)
+    const float nrm = sqrtf(warp_sum(sq));
+    const float denom = eps >= 0.f ? nrm + eps : fmaxf(nrm, -eps);
     float4* orow = reinterpret_cast<float4*>(out + row * D);
     for (int i = lane; i < nv; i += 32) {
         const float4 v = xr[i];

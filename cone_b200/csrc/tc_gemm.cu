@@ -743,6 +743,14 @@ static int get_w16(TcWeights* t, const float* W, int N, int K, cudaStream_t s, c
     return CONE_OK;
 }
 
+// The fp32 master weights changed in place (cone_weights_update): re-round every cached fp16 copy into its existing
+// buffer, so device pointers and TMA descriptors (and any CUDA graph that captured them) stay valid.
+int tc_weights_refresh(TcWeights* t, cudaStream_t s) {
+    if (!t) return CONE_OK;
+    for (auto& kv : t->cache) CONE_TRY(f32_to_f16(kv.first, kv.second.K, kv.second.ptr, kv.second.N, kv.second.K, s));
+    return CONE_OK;
+}
+
 int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     CONE_REQUIRE(t != nullptr, "tc_gemm: tensor-core weights not initialised");
     CONE_REQUIRE(tc_gemm_supported(g.M, g.N, g.K), "tc_gemm: unsupported shape M=%lld N=%d K=%d", (long long)g.M, g.N, g.K);

@@ -8,6 +8,7 @@ struct TcWeights;  // bf16 weight copies + TMA descriptors, owned by the cone_we
 
 int tc_weights_create(TcWeights** out, cudaStream_t s);
 void tc_weights_destroy(TcWeights* t);
+int tc_weights_refresh(TcWeights* t, cudaStream_t s);  // after the fp32 master weights changed in place
 // per-call activation staging (bf16 copy of A) lives in the caller's workspace
 size_t tc_scratch_bytes(int64_t max_rows, int max_k);
 void tc_set_scratch(TcWeights* t, void* scratch, size_t bytes);

@@ -151,13 +151,15 @@ class ConeEngine:
         if want == 0:
             _lib.check(-1, "cone_weights_expected_floats")
         assert blob.numel() == want, (blob.numel(), want)
+        if self._handle:  # live weights: rewrite the existing handle in place (pointers and captured graphs stay valid)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.cone_weights_update(self._handle, C.c_void_p(blob.data_ptr()), blob.numel(), _stream()),
+                           "cone_weights_update")
+            return
         new = C.c_void_p(0)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cone_weights_create(C.c_void_p(blob.data_ptr()), blob.numel(), C.byref(self.dims),
                                                     _stream(), C.byref(new)), "cone_weights_create")
-        if self._handle:
-            torch.cuda.synchronize(self.device)
-            self.lib.cone_weights_destroy(self._handle)
         self._handle = new
 
     def __del__(self):
@@ -186,13 +188,14 @@ class ConeEngine:
         _lib.check(self.lib.cone_l2_normalize(_ptr(x), _ptr(out), rows, x.shape[-1], eps, _stream()), "cone_l2_normalize")
         return out
 
-    def adapter(self, x: torch.Tensor, residual: bool = False) -> torch.Tensor:
+    def adapter(self, x: torch.Tensor, residual: bool = False, precision: Optional[str] = None) -> torch.Tensor:
         """`model.adapter_layer(x)` (cone/model.py:80); `residual=True` gives `adapter_layer(x) + x`."""
         x = _need(x, torch.float32, "x")
         out = torch.empty_like(x)
         rows = x.numel() // x.shape[-1]
+        prec = self.precision if precision is None else {"fp32": _lib.PREC_FP32, "tc": _lib.PREC_TC}[precision]
         ws, n = self._wsargs(rows * self.cfg.hidden_dim * 4 + rows * max(self.cfg.v_feat_dim, 1024) * 2 + (1 << 20))
-        _lib.check(self.lib.cone_adapter(self._handle, _ptr(x), _ptr(out), rows, int(residual), ws, n, self.precision,
+        _lib.check(self.lib.cone_adapter(self._handle, _ptr(x), _ptr(out), rows, int(residual), ws, n, prec,
                                          _stream()), "cone_adapter")
         return out
 
@@ -288,7 +291,10 @@ class ConeEngine:
                                                _ptr(out), ws, nb, self.precision, _stream()), "cone_clip_matching")
         return out
 
-    def fuse_nms(self, pred_spans, prob_fg, match, win_start, win_len, want_rows=False, cfg: Optional[ConeConfig] = None):
+    def fuse_nms(self, pred_spans, prob_fg, match, win_start, win_len, want_rows=False, cfg: Optional[ConeConfig] = None,
+                 fixed_duration: int = 0, sort_within_window: bool = True):
+        """Stage 3.  `fixed_duration` / `sort_within_window` select the single-video front end's variant
+        (run_on_video/cone_localizator.py:183-219); the defaults are eval_epoch's."""
         cfg = cfg or self.cfg
         nq_, k, nslot = prob_fg.shape
         dev = prob_fg.device
@@ -296,14 +302,15 @@ class ConeEngine:
         cnt = torch.zeros((nq_, 3), dtype=torch.int32, device=dev)
         rows = torch.zeros((nq_, k * nslot, 4), dtype=torch.float64, device=dev) if want_rows else None
         rcnt = torch.zeros((nq_,), dtype=torch.int32, device=dev) if want_rows else None
-        _lib.check(self.lib.cone_fuse_nms(_ptr(_need(pred_spans, torch.float32, "pred_spans")),
-                                          _ptr(_need(prob_fg, torch.float32, "prob_fg")),
-                                          _ptr(_need(match, torch.float32, "match")),
-                                          _ptr(_need(win_start, torch.int32, "win_start")),
-                                          _ptr(_need(win_len, torch.int32, "win_len")), nq_, k, nslot,
-                                          float(np.float32(cfg.clip_length)), float(cfg.nms_thd), cfg.max_before_nms,
-                                          cfg.max_after_nms, _ptr(out), _ptr(cnt), _ptr(rows), _ptr(rcnt), _stream()),
-                   "cone_fuse_nms")
+        _lib.check(self.lib.cone_fuse_nms_ex(_ptr(_need(pred_spans, torch.float32, "pred_spans")),
+                                             _ptr(_need(prob_fg, torch.float32, "prob_fg")),
+                                             _ptr(_need(match, torch.float32, "match")),
+                                             _ptr(_need(win_start, torch.int32, "win_start")),
+                                             _ptr(_need(win_len, torch.int32, "win_len")), nq_, k, nslot,
+                                             float(np.float32(cfg.clip_length)), float(cfg.nms_thd), cfg.max_before_nms,
+                                             cfg.max_after_nms, int(fixed_duration), int(bool(sort_within_window)),
+                                             _ptr(out), _ptr(cnt), _ptr(rows), _ptr(rcnt), _stream()),
+                   "cone_fuse_nms_ex")
         return out, cnt, rows, rcnt
 
     # ---- metric counters ---------------------------------------------------
@@ -382,6 +389,45 @@ class ConeEngine:
             "cone_ground_windows")
         # stage 3
         nms, cnt, rows, rcnt = self.fuse_nms(spans, prob, match, wstart, wlen, want_rows=want_rows)
+        return GroundingOutput(ranklist, wstart, wlen, spans, prob, match, nms, cnt, rows, rcnt)
+
+    # ---- the single-video front end ------------------------------------------
+    def prepare_video(self, frames: torch.Tensor):
+        """Per-video part of `CONELocalizator.predict_moment` (run_on_video/cone_localizator.py:127-136):
+        F.normalize of the frames, adapter + residual WITHOUT re-normalisation (the ranking features), and the
+        per-frame `input_vid_proj` of the NORMALISED frames (what the demo slices into windows).
+        Returns (xn, ctx, vidproj), all on the device."""
+        frames = _need(frames, torch.float32, "frames")
+        xn = self.l2_normalize(frames, -1e-5)
+        ctx = self.adapter(xn, residual=True, precision="fp32")  # the window ranking stays fp32 in every mode
+        _, vidproj = self.video_prepare(xn, want_ctx=False)
+        return xn, ctx, vidproj
+
+    def ground_video(self, xn: torch.Tensor, ctx: torch.Tensor, vidproj: torch.Tensor, qb: QueryBatch,
+                     cfg: Optional[ConeConfig] = None, want_rows: bool = False) -> GroundingOutput:
+        """Per-query part of `predict_moment` (:131-221) for queries of ONE video prepared by `prepare_video`:
+        tokens F.normalize'd, CLS used raw, windows zero-padded to max_v_l for pooling, spans scaled by max_v_l,
+        slots in slot order, fusion ranking with the demo's NMS constants (pass them in `cfg`).  No host sync."""
+        cfg = cfg or self.cfg
+        dev = xn.device
+        nq, k, ns = qb.tok_len.numel(), cfg.topk_window, cfg.num_queries
+        tok_norm = self.l2_normalize(qb.tokens, -1e-5)
+        scores, score_offsets = self.frame_scores(ctx, qb, qb.cls)
+        stride = cfg.num_window(qb.max_video_frames)
+        ranklist = self.window_ranklist(scores, score_offsets, qb.q_video_len, ranklist_stride=stride)
+        spans = torch.empty((nq, k, ns, 2), dtype=torch.float32, device=dev)
+        prob = torch.empty((nq, k, ns), dtype=torch.float32, device=dev)
+        match = torch.empty((nq, k, ns), dtype=torch.float32, device=dev)
+        wstart = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        wlen = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        ws, nb = self._wsargs()
+        _lib.check(self.lib.cone_ground_windows(
+            self._handle, _ptr(xn), xn.shape[0], _ptr(vidproj), _ptr(qb.q_video_start), _ptr(qb.q_video_len),
+            _ptr(ranklist), stride, _ptr(tok_norm), _ptr(qb.tok_len), _ptr(qb.cls), None, 1,
+            nq, k, _ptr(spans), _ptr(prob), _ptr(match), _ptr(wstart), _ptr(wlen), ws, nb, self.precision, _stream()),
+            "cone_ground_windows")
+        nms, cnt, rows, rcnt = self.fuse_nms(spans, prob, match, wstart, wlen, want_rows=want_rows, cfg=cfg,
+                                             fixed_duration=cfg.max_v_l, sort_within_window=False)
         return GroundingOutput(ranklist, wstart, wlen, spans, prob, match, nms, cnt, rows, rcnt)
 
 

@@ -64,6 +64,11 @@ int cone_version(void);
 int cone_weights_create(const float* blob_host, size_t n_floats, const cone_dims* dims, void* stream,
                         cone_weights** out);
 void cone_weights_destroy(cone_weights* w);
+/* Live weights: `model.load_state_dict` on an existing model, as the training loop's periodic
+ * `eval_epoch` sees it (cone/train.py:164-168).  Writes the new state dict into the handle's existing
+ * device buffers and recomputes every derived tensor in place: device pointers, TMA descriptors and
+ * CUDA graphs captured over this handle stay valid.  Ordered after prior work on `stream`. */
+int cone_weights_update(cone_weights* w, const float* blob_host, size_t n_floats, void* stream);
 size_t cone_weights_expected_floats(const cone_dims* dims);
 
 /* ---- workspace sizing ---------------------------------------------------------------------- */
@@ -73,7 +78,9 @@ size_t cone_workspace_bytes(const cone_dims* dims, int64_t n_windows, int32_t lv
 size_t cone_prepare_workspace_bytes(const cone_dims* dims, int64_t n_frames);
 
 /* ---- A1  host L2 normalisation: x / (||x|| + eps)  (utils/basic_utils.py:97-99, applied at
- * cone/ego4d_mad_dataloader.py:274-280, 459, 472).  eps = 0 gives x / ||x||.  In place if out == x. */
+ * cone/ego4d_mad_dataloader.py:274-280, 459, 472).  eps = 0 gives x / ||x||.  eps < 0 selects
+ * torch's F.normalize form x / max(||x||, -eps) (run_on_video/cone_localizator.py:127, 131).
+ * In place if out == x. */
 int cone_l2_normalize(const float* x, float* out, int64_t rows, int32_t dim, float eps, void* stream);
 
 /* ---- A2  stage 0 (cone/inference.py:250-260) + per-frame `input_vid_proj` (cone/model.py:100).
@@ -128,7 +135,9 @@ int cone_window_ranklist(const float* frame_score, const int64_t* score_offsets,
  *   cls_norm [n_queries, Dv]
  *   q_batch [n_queries] id of the reference eval batch the query falls in (dataset index /
  *       eval_bsz): proposals are mean-pooled over the window zero-padded to that batch's longest
- *       window, exactly as the reference does; n_batches = max id + 1
+ *       window, exactly as the reference does; n_batches = max id + 1.
+ *       NULL = every window is pooled over max_v_l zero-padded rows, the fixed padding of the
+ *       single-video front end (run_on_video/cone_localizator.py:141-165)
  * Outputs, [n_queries, topk, nq, ...]: pred_spans (cx,w), prob_fg = softmax(logits)[0], match;
  * win_start / win_len [n_queries, topk] int32 (len 0 = window absent: video has < topk windows). */
 int cone_ground_windows(const cone_weights* w, const float* frames_raw, int64_t n_frames, const float* vidproj,
@@ -165,6 +174,16 @@ int cone_fuse_nms(const float* pred_spans, const float* prob_fg, const float* ma
                   const int32_t* win_len, int32_t n_queries, int32_t topk, int32_t nq, float clip_length,
                   double nms_thd, int32_t max_before_nms, int32_t max_after_nms, double* out, int32_t* out_count,
                   double* rows_out, int32_t* rows_count, void* stream);
+
+/* Same with the two knobs of the single-video front end (run_on_video/cone_localizator.py:183-219):
+ * fixed_duration > 0 scales every span by that many frames instead of the window's own length
+ * (`span_cxw_to_xx(spans) * args.max_v_l`), sort_within_window = 0 keeps the moment slots of a window
+ * in slot order.  cone_fuse_nms == cone_fuse_nms_ex(fixed_duration 0, sort_within_window 1). */
+int cone_fuse_nms_ex(const float* pred_spans, const float* prob_fg, const float* match, const int32_t* win_start,
+                     const int32_t* win_len, int32_t n_queries, int32_t topk, int32_t nq, float clip_length,
+                     double nms_thd, int32_t max_before_nms, int32_t max_after_nms, int32_t fixed_duration,
+                     int32_t sort_within_window, double* out, int32_t* out_count, double* rows_out,
+                     int32_t* rows_count, void* stream);
 
 /* ---- A13  `temporal_nms(predictions, nms_thd, max_after_nms)` (utils/temporal_nms.py:25-74) on
  * one list: st/ed/score [n] fp64 in input order; keep_out [max_after_nms] indices into the input in

@@ -451,6 +451,56 @@ def window_recall(ranklists: Dict[str, List[int]], gt: Dict[str, Sequence[float]
 
 
 # --------------------------------------------------------------------------------------
+# single-video front end      run_on_video/cone_localizator.py:84-221
+# --------------------------------------------------------------------------------------
+def predict_moment(sd: Dict[str, Tensor], cfg, video_feats: Tensor, text_token_feats: Tensor, text_cls_feat: Tensor,
+                   max_before_nms: int = 100, nms_thd: float = 0.5, max_after_nms: int = 5) -> Dict[str, object]:
+    """`CONELocalizator.predict_moment` for one (video, query).  Differences from eval_epoch that are kept:
+    F.normalize (x / max(||x||, 1e-5)) of frames and tokens (:127-131); the NORMALISED frames are what is
+    sliced, projected and pooled (:156); the adapter output is NOT re-normalised before ranking and the CLS
+    vector is used raw (:133-138); every window is zero-padded to max_v_l / max_q_l (:141-165, so more than
+    max_q_l tokens is an error, as in the reference); spans are scaled by max_v_l, not by the window's length
+    (:188); slots are not sorted within a window (:186-197); only the fusion ranking is produced (:199-219).
+    The rank-list sort is stable (module docstring).  A video with fewer than topk_window windows makes the
+    reference run the model on all-masked rows (NaN rows enter the fusion); here only real windows are used.
+    Returns {"ranklist", "windows", "pred_spans", "prob_fg", "match", "rows", "moments"}."""
+    k, Lv, Lt = cfg.topk_window, cfg.max_v_l, cfg.max_q_l
+    with torch.no_grad():
+        v = F.normalize(video_feats.float(), dim=-1, eps=1e-5)
+        tok = F.normalize(text_token_feats.float(), dim=-1, eps=1e-5)
+        if tok.shape[0] > Lt:
+            raise ValueError(f"{tok.shape[0]} tokens exceed max_q_l={Lt} (pad_feature would fail in the reference)")
+        a = adapter(sd, v)
+        ranklist = window_ranklist(torch.einsum("db,b->d", a, text_cls_feat.float()), Lv)
+        stride = int(Lv / 2)
+        wins = [(max((i - 1) * stride, 0), min((i - 1) * stride + Lv, len(v))) for i in ranklist[:k]]
+        B = len(wins)
+        vid = torch.zeros((B, Lv, v.shape[1]))
+        vmask = torch.zeros((B, Lv))
+        txt = torch.zeros((B, Lt, tok.shape[1]))
+        tmask = torch.zeros((B, Lt))
+        for i, (s0, e0) in enumerate(wins):
+            vid[i, : e0 - s0] = v[s0:e0]
+            vmask[i, : e0 - s0] = 1
+            txt[i, : len(tok)] = tok
+            tmask[i, : len(tok)] = 1
+        cls = text_cls_feat.float()[None].repeat(B, 1)
+        out = cone_forward(sd, txt, tmask, vid, vmask, cfg.nheads, cfg.enc_layers, cfg.dec_layers, cfg.n_input_proj)
+        prob = F.softmax(out["pred_logits"], -1)[..., 0]
+        match = clip_matching(sd, cls, vid, vmask, out["pred_spans"])
+        rows: List[List[float]] = []
+        for i, (s0, _) in enumerate(wins):
+            spans = (span_cxw_to_xx(out["pred_spans"][i]) * Lv + torch.tensor(s0, dtype=torch.int)) * cfg.clip_length
+            cur = torch.cat([spans, prob[i][:, None], match[i][:, None]], dim=1).tolist()
+            rows.extend([[round4(e) for e in r] for r in cur])
+    fused = score_fusion(rows)
+    moments = sorted([[kk[0], kk[1], vv[2]] for kk, vv in fused.items()], key=lambda x: x[2], reverse=True)
+    moments = temporal_nms(moments[:max_before_nms], nms_thd, max_after_nms)
+    return {"ranklist": ranklist, "windows": [(s0, e0 - s0) for s0, e0 in wins], "pred_spans": out["pred_spans"].numpy(),
+            "prob_fg": prob.numpy(), "match": match.numpy(), "rows": rows, "moments": moments}
+
+
+# --------------------------------------------------------------------------------------
 # the whole path: eval_epoch stages 0-3                        cone/inference.py:227-322
 # --------------------------------------------------------------------------------------
 def eval_pipeline(sd: Dict[str, Tensor], cfg, videos: Sequence[np.ndarray], queries, *, collect_raw: bool = True,

@@ -51,7 +51,12 @@ def _install_stubs() -> None:
         sys.modules["terminaltables"] = m
     if "easydict" not in sys.modules:
         m = types.ModuleType("easydict")
-        m.EasyDict = dict
+
+        class EasyDict(dict):  # attribute access is all run_on_video/cone_localizator.py:52 needs
+            __getattr__ = dict.__getitem__
+            __setattr__ = dict.__setitem__
+
+        m.EasyDict = EasyDict
         sys.modules["easydict"] = m
 
 
@@ -260,3 +265,31 @@ def run_reference_eval_epoch(cfg, sd, ds, capture_frame_scores: int = 0) -> Dict
                 c = torch.from_numpy(O.l2_normalize_np(q.cls))
                 out[q.query_id]["frame_score"] = torch.einsum("db,b->d", a, c).detach().numpy()
     return out
+
+
+def run_reference_localizer(cfg, sd, video_feats, text_token_feats, text_cls_feat):
+    """Reference `CONELocalizator.predict_moment` (run_on_video/cone_localizator.py:121-221) on one video / query.
+    The class is instantiated without its `__init__` (which builds the Ego4D model from a checkpoint file): the
+    model is the reference `CONE` with `sd` loaded, the module-level `args` are set from `cfg`, and the rank-list
+    sort is made stable.  Returns (moments, ranklist)."""
+    import_reference()
+    import run_on_video.cone_localizator as L
+    loc = object.__new__(L.CONELocalizator)
+    loc.device = "cpu"
+    loc.localizator = build_reference_model(cfg, sd)
+    loc.slide_window_size = int(cfg.max_v_l / 2)
+    loc.max_v_l = cfg.max_v_l
+    saved = dict(L.args)
+    L.args.update(max_v_l=cfg.max_v_l, max_q_l=cfg.max_q_l, topk_window=cfg.topk_window, clip_length=cfg.clip_length,
+                  v_appear_feat_dim=cfg.v_feat_dim, v_motion_feat_dim=cfg.v_feat_dim, t_feat_dim=cfg.t_feat_dim)
+    try:
+        with _stable_sort(L):
+            v = torch.as_tensor(video_feats)
+            ranklist = loc.compute_window_ranklist(
+                loc.localizator.adapter_layer(torch.nn.functional.normalize(v, dim=-1, eps=1e-5))
+                + torch.nn.functional.normalize(v, dim=-1, eps=1e-5), torch.as_tensor(text_cls_feat))
+            moments = loc.predict_moment(v, (torch.as_tensor(text_token_feats), torch.as_tensor(text_cls_feat)))
+    finally:
+        L.args.clear()
+        L.args.update(saved)
+    return moments, ranklist
