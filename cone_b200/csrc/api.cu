@@ -1,6 +1,8 @@
 // extern "C" entry points of libcone_b200 (include/cone_b200.h): weights handle, workspace planning and the
 // launch sequences of the coarse-to-fine path.  No hidden allocation outside the weights handle.
+#include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -104,6 +106,11 @@ struct cone_weights {
     std::vector<float*> pos_qk;
     float* pos_kdec = nullptr;
     uint16_t* pos_kdec16 = nullptr;  // fp16 copy for the mma.sync cross-attention
+    // memory-direct cross-attention of the tensor-core decoder (attention.cu): per decoder layer
+    //   xq_w [9 d, d], xq_b [9 d]: rows [0, d) = c Wq, rows d + h d + j = c Wk_h^T Wq_h (c = softmax scale * log2 e)
+    //   xo_w [d, 8 d], xo_b [d]:   columns h d + j = Wo[:, head h] Wv_h;  xo_b = Wo bv + bo
+    float* xattn = nullptr;
+    std::vector<float*> xq_w, xq_b, xo_w, xo_b;
     const float* p(const std::string& name) const { return blob + off.at(name); }
 };
 
@@ -202,6 +209,7 @@ extern "C" void cone_weights_destroy(cone_weights* w) {
     if (w->tc) tc_weights_destroy(w->tc);
     if (w->pos_proj) cudaFree(w->pos_proj);
     if (w->pos_kdec16) cudaFree(w->pos_kdec16);
+    if (w->xattn) cudaFree(w->xattn);
     if (w->blob) cudaFree(w->blob);
     if (w->derived) cudaFree(w->derived);
     delete w;
@@ -249,6 +257,78 @@ static int stage_blob(cone_weights* w, const float* blob_host, size_t n_floats, 
     return CONE_OK;
 }
 
+// Folded cross-attention weights (see cone_weights::xattn), computed in fp64 on the host from the staged state dict.
+static size_t xattn_floats_per_layer(size_t d) { return 9 * d * d + 9 * d + 8 * d * d + d; }
+static void build_xattn(const cone_weights* w, const std::vector<float>& staged, std::vector<float>& out) {
+    const size_t d = w->dims.hidden, H = w->dims.nheads, hd = d / H;
+    const int DL = w->dims.dec_layers;
+    const double c = (1.0 / sqrt((double)hd)) * 1.4426950408889634;
+    out.assign(xattn_floats_per_layer(d) * DL, 0.f);
+    std::vector<double> acc(d);
+    for (int l = 0; l < DL; ++l) {
+        const std::string p = "transformer.decoder.layers." + std::to_string(l) + ".multihead_attn";
+        const float* inw = staged.data() + w->off.at(p + ".in_proj_weight");
+        const float* inb = staged.data() + w->off.at(p + ".in_proj_bias");
+        const float* ow = staged.data() + w->off.at(p + ".out_proj.weight");
+        const float* ob = staged.data() + w->off.at(p + ".out_proj.bias");
+        const float *Wq = inw, *Wk = inw + d * d, *Wv = inw + 2 * d * d;
+        const float *bq = inb, *bv = inb + 2 * d;
+        float* xq_w = out.data() + xattn_floats_per_layer(d) * l;
+        float* xq_b = xq_w + 9 * d * d;
+        float* xo_w = xq_b + 9 * d;
+        float* xo_b = xo_w + 8 * d * d;
+        for (size_t i = 0; i < d * d; ++i) xq_w[i] = (float)(c * Wq[i]);
+        for (size_t i = 0; i < d; ++i) xq_b[i] = (float)(c * bq[i]);
+        for (size_t h = 0; h < H; ++h) {
+            for (size_t j = 0; j < d; ++j) {  // row d + h d + j = c * sum_e Wk[h hd + e, j] * Wq[h hd + e, :]
+                std::fill(acc.begin(), acc.end(), 0.0);
+                double bacc = 0.0;
+                for (size_t e = 0; e < hd; ++e) {
+                    const double wk = Wk[(h * hd + e) * d + j];
+                    const float* wq = Wq + (h * hd + e) * d;
+                    for (size_t i = 0; i < d; ++i) acc[i] += wk * wq[i];
+                    bacc += wk * bq[h * hd + e];
+                }
+                float* row = xq_w + (d + h * d + j) * d;
+                for (size_t i = 0; i < d; ++i) row[i] = (float)(c * acc[i]);
+                xq_b[d + h * d + j] = (float)(c * bacc);
+            }
+            for (size_t o = 0; o < d; ++o) {  // xo_w[o, h d + j] = sum_e Wo[o, h hd + e] * Wv[h hd + e, j]
+                std::fill(acc.begin(), acc.end(), 0.0);
+                for (size_t e = 0; e < hd; ++e) {
+                    const double wo = ow[o * d + h * hd + e];
+                    const float* wv = Wv + (h * hd + e) * d;
+                    for (size_t j = 0; j < d; ++j) acc[j] += wo * wv[j];
+                }
+                float* row = xo_w + o * 8 * d + h * d;
+                for (size_t j = 0; j < d; ++j) row[j] = (float)acc[j];
+            }
+        }
+        for (size_t o = 0; o < d; ++o) {
+            double a = ob[o];
+            for (size_t e = 0; e < d; ++e) a += (double)ow[o * d + e] * bv[e];
+            xo_b[o] = (float)a;
+        }
+    }
+}
+static int upload_xattn(cone_weights* w, const std::vector<float>& staged, cudaStream_t s) {
+    std::vector<float> x;
+    build_xattn(w, staged, x);
+    const size_t d = w->dims.hidden;
+    if (w->xattn == nullptr) CONE_CUDA(cudaMalloc(&w->xattn, sizeof(float) * x.size()));
+    CONE_CUDA(cudaMemcpyAsync(w->xattn, x.data(), sizeof(float) * x.size(), cudaMemcpyHostToDevice, s));
+    CONE_CUDA(cudaStreamSynchronize(s));  // the staging vector dies at return
+    w->xq_w.clear(); w->xq_b.clear(); w->xo_w.clear(); w->xo_b.clear();
+    for (int l = 0; l < w->dims.dec_layers; ++l) {
+        float* base = w->xattn + xattn_floats_per_layer(d) * l;
+        w->xq_w.push_back(base);
+        w->xq_b.push_back(base + 9 * d * d);
+        w->xo_w.push_back(base + 9 * d * d + 9 * d);
+        w->xo_b.push_back(base + 9 * d * d + 9 * d + 8 * d * d);
+    }
+    return CONE_OK;
+}
+
 extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, const cone_dims* dims, void* stream,
                                    cone_weights** out) {
     CONE_TRY(check_dims(dims));
@@ -282,6 +362,7 @@ extern "C" int cone_weights_create(const float* blob_host, size_t n_floats, cons
     w->dec_vb = w->dec_kb + (size_t)DL * d;
     w->pos_table = w->derived + der.size();
     r = build_pos_table(w->pos_table, dims->max_v_l, (int)d, s);
+    if (r == CONE_OK) r = upload_xattn(w, staged, s);
     if (r != CONE_OK) {
         cone_weights_destroy(w);
         return r;
@@ -306,6 +387,7 @@ extern "C" int cone_weights_update(cone_weights* w, const float* blob_host, size
     CONE_CUDA(cudaMemcpyAsync(w->blob, staged.data(), sizeof(float) * w->n_floats, cudaMemcpyHostToDevice, s));
     CONE_CUDA(cudaMemcpyAsync(w->derived, der.data(), sizeof(float) * der.size(), cudaMemcpyHostToDevice, s));
     CONE_CUDA(cudaStreamSynchronize(s));  // staging vectors die at return
+    CONE_TRY(upload_xattn(w, staged, s));
     CONE_TRY(tc_weights_refresh(w->tc, s));
     if (w->pos_proj) CONE_TRY(fill_pos_proj(w, s));
     return CONE_OK;
@@ -401,7 +483,7 @@ struct CoreBuffers {
     float *src, *srcpos, *qk, *v, *att, *tmp, *h;                      // [R, .] fp32 (srcpos..h: fp32 mode only)
     uint16_t *src16, *qkv16, *att16, *h16;                             // [R, .] fp16 (tensor-core mode only)
     float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
-    uint16_t *tgt16, *dqkin16, *dqkv16, *datt16, *dq16, *dh16;               // [B*nq, .] fp16 (tensor-core mode only)
+    uint16_t *tgt16, *dqkin16, *dqkv16, *datt16, *dqt16, *dpm16, *dh16;      // [B*nq, .] fp16 (tensor-core mode only)
     int64_t *vid_base, *txt_base;
     int32_t *vlen, *tlen, *pad_len, *qidx;
     // tensor-core mode, optional: q|k|v of encoder layer 0 per FRAME and per TOKEN (the projection of a row does not
@@ -437,7 +519,8 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, i
         b.dqkin16 = a.get<uint16_t>(Q * d);
         b.dqkv16 = a.get<uint16_t>(Q * 3 * d);
         b.datt16 = a.get<uint16_t>(Q * d);
-        b.dq16 = a.get<uint16_t>(Q * d);
+        b.dqt16 = a.get<uint16_t>(Q * 9 * d);  // q | q pushed through Wk_h^T per head
+        b.dpm16 = a.get<uint16_t>(Q * 8 * d);  // attention-pooled memory per head
         b.dh16 = a.get<uint16_t>(Q * c.ffn);
     } else {
         b.t2 = a.get<float>(Q * d);
@@ -551,13 +634,18 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
     // (weights concatenated at load time: columns [0, DL*d) = K of layer 0.., [DL*d, 2*DL*d) = V of layer 0..)
     float* kdec = b.h;
     float* vdec = b.h ? b.h + (size_t)DL * d : nullptr;
-    uint16_t* kdec16 = b.h16;
-    uint16_t* vdec16 = b.h16 ? b.h16 + (size_t)DL * d : nullptr;
     if (!tc) {
         CONE_TRY(add_pos_rows(b.src, c.w->pos_table, b.vlen, b.srcpos, b.B, b.Lv, b.Lt, d, dm.max_v_l, c.s));
         CONE_TRY(linear(c, b.srcpos, d, R, c.w->dec_kw, c.w->dec_kb, DL * d, d, kdec, b.hw, 0));
         CONE_TRY(linear(c, b.src, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, vdec, b.hw, 0));
-    } else {
+    }
+    // tensor-core mode: no K / V projection of the memory at all — the cross-attention works on the raw encoder output
+    // (dec_cross_attention_mem, attention.cu).  CONE_XATTN_KV=1 selects the earlier formulation (K|V projection GEMM of
+    // the memory + per-head mma.sync kernel) for A/B measurements.
+    static const bool xattn_kv = [] { const char* e = getenv("CONE_XATTN_KV"); return e && e[0] == '1'; }();
+    uint16_t* kdec16 = b.h16;
+    uint16_t* vdec16 = b.h16 ? b.h16 + (size_t)DL * d : nullptr;
+    if (tc && xattn_kv) {
         TcGemmArgs g;  // k (without its position term: added in the cross-attention kernel) | v
         g.A16 = b.src16; g.lda = d; g.M = R; g.W = c.w->dec_kw; g.bias = c.w->dec_kb; g.N = 2 * DL * d; g.K = d;
         g.C16 = b.h16; g.ldc16 = b.hw;
@@ -616,15 +704,28 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
             LN(g, p + ".norm1");
             CONE_TRY(tc_gemm_run(t, g, c.s));
             CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Q, nq, d, c.s));
-            g = G(b.dqkin16, d, cw, cb, d, d);  // q of the cross-attention
-            g.C16 = b.dq16; g.ldc16 = d;
-            CONE_TRY(tc_gemm_run(t, g, c.s));
-            CONE_TRY(dec_cross_attention(b.dq16, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt16, d,
-                                         b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.w->pos_kdec16 + (size_t)l * d,
-                                         (int64_t)DL * d, dm.max_v_l, c.s));
-            g = G(b.datt16, d, c.w->p(p + ".multihead_attn.out_proj.weight"), c.w->p(p + ".multihead_attn.out_proj.bias"), d, d);
-            LN(g, p + ".norm2");
-            CONE_TRY(tc_gemm_run(t, g, c.s));
+            // cross-attention on the raw memory: q | Wk_h^T q_h in one GEMM (N = 9 d), pooled memory per head out of the
+            // attention kernel, Wv_h and the output projection folded into the next GEMM (K = 8 d)
+            if (!xattn_kv) {
+                g = G(b.dqkin16, d, c.w->xq_w[l], c.w->xq_b[l], 9 * d, d);
+                g.C16 = b.dqt16; g.ldc16 = 9 * d;
+                CONE_TRY(tc_gemm_run(t, g, c.s));
+                CONE_TRY(dec_cross_attention_mem(b.src16, d, b.dqt16, 9 * d, b.dpm16, 8 * d, b.vlen, b.tlen, b.B, nq, b.Lv,
+                                                 b.Lt, c.w->pos_kdec16 + (size_t)l * d, (int64_t)DL * d, dm.max_v_l, c.s));
+                g = G(b.dpm16, 8 * d, c.w->xo_w[l], c.w->xo_b[l], d, 8 * d);
+                LN(g, p + ".norm2");
+                CONE_TRY(tc_gemm_run(t, g, c.s));
+            } else {
+                g = G(b.dqkin16, d, cw, cb, d, d);  // q of the cross-attention
+                g.C16 = b.dqt16; g.ldc16 = d;
+                CONE_TRY(tc_gemm_run(t, g, c.s));
+                CONE_TRY(dec_cross_attention(b.dqt16, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt16, d,
+                                             b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.w->pos_kdec16 + (size_t)l * d,
+                                             (int64_t)DL * d, dm.max_v_l, c.s));
+                g = G(b.datt16, d, c.w->p(p + ".multihead_attn.out_proj.weight"), c.w->p(p + ".multihead_attn.out_proj.bias"), d, d);
+                LN(g, p + ".norm2");
+                CONE_TRY(tc_gemm_run(t, g, c.s));
+            }
             g = G(b.tgt16, d, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d);
             g.relu = 1; g.C16 = b.dh16; g.ldc16 = ff;
             CONE_TRY(tc_gemm_run(t, g, c.s));

@@ -374,6 +374,11 @@ __device__ __forceinline__ void ldsm_x4(uint32_t* r, const __half* p) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"((uint32_t)__cvta_generic_to_shared(p)));
 }
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, const __half* p) {  // lanes 0-15 supply the row addresses
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r0), "=r"(r1)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -758,6 +763,211 @@ dec_cross_attention_mma_kernel(const __half* __restrict__ q, int64_t ldq, const 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Memory-direct decoder cross-attention (CONE_PREC_TC).  The K and V projections of the memory are never formed:
+//   score(slot, h, key) = q_h . (Wk_h (m_key + pos_key) + bk_h)
+//                       = (Wk_h^T q_h) . m_key + q_h . (Wk_h pos_key) + const(key)      [const cancels in the softmax]
+//   out(slot, h)        = sum_key p_key (Wv_h m_key + bv_h) = Wv_h (sum_key p_key m_key) + bv_h     [sum p = 1]
+// so the kernel works on the RAW encoder output m [S, 256] of the window: the queries arrive already pushed through
+// Wk_h^T (qt [slot, h, 256], produced by the same GEMM that makes q), and what leaves is the attention-pooled memory
+// pm [slot, h, 256]; Wv_h and the output projection are folded into the next GEMM (K = 8 x 256).  This removes the
+// [R, 2 DL 256] K|V projection GEMM of the memory (the largest decoder launch) and its 2 x 1 KB per memory row and
+// layer of HBM traffic; the window's memory is read once (512 B per row) into shared memory and feeds both products.
+// One CTA per window, one warp per 16 rows of the (head, slot) x key score matrix (8 nq rows): S = Qt.M^T with
+// mma.sync m16n8k16 (K = 256: A fragments of qt stay in registers, B fragments by ldmatrix), position term through
+// the per-layer pos.Wk^T table (K = 32 per head, fragments straight from 16-byte global loads, contraction index
+// permuted as in the kernel above), masked softmax on the accumulators, P.M with transposing ldmatrix.
+// The softmax scale and log2(e) are folded into the weights that produce q and qt.
+// ------------------------------------------------------------------------------------------------
+constexpr int XM_PAD = 264;  // halves per shared-memory row (256 + 8): 528-byte stride -> conflict-free ldmatrix
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+
+template <int NB, int MT>
+__global__ void __launch_bounds__(MT * 64, NB <= 20 ? 2 : 1)
+dec_cross_attention_mem_kernel(const __half* __restrict__ mem, int64_t ldm, const __half* __restrict__ qqt, int64_t ldq,
+                               __half* __restrict__ pm, int64_t ldp, const int32_t* __restrict__ vlen,
+                               const int32_t* __restrict__ tlen, int nq, int Lv, int Lt,
+                               const __half* __restrict__ posk, int64_t ldposk, int table_lv) {
+    // Two warps per 16-row block of the score matrix (ncu on the one-warp-per-block version: 6 warps per SM, every stall
+    // a fixed-latency dependency): for the scores they split the key blocks (even / odd), exchange row maxima and
+    // sums through shared memory, publish their halves of P there, and for P.M they split the 256 channels.
+    constexpr int D = 256;
+    constexpr int NW = MT * 2;     // warps
+    constexpr int NJ = NB / 2;     // key blocks per warp
+    constexpr int PS_PAD = NB * 8 + 8;  // halves per row of P in shared memory (conflict-free 4-byte stores and ldmatrix)
+    static_assert(PS_PAD <= XM_PAD, "P must fit the shared memory of the qt rows it replaces");
+    extern __shared__ __align__(16) unsigned char xsm[];
+    __half* Ms = reinterpret_cast<__half*>(xsm);   // [NB * 8][XM_PAD] memory rows of the window (rows >= S are zero)
+    __half* Qt = Ms + NB * 8 * XM_PAD;             // [MT * 16][XM_PAD] qt rows, row = head * nq + slot
+    __half* Ps = Qt;                               // [MT * 16][PS_PAD] P, once the qt fragments are in registers
+    float* red = reinterpret_cast<float*>(Qt + MT * 16 * XM_PAD);  // [MT][2 halves][16 rows][max, sum]
+    const int64_t b = blockIdx.x;
+    const int S = Lv + Lt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mt = warp >> 1, half = warp & 1;
+    const int64_t row0 = b * S;
+    const int R = 8 * nq;  // valid score rows
+
+    {   // memory rows: 32 chunks of 16 bytes per row, one row per warp and iteration (pointer increments only)
+        const int c = lane * 8;
+        const __half* src = mem + (row0 + warp) * ldm + c;
+        __half* dst = Ms + warp * XM_PAD + c;
+#pragma unroll 4
+        for (int r = warp; r < NB * 8; r += NW) {
+            if (r < S) cp_async16(dst, src);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            src += (int64_t)NW * ldm;
+            dst += NW * XM_PAD;
+        }
+        for (int r = warp; r < MT * 16; r += NW) {
+            __half* qd = Qt + r * XM_PAD + c;
+            if (r < R) {
+                const int hh = r / nq, slot = r - hh * nq;
+                cp_async16(qd, qqt + (b * nq + slot) * ldq + D + hh * D + c);
+            } else {
+                *reinterpret_cast<uint4*>(qd) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int vl = vlen[b], tl = tlen[b];
+    const int g = lane >> 2, t4 = lane & 3;
+    const int l8 = lane & 7, lq = lane >> 3;
+    const int r_lo = mt * 16 + g, r_hi = r_lo + 8;           // this lane's two score rows
+    const int h_lo = r_lo < R ? r_lo / nq : -1, h_hi = r_hi < R ? r_hi / nq : -1;
+    const int64_t q_lo = r_lo < R ? (b * nq + (r_lo - h_lo * nq)) : 0, q_hi = r_hi < R ? (b * nq + (r_hi - h_hi * nq)) : 0;
+
+    float sc[NJ][4];  // key block jb = 2 j + half
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+    {   // content term: 16 k-steps over the 256 channels
+        uint32_t aq[16][4];
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+            ldsm_x4(aq[ks], Qt + (mt * 16 + l8 + (lq & 1) * 8) * XM_PAD + ks * 16 + (lq >> 1) * 8);
+        __syncthreads();  // every warp holds its qt fragments: the rows may now be overwritten by P
+        // One k-step (16 channels) at a time over this warp's key blocks: back-to-back MMAs never share an accumulator.
+        // All blocks are processed without range tests: rows past S are zero in shared memory (masked below).
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                uint32_t b0, b1;  // keys jb*8..+7, channels ks*16 + (0-7 | 8-15)
+                ldsm_x2(b0, b1, Ms + ((2 * j + half) * 8 + l8) * XM_PAD + ks * 16 + (lq & 1) * 8);
+                mma_16816(sc[j], aq[ks], b0, b1);
+            }
+        }
+    }
+    if (posk != nullptr) {  // position term of the video keys, one head of this row block at a time
+        const int h_first = (mt * 16) / nq;
+        const int h_last = min(7, (mt * 16 + 15) / nq);
+        for (int hh = h_first; hh <= h_last; ++hh) {
+            uint4 xl = make_uint4(0u, 0u, 0u, 0u), xh = xl;
+            if (h_lo == hh) xl = *reinterpret_cast<const uint4*>(qqt + q_lo * ldq + hh * HD + t4 * 8);
+            if (h_hi == hh) xh = *reinterpret_cast<const uint4*>(qqt + q_hi * ldq + hh * HD + t4 * 8);
+            const uint32_t a0[4] = {xl.x, xh.x, xl.y, xh.y}, a1[4] = {xl.z, xh.z, xl.w, xh.w};
+            const __half* pbase = posk + ((int64_t)vl * table_lv + half * 8 + g) * ldposk + hh * HD + t4 * 8;
+            // the table rows of all of this warp's key blocks are requested together (ncu on the first version: one L2
+            // round trip per key block and head, 64 in a row, was 3/4 of the kernel's time)
+            uint4 pf[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                pf[j] = make_uint4(0u, 0u, 0u, 0u);
+                if ((2 * j + half) * 8 + g < Lv) pf[j] = __ldg(reinterpret_cast<const uint4*>(pbase + (int64_t)j * 16 * ldposk));
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) mma_16816(sc[j], a0, pf[j].x, pf[j].y);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) mma_16816(sc[j], a1, pf[j].z, pf[j].w);
+        }
+    }
+    // masked softmax over the keys (exp2 domain), rows g and g + 8; the partner warp holds the other key blocks
+    float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int key = (2 * j + half) * 8 + t4 * 2 + e;
+            const bool ok = key < S && key_valid(key, Lv, vl, tl);
+            sc[j][e] = ok ? sc[j][e] : -CUDART_INF_F;
+            sc[j][2 + e] = ok ? sc[j][2 + e] : -CUDART_INF_F;
+            m_lo = fmaxf(m_lo, sc[j][e]);
+            m_hi = fmaxf(m_hi, sc[j][2 + e]);
+        }
+    }
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float* my_red = red + ((mt * 2 + half) * 16) * 2;
+    const float* other_red = red + ((mt * 2 + (half ^ 1)) * 16) * 2;
+    if (t4 == 0) {
+        my_red[g * 2] = m_lo;
+        my_red[(g + 8) * 2] = m_hi;
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + mt) : "memory");  // the two warps of this row block
+    m_lo = fmaxf(m_lo, other_red[g * 2]);
+    m_hi = fmaxf(m_hi, other_red[(g + 8) * 2]);
+    // a row whose keys are all masked keeps offset 0: exp2(-inf) = 0, sum 0 -> NaN, like torch's softmax of all -inf
+    const float o_lo = m_lo == -CUDART_INF_F ? 0.f : m_lo, o_hi = m_hi == -CUDART_INF_F ? 0.f : m_hi;
+    float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const uint32_t pl = pack_half2(fast_exp2(sc[j][0] - o_lo), fast_exp2(sc[j][1] - o_lo));
+        const uint32_t ph = pack_half2(fast_exp2(sc[j][2] - o_hi), fast_exp2(sc[j][3] - o_hi));
+        // the row sum is taken over the fp16 values that multiply M, so the normalisation is exact for them
+        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&pl));
+        const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&ph));
+        s_lo += fl.x + fl.y;
+        s_hi += fh.x + fh.y;
+        const int key = (2 * j + half) * 8 + t4 * 2;
+        *reinterpret_cast<uint32_t*>(Ps + r_lo * PS_PAD + key) = pl;
+        *reinterpret_cast<uint32_t*>(Ps + r_hi * PS_PAD + key) = ph;
+    }
+    s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+    s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+    s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+    s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+    if (t4 == 0) {
+        my_red[g * 2 + 1] = s_lo;
+        my_red[(g + 8) * 2 + 1] = s_hi;
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + mt) : "memory");  // sums and both halves of P are visible
+    const float i_lo = 1.f / (s_lo + other_red[g * 2 + 1]), i_hi = 1.f / (s_hi + other_red[(g + 8) * 2 + 1]);
+
+    // pooled memory: out[16 rows x 128 channels of this warp] = P . M over all keys
+    float out[16][4];
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) out[nt][0] = out[nt][1] = out[nt][2] = out[nt][3] = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < NJ; ++kb) {
+        uint32_t ap[4];  // P rows (0-7 | 8-15) x keys kb*16 + (0-7 | 8-15)
+        ldsm_x4(ap, Ps + (mt * 16 + l8 + (lq & 1) * 8) * PS_PAD + kb * 16 + (lq >> 1) * 8);
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {
+            uint32_t bv[4];  // keys kb*16 + (0-7 | 8-15) x channels half*128 + np*16 + (0-7 | 8-15)
+            ldsm_x4_trans(bv, Ms + (kb * 16 + l8 + (lq & 1) * 8) * XM_PAD + half * 128 + (np * 2 + (lq >> 1)) * 8);
+            mma_16816(out[np * 2], ap, bv[0], bv[1]);
+            mma_16816(out[np * 2 + 1], ap, bv[2], bv[3]);
+        }
+    }
+    __half* o_lo_p = pm + q_lo * ldp + (h_lo < 0 ? 0 : h_lo) * D + half * 128 + t4 * 2;
+    __half* o_hi_p = pm + q_hi * ldp + (h_hi < 0 ? 0 : h_hi) * D + half * 128 + t4 * 2;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+        if (h_lo >= 0) *reinterpret_cast<uint32_t*>(o_lo_p + nt * 8) = pack_half2(out[nt][0] * i_lo, out[nt][1] * i_lo);
+        if (h_hi >= 0) *reinterpret_cast<uint32_t*>(o_hi_p + nt * 8) = pack_half2(out[nt][2] * i_hi, out[nt][3] * i_hi);
+    }
+}
+
 }  // namespace
 
 int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, float* o, int64_t ldo,
@@ -888,6 +1098,47 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
     }
 #undef CONE_ENC_ATT
     CONE_LAUNCH_CHECK("enc_self_attention_f16");
+    return CONE_OK;
+}
+
+// q | qt [B nq, 256 + 8 * 256] fp16 -> attention-pooled memory pm [B nq, 8 * 256] fp16 (see the kernel's comment)
+int dec_cross_attention_mem(const void* mem, int64_t ldm, const void* qqt, int64_t ldq, void* pm, int64_t ldp,
+                            const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv, int Lt, const void* posk,
+                            int64_t ldposk, int table_lv, cudaStream_t s) {
+    if (B == 0) return CONE_OK;
+    const int S = Lv + Lt;
+    CONE_REQUIRE(nq >= 1 && nq <= 8 && S <= MAX_S, "dec_cross_attention_mem: unsupported nq=%d S=%d", nq, S);
+    CONE_REQUIRE((ldm & 7) == 0 && (ldq & 7) == 0 && (ldp & 1) == 0 && (ldposk & 7) == 0,
+                 "dec_cross_attention_mem: rows must be 16-byte aligned");
+    const int MT = nq <= 6 ? 3 : 4;  // warps = 16-row blocks of the 8 nq score rows (rows past 8 nq are zero)
+    const int NB = S <= 112 ? 14 : (S <= 160 ? 20 : (S <= 208 ? 26 : 32));  // key blocks of 8, all processed
+    const size_t smem = (size_t)(NB * 8 + MT * 16) * XM_PAD * sizeof(__half) + (size_t)MT * 2 * 16 * 2 * sizeof(float);
+    // algorithmic work: both products over the raw memory, which is read once
+    ProfScope ps(s, P_DEC_ATTN, 2.0 * 2.0 * (double)B * 8 * nq * S * 256, 2.0 * (double)B * S * 256 + 2.0 * 2.0 * (double)B * nq * 9 * 256);
+#define CONE_XMEM(NBV, MTV)                                                                                             \
+    do {                                                                                                                \
+        static bool attr = false;                                                                                       \
+        if (!attr) {                                                                                                    \
+            CONE_CUDA(cudaFuncSetAttribute(dec_cross_attention_mem_kernel<NBV, MTV>,                                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+            attr = true;                                                                                                \
+        }                                                                                                               \
+        dec_cross_attention_mem_kernel<NBV, MTV><<<(unsigned)B, MTV * 64, smem, s>>>(                                   \
+            static_cast<const __half*>(mem), ldm, static_cast<const __half*>(qqt), ldq, static_cast<__half*>(pm), ldp,  \
+            vlen, tlen, nq, Lv, Lt, static_cast<const __half*>(posk), ldposk, table_lv);                                \
+    } while (0)
+#define CONE_XMEM_MT(NBV)            \
+    do {                             \
+        if (MT == 3) CONE_XMEM(NBV, 3); \
+        else CONE_XMEM(NBV, 4);      \
+    } while (0)
+    if (NB == 14) CONE_XMEM_MT(14);
+    else if (NB == 20) CONE_XMEM_MT(20);
+    else if (NB == 26) CONE_XMEM_MT(26);
+    else CONE_XMEM_MT(32);
+#undef CONE_XMEM_MT
+#undef CONE_XMEM
+    CONE_LAUNCH_CHECK("dec_cross_attention_mem");
     return CONE_OK;
 }
 

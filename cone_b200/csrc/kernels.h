@@ -86,6 +86,13 @@ int dec_cross_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, 
                         int Lt, int nheads, int kv_f16, const void* posk, int64_t ldposk, int table_lv,
                         cudaStream_t s);  // posk: fp32 table (kv_f16 = 0) or fp16 table (kv_f16 = 1), or null
 
+// memory-direct cross-attention of the tensor-core decoder: mem [B S, 256] fp16 raw encoder output, qqt [B nq, 9 * 256] fp16
+// = q (softmax scale folded in) | q pushed through Wk_h^T per head; pm [B nq, 8 * 256] fp16 = per-head attention-pooled
+// memory (Wv and the output projection are applied by the next GEMM); posk = fp16 pos.Wk^T table
+int dec_cross_attention_mem(const void* mem, int64_t ldm, const void* qqt, int64_t ldq, void* pm, int64_t ldp,
+                            const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv, int Lt, const void* posk,
+                            int64_t ldposk, int table_lv, cudaStream_t s);
+
 // ---------------------------------------------------------------- prefilter.cu
 int window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count, int n_queries,
                     int max_v_l, int32_t* ranklist, float* winscore, int ranklist_stride, cudaStream_t s);

@@ -1,10 +1,16 @@
 #!/usr/bin/env python
 """Per-kernel table from a metrics-only ncu launch list (`ncu --metrics ... --csv --log-file X.csv bench.py ...`):
-   python profiles/summarize_step.py X.csv [out.md] [traffic.json]
+   python profiles/summarize_step.py X.csv [out.md] [traffic.json] [--step N]
+--step N keeps only the N-th step of the capture (steps end with fuse_nms_kernel; 0 = the warm-up step, 1 = the timed one).
 Groups launches by kernel (and template arguments), prints launches, total/avg device time, DRAM bytes per launch,
 achieved DRAM GB/s and the pipe counters; writes the DRAM bytes per launch of the tcgen05 GEMM to traffic.json."""
 import collections, csv, json, re, sys
 
+STEP = None
+if "--step" in sys.argv:
+    i = sys.argv.index("--step")
+    STEP = int(sys.argv[i + 1])
+    del sys.argv[i:i + 2]
 rows = list(csv.reader(open(sys.argv[1])))
 h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 H = rows[h]
@@ -25,6 +31,13 @@ def short(n):
     return n[:46]
 
 
+if STEP is not None:  # launches after the (STEP-1)-th fuse_nms up to and including the STEP-th one
+    ids = list(launch)
+    ends = [i for i, k in enumerate(ids) if "fuse_nms_kernel" in launch[k]["name"]]
+    first_step = [i for i, k in enumerate(ids) if "l2norm_rows_kernel" in launch[k]["name"]]
+    lo = (ends[STEP - 1] + 1) if STEP > 0 else min(i for i in first_step if i > 4)  # skip the weight-handle set-up launches
+    keep = ids[lo:ends[STEP] + 1]
+    launch = collections.OrderedDict((k, launch[k]) for k in keep)
 groups = collections.OrderedDict()
 for d in launch.values():
     groups.setdefault(short(d["name"]), []).append(d)

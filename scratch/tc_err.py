@@ -1,0 +1,25 @@
+"""Error distribution of the tensor-core mode against the oracle on the end-to-end test case (diagnostic)."""
+import sys, os, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cone_b200.config import EGO4D
+from cone_b200.engine import ConeEngine
+from cone_b200.inference import ground_dataset
+from cone_b200.synth import make_dataset
+from cone_b200.weights import init_state_dict
+from oracle import cone_oracle as O
+for wseed, dseed in ((21, 33), (5, 7), (9, 11)):
+    cfg = EGO4D.replace(eval_bsz=8)
+    sd = init_state_dict(cfg, wseed)
+    e = ConeEngine(cfg, sd, device="cuda:0", precision="tc", workspace_bytes=3 << 30)
+    ds = make_dataset(cfg, 4, [900, 455, 91, 1300], 4, seed=dseed)
+    res = ground_dataset(e, ds.videos, ds.queries)
+    ora = O.eval_pipeline(sd, cfg, ds.videos, ds.queries)
+    errs = []
+    for q in ds.queries:
+        r, o = res[q.query_id], ora[q.query_id]
+        if r["ranklist"][: cfg.topk_window] != o["ranklist"][: cfg.topk_window]:
+            continue
+        errs.append(np.abs(r["pred_spans"] - np.stack(o["pred_spans"])).ravel())
+        errs.append(np.abs(r["prob_fg"] - np.stack(o["prob_fg"])).ravel())
+    e = np.concatenate(errs)
+    print(f"seeds {wseed},{dseed}: n {e.size} within1e-3 {np.mean(e <= 1e-3):.4%} n_over {int((e > 1e-3).sum())} max {e.max():.2e} rms {np.sqrt(np.mean(e**2)):.2e} p99 {np.percentile(e,99):.2e}")
