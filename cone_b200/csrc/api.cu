@@ -640,17 +640,7 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
         CONE_TRY(linear(c, b.src, d, R, c.w->dec_vw, c.w->dec_vb, DL * d, d, vdec, b.hw, 0));
     }
     // tensor-core mode: no K / V projection of the memory at all — the cross-attention works on the raw encoder output
-    // (dec_cross_attention_mem, attention.cu).  CONE_XATTN_KV=1 selects the earlier formulation (K|V projection GEMM of
-    // the memory + per-head mma.sync kernel) for A/B measurements.
-    static const bool xattn_kv = [] { const char* e = getenv("CONE_XATTN_KV"); return e && e[0] == '1'; }();
-    uint16_t* kdec16 = b.h16;
-    uint16_t* vdec16 = b.h16 ? b.h16 + (size_t)DL * d : nullptr;
-    if (tc && xattn_kv) {
-        TcGemmArgs g;  // k (without its position term: added in the cross-attention kernel) | v
-        g.A16 = b.src16; g.lda = d; g.M = R; g.W = c.w->dec_kw; g.bias = c.w->dec_kb; g.N = 2 * DL * d; g.K = d;
-        g.C16 = b.h16; g.ldc16 = b.hw;
-        CONE_TRY(tc_gemm_run(c.w->tc, g, c.s));
-    }
+    // (dec_cross_attention_mem, attention.cu)
     CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * Q * d, c.s));
     if (tc) CONE_CUDA(cudaMemsetAsync(b.tgt16, 0, sizeof(uint16_t) * Q * d, c.s));
     const float* qpos = c.w->p("query_embed.weight");
@@ -706,26 +696,14 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
             CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Q, nq, d, c.s));
             // cross-attention on the raw memory: q | Wk_h^T q_h in one GEMM (N = 9 d), pooled memory per head out of the
             // attention kernel, Wv_h and the output projection folded into the next GEMM (K = 8 d)
-            if (!xattn_kv) {
-                g = G(b.dqkin16, d, c.w->xq_w[l], c.w->xq_b[l], 9 * d, d);
-                g.C16 = b.dqt16; g.ldc16 = 9 * d;
-                CONE_TRY(tc_gemm_run(t, g, c.s));
-                CONE_TRY(dec_cross_attention_mem(b.src16, d, b.dqt16, 9 * d, b.dpm16, 8 * d, b.vlen, b.tlen, b.B, nq, b.Lv,
-                                                 b.Lt, c.w->pos_kdec16 + (size_t)l * d, (int64_t)DL * d, dm.max_v_l, c.s));
-                g = G(b.dpm16, 8 * d, c.w->xo_w[l], c.w->xo_b[l], d, 8 * d);
-                LN(g, p + ".norm2");
-                CONE_TRY(tc_gemm_run(t, g, c.s));
-            } else {
-                g = G(b.dqkin16, d, cw, cb, d, d);  // q of the cross-attention
-                g.C16 = b.dqt16; g.ldc16 = d;
-                CONE_TRY(tc_gemm_run(t, g, c.s));
-                CONE_TRY(dec_cross_attention(b.dqt16, d, kdec16 + (size_t)l * d, b.hw, vdec16 + (size_t)l * d, b.hw, b.datt16, d,
-                                             b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt, H, 1, c.w->pos_kdec16 + (size_t)l * d,
-                                             (int64_t)DL * d, dm.max_v_l, c.s));
-                g = G(b.datt16, d, c.w->p(p + ".multihead_attn.out_proj.weight"), c.w->p(p + ".multihead_attn.out_proj.bias"), d, d);
-                LN(g, p + ".norm2");
-                CONE_TRY(tc_gemm_run(t, g, c.s));
-            }
+            g = G(b.dqkin16, d, c.w->xq_w[l], c.w->xq_b[l], 9 * d, d);
+            g.C16 = b.dqt16; g.ldc16 = 9 * d;
+            CONE_TRY(tc_gemm_run(t, g, c.s));
+            CONE_TRY(dec_cross_attention_mem(b.src16, d, b.dqt16, 9 * d, b.dpm16, 8 * d, b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt,
+                                             c.w->pos_kdec16 + (size_t)l * d, (int64_t)DL * d, dm.max_v_l, c.s));
+            g = G(b.dpm16, 8 * d, c.w->xo_w[l], c.w->xo_b[l], d, 8 * d);
+            LN(g, p + ".norm2");
+            CONE_TRY(tc_gemm_run(t, g, c.s));
             g = G(b.tgt16, d, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d);
             g.relu = 1; g.C16 = b.dh16; g.ldc16 = ff;
             CONE_TRY(tc_gemm_run(t, g, c.s));

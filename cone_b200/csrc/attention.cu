@@ -619,152 +619,6 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
 
 
 // ------------------------------------------------------------------------------------------------
-// Decoder cross-attention on the legacy tensor path (CONE_PREC_TC): nq <= 8 moment slots against S memory keys, fp16
-// K / V straight from global memory into mma.sync fragments — no shared memory, no block-level synchronisation.
-// One warp per (window, head).  The m16n8k16 fragments are filled so that every global load is a 16-byte (K, position
-// table) or 8-byte (V) vector of consecutive elements of one row:
-//   scores  S[slot, key] = sum_d Q[slot, d] K[key, d]: the contraction index may be permuted freely, so lane
-//           (g = lane/4, t4 = lane%4) puts dims [8 t4, 8 t4 + 8) of key (8 jb + g) — one 16-byte load — into the B
-//           fragments of the two k-steps, and the same dims of Q[slot g] into the A fragments (rows 8-15 are zero);
-//           the position term of K comes from an fp16 table through two more MMAs into the same accumulator
-//   softmax on the accumulator fragments (2 keys per lane per key block), exp2 domain (the scale is folded into Q)
-//   P.V     the output-dim index of the n-blocks is permuted instead: lane g owns dims [4 g, 4 g + 4) — one 8-byte
-//           load per key — and ends up holding 8 consecutive output channels of its slot
-// The SIMT version of this kernel spent 54 k warp-instructions per window (ncu), this one ~6 k.
-template <int NB>
-__global__ void __launch_bounds__(256, 3)
-dec_cross_attention_mma_kernel(const __half* __restrict__ q, int64_t ldq, const __half* __restrict__ k, int64_t ldk,
-                               const __half* __restrict__ v, int64_t ldv, __half* __restrict__ o, int64_t ldo,
-                               const int32_t* __restrict__ vlen, const int32_t* __restrict__ tlen, int64_t B, int nq, int Lv,
-                               int Lt, const __half* __restrict__ posk, int64_t ldposk, int table_lv) {
-    constexpr int KB = 5;  // key blocks (of 8 keys) whose loads are in flight together
-    constexpr int VB = 5;  // k-steps (of 16 keys) whose V loads are in flight together
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= B * 8) return;
-    const int64_t b = wid >> 3;
-    const int h = (int)(wid & 7);
-    const int g = lane >> 2, t4 = lane & 3;
-    const int S = Lv + Lt;
-    const int nkb = (S + 7) >> 3;
-    const int vl = vlen[b], tl = tlen[b];
-    const int64_t row0 = b * S;
-    const int colq = h * HD + t4 * 8;  // this lane's 8 contraction dims
-    // A fragments of Q (slot g), pre-scaled by softmax scale * log2(e)
-    uint32_t a0[4] = {0u, 0u, 0u, 0u}, a1[4] = {0u, 0u, 0u, 0u};
-    if (g < nq) {
-        const float sl2 = 0.17677669529663687f * 1.4426950408889634f;
-        const uint4 qraw = *reinterpret_cast<const uint4*>(q + (b * nq + g) * ldq + colq);
-        const __half2* qh = reinterpret_cast<const __half2*>(&qraw);
-        const float2 x0 = __half22float2(qh[0]), x1 = __half22float2(qh[1]), y0 = __half22float2(qh[2]), y1 = __half22float2(qh[3]);
-        a0[0] = pack_half2(x0.x * sl2, x0.y * sl2);
-        a0[2] = pack_half2(x1.x * sl2, x1.y * sl2);
-        a1[0] = pack_half2(y0.x * sl2, y0.y * sl2);
-        a1[2] = pack_half2(y1.x * sl2, y1.y * sl2);
-    }
-    float sc[NB][2];
-    float mx = -CUDART_INF_F;
-#pragma unroll
-    for (int base = 0; base < NB; base += KB) {
-        uint4 kf[KB], pf[KB];
-#pragma unroll
-        for (int r = 0; r < KB; ++r) {
-            const int jb = base + r;
-            kf[r] = make_uint4(0u, 0u, 0u, 0u);
-            pf[r] = kf[r];
-            if (jb < NB && jb < nkb) {
-                const int key = jb * 8 + g;
-                const int krow = key < S ? key : S - 1;  // keys past the window are masked below
-                kf[r] = *reinterpret_cast<const uint4*>(k + (row0 + krow) * ldk + colq);
-                if (posk != nullptr && key < Lv)
-                    pf[r] = __ldg(reinterpret_cast<const uint4*>(posk + ((int64_t)vl * table_lv + key) * ldposk + colq));
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < KB; ++r) {
-            const int jb = base + r;
-            if (jb < NB) {
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
-                if (jb < nkb) {
-                    mma_16816(c, a0, kf[r].x, kf[r].y);
-                    mma_16816(c, a1, kf[r].z, kf[r].w);
-                    mma_16816(c, a0, pf[r].x, pf[r].y);
-                    mma_16816(c, a1, pf[r].z, pf[r].w);
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int key = jb * 8 + t4 * 2 + e;
-                    const bool ok = jb < nkb && key < S && key_valid(key, Lv, vl, tl);
-                    sc[jb][e] = ok ? c[e] : -CUDART_INF_F;
-                    mx = fmaxf(mx, sc[jb][e]);
-                }
-            }
-        }
-    }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float sum = 0.f;
-#pragma unroll
-    for (int jb = 0; jb < NB; ++jb) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float pe = fast_exp2(sc[jb][e] - mx);  // exp2(-inf) = 0 for masked keys; all masked -> NaN like torch
-            sc[jb][e] = pe;
-            sum += pe;
-        }
-    }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-
-    float out[4][4];
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb) out[nb][0] = out[nb][1] = out[nb][2] = out[nb][3] = 0.f;
-    const int colv = h * HD + g * 4;  // this lane's 4 output dims (n index (nb, g) <-> dim 4 g + nb)
-#pragma unroll
-    for (int base = 0; base < NB / 2; base += VB) {
-        uint2 vf[VB][4];
-#pragma unroll
-        for (int r = 0; r < VB; ++r) {
-            const int kb = base + r;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                vf[r][i] = make_uint2(0u, 0u);
-                if (kb < NB / 2 && kb * 2 < nkb) {
-                    const int key = kb * 16 + (i >> 1) * 8 + t4 * 2 + (i & 1);
-                    if (key < S) vf[r][i] = *reinterpret_cast<const uint2*>(v + (row0 + key) * ldv + colv);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < VB; ++r) {
-            const int kb = base + r;
-            if (kb < NB / 2 && kb * 2 < nkb) {
-                uint32_t ap[4];
-                ap[0] = pack_half2(sc[2 * kb][0], sc[2 * kb][1]);
-                ap[1] = 0u;
-                ap[2] = pack_half2(sc[2 * kb + 1][0], sc[2 * kb + 1][1]);
-                ap[3] = 0u;
-                mma_16816(out[0], ap, __byte_perm(vf[r][0].x, vf[r][1].x, 0x5410), __byte_perm(vf[r][2].x, vf[r][3].x, 0x5410));
-                mma_16816(out[1], ap, __byte_perm(vf[r][0].x, vf[r][1].x, 0x7632), __byte_perm(vf[r][2].x, vf[r][3].x, 0x7632));
-                mma_16816(out[2], ap, __byte_perm(vf[r][0].y, vf[r][1].y, 0x5410), __byte_perm(vf[r][2].y, vf[r][3].y, 0x5410));
-                mma_16816(out[3], ap, __byte_perm(vf[r][0].y, vf[r][1].y, 0x7632), __byte_perm(vf[r][2].y, vf[r][3].y, 0x7632));
-            }
-        }
-    }
-    if (g < nq) {
-        const float is = 1.f / sum;
-        // out[nb][e] = O[slot g][n = 2 t4 + e of n-block nb] <-> dim 4 (2 t4 + e) + nb: 8 consecutive channels
-        uint4 ov;
-        ov.x = pack_half2(out[0][0] * is, out[1][0] * is);
-        ov.y = pack_half2(out[2][0] * is, out[3][0] * is);
-        ov.z = pack_half2(out[0][1] * is, out[1][1] * is);
-        ov.w = pack_half2(out[2][1] * is, out[3][1] * is);
-        *reinterpret_cast<uint4*>(o + (b * nq + g) * ldo + h * HD + t4 * 8) = ov;
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
 // Memory-direct decoder cross-attention (CONE_PREC_TC).  The K and V projections of the memory are never formed:
 //   score(slot, h, key) = q_h . (Wk_h (m_key + pos_key) + bk_h)
 //                       = (Wk_h^T q_h) . m_key + q_h . (Wk_h pos_key) + const(key)      [const cancels in the softmax]
@@ -777,7 +631,8 @@ dec_cross_attention_mma_kernel(const __half* __restrict__ q, int64_t ldq, const 
 // One CTA per window, one warp per 16 rows of the (head, slot) x key score matrix (8 nq rows): S = Qt.M^T with
 // mma.sync m16n8k16 (K = 256: A fragments of qt stay in registers, B fragments by ldmatrix), position term through
 // the per-layer pos.Wk^T table (K = 32 per head, fragments straight from 16-byte global loads, contraction index
-// permuted as in the kernel above), masked softmax on the accumulators, P.M with transposing ldmatrix.
+// permuted: lane (g, t4) puts channels [8 t4, 8 t4 + 8) of key 8 jb + g — one 16-byte load — into the B fragments
+// of the head's two k-steps and the same channels of q into the A fragments), masked softmax on the accumulators, P.M with transposing ldmatrix.
 // The softmax scale and log2(e) are folded into the weights that produce q and qt.
 // ------------------------------------------------------------------------------------------------
 constexpr int XM_PAD = 264;  // halves per shared-memory row (256 + 8): 528-byte stride -> conflict-free ldmatrix
@@ -1039,25 +894,9 @@ int dec_cross_attention(const void* q_any, int64_t ldq, const void* k, int64_t l
                                                                     static_cast<const KV*>(v), ldv, o, ldo, vlen, tlen, \
                                                                     nq, Lv, Lt, posk, ldposk, table_lv);                \
     } while (0)
-    if (kv_f16) {
-        // posk is the fp16 table in this mode
-        const __half* k16 = static_cast<const __half*>(k);
-        const __half* v16 = static_cast<const __half*>(v);
-        const __half* p16 = static_cast<const __half*>(posk_any);
-        const __half* q16 = static_cast<const __half*>(q_any);
-        __half* o16 = static_cast<__half*>(o_any);
-        CONE_REQUIRE((ldq & 7) == 0 && (ldo & 7) == 0, "dec_cross_attention: fp16 q / o rows must be 16-byte aligned");
-        const unsigned g8 = (unsigned)B;  // 8 warps = the 8 heads of one window
-        if (S <= 160) {
-            dec_cross_attention_mma_kernel<20><<<g8, 256, 0, s>>>(q16, ldq, k16, ldk, v16, ldv, o16, ldo, vlen, tlen, B, nq, Lv, Lt,
-                                                                 p16, ldposk, table_lv);
-        } else {
-            dec_cross_attention_mma_kernel<32><<<g8, 256, 0, s>>>(q16, ldq, k16, ldk, v16, ldv, o16, ldo, vlen, tlen, B, nq, Lv, Lt,
-                                                                 p16, ldposk, table_lv);
-        }
-    } else {
-        if (NQ == 5) CONE_XATT(float, 5); else CONE_XATT(float, 8);
-    }
+    CONE_REQUIRE(!kv_f16, "dec_cross_attention: the tensor-core decoder uses dec_cross_attention_mem");
+    if (NQ == 5) CONE_XATT(float, 5); else CONE_XATT(float, 8);
+
 #undef CONE_XATT
     CONE_LAUNCH_CHECK("dec_cross_attention");
     return CONE_OK;

@@ -78,9 +78,8 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
 // qk / v / o are fp32 (f16 = 0) or fp16 (f16 = 1)
 int dec_self_attention(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo, int64_t B,
                        int nq, int nheads, int f16, cudaStream_t s);
-// decoder cross-attention: nq queries x S memory keys with key-padding mask
-// k / v are fp32 (kv_f16 = 0) or fp16 (kv_f16 = 1) with leading dims in elements
-// with kv_f16 = 1 the queries q and the output o are fp16 as well (the tensor-core decoder chain)
+// decoder cross-attention of the fp32 mode: nq queries x S memory keys with key-padding mask, fp32 q / k / v / o
+// (kv_f16 must be 0: the tensor-core decoder uses dec_cross_attention_mem below)
 int dec_cross_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         void* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv,
                         int Lt, int nheads, int kv_f16, const void* posk, int64_t ldposk, int table_lv,

@@ -57,22 +57,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
-// Busy-polling wait (mbarrier.test_wait never suspends the warp): for the accumulator hand-offs between the MMA issuer
-// and the epilogue warps, where the wake-up latency of a suspended try_wait sits on the critical path of every tile.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -159,18 +143,6 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float* v) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// wait::ld that also "touches" the 32 destination registers of an earlier tcgen05.ld, so that the compiler cannot move
-// any use of them above the wait while another load is already in flight (software-pipelined epilogue)
-__device__ __forceinline__ void tmem_ld_wait_use32(float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
     asm volatile(
@@ -196,7 +168,6 @@ struct TcEpilogue {
     const float* ln_g;   // fused LayerNorm over the N = BN columns of the row (null = off)
     const float* ln_b;
     float ln_eps;
-    int spin;            // accumulator hand-off barriers are polled instead of waited on (CONE_TC_SPIN=1)
 };
 
 // Byte offset of 16-byte unit `u` of row `r` in a [rows x 128 B] box with the TMA 128-byte swizzle.
@@ -238,10 +209,7 @@ constexpr int FAST_STAGES = 4;  // A + W ring depth of the streamlined epilogues
 // row in registers was measured 20-50 % SLOWER than the generic TMA-box one and was dropped: profiles/r01_notes.md.)
 // ncu on the generic epilogue at 2 warps per scheduler: ~9 issue cycles per instruction, a third of the stalls in
 // LDCU -> UISETP -> BRA chains of the run-time flags, another tenth on bias loads issued after the TMEM wait.
-//   EPI_PLAIN16_DB: EPI_PLAIN16 with 32-column steps through TWO [32 x 32] half-boxes (64-byte swizzle) per warp: the
-//                warp fills one half while the TMA store of the other is still reading shared memory, instead of
-//                waiting for its single box to drain before every refill (selected with CONE_TC_EPI_DB=1)
-enum { EPI_PLAIN16 = 0, EPI_LN16 = 1, EPI_GENERIC = 2, EPI_PLAIN16_DB = 3 };
+enum { EPI_PLAIN16 = 0, EPI_LN16 = 1, EPI_GENERIC = 2 };
 
 // 64 fp32 values of one row -> fp16 -> this lane's row of a [32 x 64] 128-byte-swizzled box -> one TMA store
 __device__ __forceinline__ void store_box16(const float* x, uint8_t* box, const CUtensorMap* map, int col, int row0,
@@ -272,7 +240,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmC32, TcEpilogue ep, int64_t M, int N, int K) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int HALF = BN / 2;  // columns per epilogue warp
-    constexpr bool FAST = MODE == EPI_PLAIN16 || MODE == EPI_PLAIN16_DB;
+    constexpr bool FAST = MODE == EPI_PLAIN16;
     constexpr int NSTAGE = WRES ? WRES_STAGES : (FAST ? FAST_STAGES : STAGES);
     constexpr int B_RING = WRES ? WRES_KBLOCKS * B_BYTES : NSTAGE * B_BYTES;  // resident tile or ring
     constexpr int N_BOX = (WRES || FAST) ? EPI_WARPS : 2 * EPI_WARPS;         // one box per warp unless generic + ring
@@ -366,8 +334,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t acc_phase = 0;
             if (WRES) mbar_wait(wfull, 0);
             for (int64_t t = t_begin; t < t_end; t += t_step) {
-                if (ep.spin) mbar_wait_spin(&tempty[acc], acc_phase ^ 1);
-                else mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+                mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_k; ++kb) {
@@ -405,8 +372,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int64_t m0 = (WRES ? t : t / n_tiles) * BM;
             const int n0 = (WRES ? n_fixed : (int)(t % n_tiles)) * BN + half * HALF;  // first of this warp's 128 columns
             const int row0 = (int)m0 + quarter * 32;                                  // first of this warp's 32 rows
-            if (ep.spin) mbar_wait_spin(&tfull[acc], acc_phase);
-            else mbar_wait(&tfull[acc], acc_phase);
+            mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
             auto release_acc = [&]() {  // this warp's slice of the accumulator is in registers
@@ -425,60 +391,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
                 }
             };
-            if (MODE == EPI_PLAIN16_DB) {
-                // software pipeline: the TMEM load of step ch+1 is in flight while step ch is converted and stored (ncu on
-                // EPI_PLAIN16: all 8 epilogue warps alternate in lockstep between a TMEM-read phase and an ALU / store
-                // phase, the tile costs ~4200 cycles against 2048 of MMA; see profiles/r01_notes.md)
-                float xbuf[2][32];
-                tmem_ld_32x32(taddr, xbuf[0]);
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    float* x = xbuf[ch & 1];
-                    tmem_ld_wait_use32(x);
-                    if (ch < 3) tmem_ld_32x32(taddr + (ch + 1) * 32, xbuf[(ch + 1) & 1]);
-                    else release_acc();
+            for (int ch = 0; ch < 2; ++ch) {
+                float x[64];
+                tmem_ld_32x64(taddr + ch * 64, x);
+                tmem_ld_wait();
+                if (ch == 1) release_acc();
+                add_bias(x, ch * 64);
+                if (ep.relu) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + ch * 32) + q);
-                        x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
-                    }
-                    if (ep.relu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-                    }
-                    uint8_t* hb = box + (ch & 1) * (BOX_BYTES / 2);
-                    if (lane == 0) tma_store_wait_read<1>();  // the store issued from this half two steps ago has drained
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {  // [32 rows x 64 B], 64-byte swizzle: unit ^= (row >> 1) & 3
-                        uint4 v;
-                        v.x = pack_h2(x[8 * u], x[8 * u + 1]);
-                        v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
-                        v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
-                        v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
-                        *reinterpret_cast<uint4*>(hb + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = v;
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC16, hb, n0 + ch * 32, row0);
-                        tma_store_commit();
-                    }
+                    for (int j = 0; j < 64; ++j) x[j] = fmaxf(x[j], 0.f);
                 }
-            } else {
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    float x[64];
-                    tmem_ld_32x64(taddr + ch * 64, x);
-                    tmem_ld_wait();
-                    if (ch == 1) release_acc();
-                    add_bias(x, ch * 64);
-                    if (ep.relu) {
-#pragma unroll
-                        for (int j = 0; j < 64; ++j) x[j] = fmaxf(x[j], 0.f);
-                    }
-                    store_box16(x, box, &tmC16, n0 + ch * 64, row0, lane);
-                }
+                store_box16(x, box, &tmC16, n0 + ch * 64, row0, lane);
             }
         }
         if (lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last bulk stores
@@ -507,8 +431,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int64_t m0 = (WRES ? t : t / n_tiles) * BM;
             const int n0 = (WRES ? n_fixed : (int)(t % n_tiles)) * BN + half * HALF;  // first column of this warp's half
             const int row0 = (int)m0 + quarter * 32;               // first row of this warp's 32 rows
-            if (ep.spin) mbar_wait_spin(&tfull[acc], acc_phase);
-            else mbar_wait(&tfull[acc], acc_phase);
+            mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
 
@@ -710,7 +633,7 @@ EncodeTiledFn encode_fn() {
 // 2-D tensor [rows, cols] with row pitch ld (elements); box = [box_cols, box_rows] with a 128-byte inner extent,
 // 128-byte swizzle
 int make_map(CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-             int box_rows, bool swizzle64 = false) {
+             int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -723,7 +646,7 @@ int make_map(CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
@@ -737,7 +660,7 @@ constexpr size_t tc_smem_bytes() {
     constexpr size_t tail = 64 * sizeof(uint64_t) + 8 * 32 * 8 + 64;  // barriers, LayerNorm partials, TMEM slot
     constexpr size_t b_bytes = (size_t)BN * BK * 2;
     if (WRES) return (size_t)WRES_STAGES * A_BYTES + WRES_KBLOCKS * b_bytes + 8 * BOX_BYTES + tail;
-    if (MODE == EPI_PLAIN16 || MODE == EPI_PLAIN16_DB) return (size_t)FAST_STAGES * (A_BYTES + b_bytes) + 8 * BOX_BYTES + tail;
+    if (MODE == EPI_PLAIN16) return (size_t)FAST_STAGES * (A_BYTES + b_bytes) + 8 * BOX_BYTES + tail;
     return 1024 + (size_t)STAGES * (A_BYTES + b_bytes) + 16 * BOX_BYTES + tail;
 }
 static_assert(tc_smem_bytes<256, true, EPI_GENERIC>() <= 232448, "weights-resident layout exceeds 227 KB");
@@ -848,12 +771,7 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     mapC16 = mapA;
     mapC32 = mapA;  // placeholders when unused (never dereferenced)
     if (g.R16) CONE_TRY(make_map(&mapR, g.R16, false, g.M, g.N, g.ldr16, 64, 32));
-    const bool plain16 = w->BN == 256 && g.C16 && !g.C32 && !g.R16 && !g.R32 && !g.ln_g && g.bias;
-    static const bool epi_db = [] { const char* e = getenv("CONE_TC_EPI_DB"); return e && e[0] == '1'; }();
-    if (g.C16) {
-        if (plain16 && epi_db) CONE_TRY(make_map(&mapC16, g.C16, false, g.M, g.N, g.ldc16, 32, 32, true));
-        else CONE_TRY(make_map(&mapC16, g.C16, false, g.M, g.N, g.ldc16, 64, 32));
-    }
+    if (g.C16) CONE_TRY(make_map(&mapC16, g.C16, false, g.M, g.N, g.ldc16, 64, 32));
     if (g.C32) CONE_TRY(make_map(&mapC32, g.C32, true, g.M, g.N, g.ldc32, 32, 32));
     TcEpilogue ep{};
     ep.bias = g.bias;
@@ -866,8 +784,6 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     ep.ln_g = g.ln_g;
     ep.ln_b = g.ln_b;
     ep.ln_eps = 1e-5f;
-    static const bool epi_spin = [] { const char* e = getenv("CONE_TC_SPIN"); return e && e[0] == '1'; }();
-    ep.spin = epi_spin ? 1 : 0;
     const int64_t m_tiles = cdiv64(g.M, BM);
     const int n_tiles = g.N / w->BN;
     const int64_t tiles = m_tiles * n_tiles;
@@ -893,17 +809,16 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
         tc_gemm_kernel<BNV, WR, MD><<<grid, TC_THREADS, tc_smem_bytes<BNV, WR, MD>(), s>>>(                             \
             mapA, w->map, mapR, mapC16, mapC32, ep, g.M, g.N, g.K);                                                     \
     } while (0)
+    const bool plain16 = w->BN == 256 && g.C16 && !g.C32 && !g.R16 && !g.R32 && !g.ln_g && g.bias;
     const bool ln16 = w->BN == 256 && g.C16 && !g.C32 && g.R16 && !g.R32 && g.ln_g && g.bias && !g.relu;
     if (w->BN != 256) {
         CONE_TC_LAUNCH(128, false, EPI_GENERIC);
     } else if (wres) {
-        if (plain16 && epi_db) CONE_TC_LAUNCH(256, true, EPI_PLAIN16_DB);
-        else if (plain16) CONE_TC_LAUNCH(256, true, EPI_PLAIN16);
+        if (plain16) CONE_TC_LAUNCH(256, true, EPI_PLAIN16);
         else if (ln16) CONE_TC_LAUNCH(256, true, EPI_LN16);
         else CONE_TC_LAUNCH(256, true, EPI_GENERIC);
     } else {
-        if (plain16 && epi_db) CONE_TC_LAUNCH(256, false, EPI_PLAIN16_DB);
-        else if (plain16) CONE_TC_LAUNCH(256, false, EPI_PLAIN16);
+        if (plain16) CONE_TC_LAUNCH(256, false, EPI_PLAIN16);
         else if (ln16) CONE_TC_LAUNCH(256, false, EPI_LN16);
         else CONE_TC_LAUNCH(256, false, EPI_GENERIC);
     }

@@ -1,0 +1,10 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench_tc.json 2> gpurun_out/bench_tc.err
+timeout 600 python bench.py --precision fp32 --no-cpu-baseline > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,launch__grid_size,lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed
+timeout 900 ncu --metrics $M --clock-control none -c 260 --csv --log-file gpurun_out/step_metrics.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tc_gemm_kernel|enc_attention_f16|dec_cross_attention_mem' -s 30 -c 10 -o gpurun_out/prof_top python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+python profiles/localizer_latency.py --precision tc > gpurun_out/localizer_tc.json 2> gpurun_out/localizer_tc.err
+python profiles/localizer_latency.py > gpurun_out/localizer_fp32.json 2> gpurun_out/localizer_fp32.err
+ls -la gpurun_out | head -40
