@@ -724,24 +724,38 @@ dec_cross_attention_mem_kernel(const __half* __restrict__ mem, int64_t ldm, cons
     if (posk != nullptr) {  // position term of the video keys, one head of this row block at a time
         const int h_first = (mt * 16) / nq;
         const int h_last = min(7, (mt * 16 + 15) / nq);
-        for (int hh = h_first; hh <= h_last; ++hh) {
-            uint4 xl = make_uint4(0u, 0u, 0u, 0u), xh = xl;
-            if (h_lo == hh) xl = *reinterpret_cast<const uint4*>(qqt + q_lo * ldq + hh * HD + t4 * 8);
-            if (h_hi == hh) xh = *reinterpret_cast<const uint4*>(qqt + q_hi * ldq + hh * HD + t4 * 8);
-            const uint32_t a0[4] = {xl.x, xh.x, xl.y, xh.y}, a1[4] = {xl.z, xh.z, xl.w, xh.w};
-            const __half* pbase = posk + ((int64_t)vl * table_lv + half * 8 + g) * ldposk + hh * HD + t4 * 8;
-            // the table rows of all of this warp's key blocks are requested together (ncu on the first version: one L2
-            // round trip per key block and head, 64 in a row, was 3/4 of the kernel's time)
-            uint4 pf[NJ];
+        // Two heads per pass: the table rows of all of this warp's key blocks for both heads are requested together
+        // (ncu: one L2 round trip per (key block, head), 64 in a row, was 3/4 of the first version's time; one per head
+        // was still a quarter of the second's).
+        constexpr int HP = MT <= 3 ? 2 : 1;  // heads per pass (register budget: 170 at 6 warps per CTA, 128 at 8)
+        for (int hh = h_first; hh <= h_last; hh += HP) {
+            uint32_t a[HP][2][4];
+            uint4 pf[HP][NJ];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                pf[j] = make_uint4(0u, 0u, 0u, 0u);
-                if ((2 * j + half) * 8 + g < Lv) pf[j] = __ldg(reinterpret_cast<const uint4*>(pbase + (int64_t)j * 16 * ldposk));
+            for (int u = 0; u < HP; ++u) {
+                const int hu = hh + u;  // hu > h_last: no row of this block belongs to it, its A fragments are zero
+                uint4 xl = make_uint4(0u, 0u, 0u, 0u), xh = xl;
+                if (h_lo == hu) xl = *reinterpret_cast<const uint4*>(qqt + q_lo * ldq + hu * HD + t4 * 8);
+                if (h_hi == hu) xh = *reinterpret_cast<const uint4*>(qqt + q_hi * ldq + hu * HD + t4 * 8);
+                a[u][0][0] = xl.x; a[u][0][1] = xh.x; a[u][0][2] = xl.y; a[u][0][3] = xh.y;
+                a[u][1][0] = xl.z; a[u][1][1] = xh.z; a[u][1][2] = xl.w; a[u][1][3] = xh.w;
+                const __half* pbase = posk + ((int64_t)vl * table_lv + half * 8 + g) * ldposk + hu * HD + t4 * 8;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    pf[u][j] = make_uint4(0u, 0u, 0u, 0u);
+                    if (hu <= h_last && (2 * j + half) * 8 + g < Lv)
+                        pf[u][j] = __ldg(reinterpret_cast<const uint4*>(pbase + (int64_t)j * 16 * ldposk));
+                }
             }
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) mma_16816(sc[j], a0, pf[j].x, pf[j].y);
+            for (int u = 0; u < HP; ++u) {
+                if (hh + u <= h_last) {  // warp-uniform
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) mma_16816(sc[j], a1, pf[j].z, pf[j].w);
+                    for (int j = 0; j < NJ; ++j) mma_16816(sc[j], a[u][0], pf[u][j].x, pf[u][j].y);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) mma_16816(sc[j], a[u][1], pf[u][j].z, pf[u][j].w);
+                }
+            }
         }
     }
     // masked softmax over the keys (exp2 domain), rows g and g + 8; the partner warp holds the other key blocks

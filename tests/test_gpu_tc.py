@@ -63,6 +63,22 @@ def test_tc_forward_dense_vs_oracle(cfg, wseed):
     assert_close(match.cpu(), wmatch, TC_TOL, "match")
 
 
+@pytest.mark.parametrize("max_v_l,nq,wseed", [(180, 8, 31), (220, 3, 32), (60, 1, 33), (125, 6, 34)])
+def test_tc_forward_other_window_sizes_and_slot_counts(max_v_l, nq, wseed):
+    """The memory-direct cross-attention is instantiated per window size (14 / 20 / 26 / 32 key blocks) and per number of
+    16-row score blocks (8 nq rows): cover the instantiations the two dataset presets do not reach."""
+    cfg = EGO4D.replace(max_v_l=max_v_l, num_queries=nq, max_q_l=24)
+    sd = init_state_dict(cfg, wseed)
+    e = ConeEngine(cfg, sd, device=DEV, precision="tc", workspace_bytes=2 << 30)
+    vid, vm, txt, tm, cls = dense_case(cfg, 200 + wseed)
+    with torch.no_grad():
+        want = O.cone_forward(sd, txt, tm, vid, vm)
+    vl, tl = vm.sum(1).int().to(DEV), tm.sum(1).int().to(DEV)
+    logits, spans, _, _, _ = e.forward(txt.to(DEV), tl, vid.to(DEV), vl)
+    assert_close(spans.cpu(), want["pred_spans"], 1.5 * TC_TOL, "pred_spans")
+    assert_close(torch.softmax(logits, -1).cpu(), torch.softmax(want["pred_logits"], -1), 1.5 * TC_TOL, "class probabilities")
+
+
 def test_tc_end_to_end_vs_oracle():
     cfg = EGO4D.replace(eval_bsz=8)
     sd = init_state_dict(cfg, 21)
