@@ -65,6 +65,15 @@ static const char* kProfNames[cone::P_COUNT] = {"gemm_fp32", "gemm_tc", "enc_att
                                                 "convert"};
 extern "C" void cone_profile_enable(int on) {
     cone::g_prof_on = on != 0;
+    // events are created here, not at the first profiled launches: event creation inside a timed region showed up as
+    // host-side gaps between launches
+    if (on) {
+        while (cone::g_event_pool.size() < 4096) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) break;
+            cone::g_event_pool.push_back(e);
+        }
+    }
 }
 extern "C" int cone_profile_categories(void) { return cone::P_COUNT; }
 extern "C" const char* cone_profile_name(int cat) { return (cat >= 0 && cat < cone::P_COUNT) ? kProfNames[cat] : ""; }
