@@ -64,6 +64,84 @@ span_mean_pool_kernel(const float* __restrict__ frames, int64_t n_frames, const 
     }
 }
 
+// One CTA per WINDOW: the rows between the earliest start and the latest end of the window's NQ proposals are read once
+// and every row is added to the accumulators of the proposals whose slice contains it.  Each proposal's rows are
+// still added in increasing order into its own accumulator, so the result is bit-identical to the per-proposal kernel
+// above; what changes is the traffic: the proposals of a window overlap (ncu: 39 rows per proposal on average, 195 per
+// window, against at most Lv = 125 distinct rows).
+template <int NQ>
+__global__ void __launch_bounds__(256)
+span_mean_pool_window_kernel(const float* __restrict__ frames, int64_t n_frames, const int64_t* __restrict__ vid_base,
+                             const int32_t* __restrict__ vlen, const int32_t* __restrict__ pad_len,
+                             const float* __restrict__ spans, float* __restrict__ pooled, int nq, int Dv) {
+    const int64_t b = blockIdx.x;
+    const int len = vlen[b];
+    const float dur = (float)len;
+    const int pl = pad_len[b];
+    const int64_t base = vid_base[b];
+    int st[NQ], en[NQ], cnt[NQ];  // data rows [st, en) and slice length (pad rows included) of every proposal
+    int lo = 0x7fffffff, hi = 0;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+        st[j] = en[j] = cnt[j] = 0;
+        if (j < nq) {
+            const float cx = spans[(b * nq + j) * 2 + 0], w = spans[(b * nq + j) * 2 + 1];
+            const float hw = __fmul_rn(0.5f, w);
+            const float x1 = __fmul_rn(__fsub_rn(cx, hw), dur);
+            const float x2 = __fmul_rn(__fadd_rn(cx, hw), dur);
+            int start = (int)floorf(x1);
+            start = start < 0 ? 0 : start;
+            int end = (int)ceilf(x2);
+            if (end > pl) end = pl;
+            cnt[j] = end - start;
+            int vend = end < len ? end : len;                                  // rows that hold data
+            const int64_t room = n_frames - base;                              // rows past the tensor end: none
+            if ((int64_t)vend > room) vend = (int)(room < 0 ? 0 : room);
+            st[j] = start;
+            en[j] = vend > start ? vend : start;
+            if (en[j] > st[j]) {
+                lo = st[j] < lo ? st[j] : lo;
+                hi = en[j] > hi ? en[j] : hi;
+            }
+        }
+    }
+    const int nv = Dv >> 2;
+    for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+        float4 acc[NQ];
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = lo; r < hi; r += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = (r + u < hi) ? __ldg(reinterpret_cast<const float4*>(frames + (base + r + u) * Dv) + c)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    if (r + u >= st[j] && r + u < en[j]) {
+                        acc[j].x += v[u].x; acc[j].y += v[u].y; acc[j].z += v[u].z; acc[j].w += v[u].w;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            if (j < nq) {
+                float4 o;
+                if (cnt[j] > 0) {
+                    const float fn = (float)cnt[j];
+                    o = make_float4(acc[j].x / fn, acc[j].y / fn, acc[j].z / fn, acc[j].w / fn);
+                } else {
+                    o = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+                }
+                reinterpret_cast<float4*>(pooled + (b * nq + j) * Dv)[c] = o;
+            }
+        }
+    }
+}
+
 // out[p] = sum_d (x[p,d] / ||x[p]||) * t[qidx[b], d]     one warp per proposal
 __global__ void norm_dot_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                 const int32_t* __restrict__ qidx, float* __restrict__ out, int64_t rows, int nq, int Dv) {
@@ -98,8 +176,16 @@ int span_mean_pool(const float* frames, int64_t n_frames, const int64_t* vid_bas
     CONE_REQUIRE((Dv & 3) == 0, "span_mean_pool: Dv must be a multiple of 4");
     const int threads = (Dv / 4) >= 256 ? 256 : ((Dv / 4 + 31) / 32) * 32;
     ProfScope ps(s, P_POOL);
-    span_mean_pool_kernel<<<(unsigned)(B * nq), threads, 0, s>>>(frames, n_frames, vid_base, vlen, pad_len, spans, pooled,
-                                                               nq, Dv);
+    if (nq <= 5) {
+        span_mean_pool_window_kernel<5><<<(unsigned)B, threads, 0, s>>>(frames, n_frames, vid_base, vlen, pad_len, spans,
+                                                                     pooled, nq, Dv);
+    } else if (nq <= 8) {
+        span_mean_pool_window_kernel<8><<<(unsigned)B, threads, 0, s>>>(frames, n_frames, vid_base, vlen, pad_len, spans,
+                                                                     pooled, nq, Dv);
+    } else {  // many proposals per window (cone_clip_matching allows up to 64): one CTA per proposal
+        span_mean_pool_kernel<<<(unsigned)(B * nq), threads, 0, s>>>(frames, n_frames, vid_base, vlen, pad_len, spans,
+                                                                   pooled, nq, Dv);
+    }
     CONE_LAUNCH_CHECK("span_mean_pool");
     return CONE_OK;
 }
