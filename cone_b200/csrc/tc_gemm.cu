@@ -200,7 +200,7 @@ constexpr int FAST_STAGES = 4;  // A + W ring depth of the streamlined epilogues
 
 // Epilogue variants.  The shape that carries most of the model's 2.9 M rows is compile-time specialised (no flag
 // tests, 64-column steps, accumulator released right after the second TMEM load, one staging box per warp):
-//   EPI_PLAIN16: bias (+ReLU) -> fp16                                         (QKV, FFN1, decoder K|V projections)
+//   EPI_PLAIN16: bias (+ReLU) -> fp16                                         (QKV, FFN1, decoder q | Wk^T q)
 //   EPI_LN16:    the generic code below with its flags fixed at compile time to bias + fp16 residual (TMA boxes) ->
 //                LayerNorm -> fp16                                             (out_proj, FFN2)
 //   EPI_GENERIC: every flag at run time: residual through TMA boxes, LayerNorm over the 256-wide row (out_proj,
