@@ -26,6 +26,17 @@ def lpt_assign(costs: Sequence[float], world_size: int) -> List[List[int]]:
     return [sorted(x) for x in out]
 
 
+def shard_queries(queries: Sequence, world_size: int, rank: int, eval_bsz: int = 1) -> list:
+    """One giant video (BASELINE.json configs[4]): the video is replicated on every rank and its QUERIES
+    are sharded.  Whole eval batches of `eval_bsz` consecutive queries stay together (the reference pools proposals over
+    windows padded to the longest window of an eval batch), batches are dealt round-robin."""
+    n_batches = (len(queries) + eval_bsz - 1) // eval_bsz
+    out = []
+    for b in range(rank, n_batches, world_size):
+        out.extend(queries[b * eval_bsz: (b + 1) * eval_bsz])
+    return out
+
+
 def gather_predictions(nms: torch.Tensor, count: torch.Tensor, qid: torch.Tensor | None = None, group=None,
                        equal_shards: bool = False) -> Tuple[torch.Tensor, ...]:
     """All-gather per-query prediction blocks [Nq_local, 3, max_after, 5] (+ counts [Nq_local, 3], + optional

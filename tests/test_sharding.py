@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cone_b200.sharding import gather_predictions, lpt_assign, video_cost
+from cone_b200.sharding import gather_predictions, lpt_assign, shard_queries, video_cost
 
 
 def test_lpt_assign_balances_and_is_deterministic():
@@ -20,6 +20,14 @@ def test_lpt_assign_balances_and_is_deterministic():
     loads = [sum(costs[i] for i in r) for r in a]
     assert max(loads) / (sum(loads) / 8) < 1.03  # within 3 % of perfect balance
     assert lpt_assign([5.0, 1.0], 4) == [[0], [1], [], []]
+
+
+def test_shard_queries_keeps_eval_batches_together():
+    qs = list(range(23))
+    parts = [shard_queries(qs, 4, r, eval_bsz=4) for r in range(4)]
+    assert sorted(x for p in parts for x in p) == qs
+    assert parts[0] == [0, 1, 2, 3, 16, 17, 18, 19] and parts[1] == [4, 5, 6, 7, 20, 21, 22] and parts[3] == [12, 13, 14, 15]
+    assert shard_queries(qs, 1, 0, eval_bsz=16) == qs
 
 
 def _free_port():
