@@ -508,8 +508,19 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
         const bool all_valid = (k1 <= vl) || (k1 <= Lv + tl && (vl == Lv || k0 >= Lv));
         blkflags = __ballot_sync(0xffffffffu, !all_valid);
     }
+    // Rows from Lv + tl on are text padding: they are never valid keys and nobody reads their outputs, so a 16-row block
+    // that holds only such rows is not computed (zeros are written: the rows stay finite for the GEMMs that follow).
+    const int nrb_live = (Lv + tl + 15) >> 4;
     for (int rb = warp; rb < nrb; rb += ATT_WARPS) {
         const int r_lo = rb * 16 + g, r_hi = r_lo + 8;
+        if (rb >= nrb_live) {  // warp-uniform
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                if (r_lo < S) *reinterpret_cast<uint32_t*>(o + (row0 + r_lo) * ldo + h * HD + nb * 8 + t4 * 2) = 0u;
+                if (r_hi < S) *reinterpret_cast<uint32_t*>(o + (row0 + r_hi) * ldo + h * HD + nb * 8 + t4 * 2) = 0u;
+            }
+            continue;
+        }
         uint32_t aq[2][4];
         // A fragments of Q: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15) for each 16-wide k step
 #pragma unroll
