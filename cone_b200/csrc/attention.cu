@@ -511,6 +511,7 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
     // Rows from Lv + tl on are text padding: they are never valid keys and nobody reads their outputs, so a 16-row block
     // that holds only such rows is not computed (zeros are written: the rows stay finite for the GEMMs that follow).
     const int nrb_live = (Lv + tl + 15) >> 4;
+    const int nkb_live = (Lv + tl + 7) >> 3;  // key blocks from here on hold only padding: their P is exactly 0
     for (int rb = warp; rb < nrb; rb += ATT_WARPS) {
         const int r_lo = rb * 16 + g, r_hi = r_lo + 8;
         if (rb >= nrb_live) {  // warp-uniform
@@ -544,7 +545,10 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
                 for (int jj = 0; jj < CH; ++jj) {
                     const int jb = ch * CH + jj;
                     sc[jj][0] = sc[jj][1] = sc[jj][2] = sc[jj][3] = -CUDART_INF_F;
-                    if (EXACT || jb < nkb) {
+                    // the last 16 keys of the tile are often all text padding (see nkb_live): only these two key blocks
+                    // carry the (warp-uniform) test, the others stay unconditional in the exact-size variant
+                    const bool live = jb < NB - 2 || jb < nkb_live;
+                    if ((EXACT || jb < nkb) && live) {
                         sc[jj][0] = sc[jj][1] = sc[jj][2] = sc[jj][3] = 0.f;
                         uint32_t bk[4];  // B fragments of K for keys jb*8..+7: dims 0-7, 8-15, 16-23, 24-31
                         ldsm_x4(bk, Ks + (jb * 8 + l8) * QK_PAD + lq * 8);
@@ -591,7 +595,7 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
 #pragma unroll
                 for (int kk = 0; kk < CH / 2; ++kk) {
                     const int kb = ch * (CH / 2) + kk;  // k-step of 16 keys
-                    if (EXACT || kb * 2 < nkb) {
+                    if ((EXACT || kb * 2 < nkb) && (kb < NB / 2 - 1 || kb * 2 < nkb_live)) {
                         uint32_t ap[4];
                         ap[0] = pack_half2(sc[2 * kk][0], sc[2 * kk][1]);
                         ap[1] = pack_half2(sc[2 * kk][2], sc[2 * kk][3]);
