@@ -652,8 +652,11 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
     }
     // tensor-core mode: no K / V projection of the memory at all — the cross-attention works on the raw encoder output
     // (dec_cross_attention_mem, attention.cu)
-    CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * Q * d, c.s));
-    if (tc) CONE_CUDA(cudaMemsetAsync(b.tgt16, 0, sizeof(uint16_t) * Q * d, c.s));
+    // The decoder starts from tgt = 0 (transformer.py:61), so everything up to the first cross-attention — self-attention
+    // block, norm1, and the cross-attention queries — is the same for every window: in tensor-core mode it is computed
+    // for ONE window (nq rows) and broadcast (identical bits: every row of these kernels is computed independently).
+    CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * (tc ? nq : Q) * d, c.s));
+    if (tc) CONE_CUDA(cudaMemsetAsync(b.tgt16, 0, sizeof(uint16_t) * nq * d, c.s));
     const float* qpos = c.w->p("query_embed.weight");
     for (int l = 0; l < DL; ++l) {
         const std::string p = "transformer.decoder.layers." + std::to_string(l);
@@ -682,6 +685,8 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
             // conversion passes); the residual stream stays fp32: the residual-adding GEMMs read it (R32), apply
             // LayerNorm in their epilogue and write it back as fp32 (next residual) and fp16 (next operand).
             TcWeights* t = c.w->tc;
+            const bool shared = (l == 0);           // window-independent prefix of layer 0: one window's rows
+            const int64_t Qs = shared ? nq : Q;
             auto G = [&](const uint16_t* A, int64_t lda, const float* W, const float* bias, int N, int K) {
                 TcGemmArgs g;
                 g.A16 = A; g.lda = lda; g.M = Q; g.W = W; g.bias = bias; g.N = N; g.K = K;
@@ -693,25 +698,30 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
                 g.C32 = b.tgt; g.ldc32 = d;
                 g.C16 = b.tgt16; g.ldc16 = d;
             };
-            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Q, nq, d, c.s));
+            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Qs, nq, d, c.s));
             TcGemmArgs g = G(b.dqkin16, d, inw, inb, 2 * d, d);  // q | k of the self-attention
-            g.C16 = b.dqkv16; g.ldc16 = 3 * d;
+            g.M = Qs; g.C16 = b.dqkv16; g.ldc16 = 3 * d;
             CONE_TRY(tc_gemm_run(t, g, c.s));
             g = G(b.tgt16, d, inw + (size_t)2 * d * d, inb + 2 * d, d, d);  // v
-            g.C16 = b.dqkv16 + 2 * d; g.ldc16 = 3 * d;
+            g.M = Qs; g.C16 = b.dqkv16 + 2 * d; g.ldc16 = 3 * d;
             CONE_TRY(tc_gemm_run(t, g, c.s));
-            CONE_TRY(dec_self_attention(b.dqkv16, 3 * d, b.dqkv16 + 2 * d, 3 * d, b.datt16, d, b.B, nq, H, 1, c.s));
+            CONE_TRY(dec_self_attention(b.dqkv16, 3 * d, b.dqkv16 + 2 * d, 3 * d, b.datt16, d, shared ? 1 : b.B, nq, H, 1, c.s));
             g = G(b.datt16, d, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"), d, d);
             LN(g, p + ".norm1");
+            g.M = Qs;
             CONE_TRY(tc_gemm_run(t, g, c.s));
-            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Q, nq, d, c.s));
+            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Qs, nq, d, c.s));
             // cross-attention on the raw memory: q | Wk_h^T q_h in one GEMM (N = 9 d), pooled memory per head out of the
             // attention kernel, Wv_h and the output projection folded into the next GEMM (K = 8 d)
             g = G(b.dqkin16, d, c.w->xq_w[l], c.w->xq_b[l], 9 * d, d);
-            g.C16 = b.dqt16; g.ldc16 = 9 * d;
+            g.M = Qs; g.C16 = b.dqt16; g.ldc16 = 9 * d;
             CONE_TRY(tc_gemm_run(t, g, c.s));
+            if (shared) {  // the fp32 residual of every window = the shared rows (staged in b.hs, free until the heads)
+                CONE_CUDA(cudaMemcpyAsync(b.hs, b.tgt, sizeof(float) * nq * d, cudaMemcpyDeviceToDevice, c.s));
+                CONE_TRY(add_row_table(nullptr, b.hs, b.tgt, Q, nq, d, c.s));
+            }
             CONE_TRY(dec_cross_attention_mem(b.src16, d, b.dqt16, 9 * d, b.dpm16, 8 * d, b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt,
-                                             c.w->pos_kdec16 + (size_t)l * d, (int64_t)DL * d, dm.max_v_l, c.s));
+                                             c.w->pos_kdec16 + (size_t)l * d, (int64_t)DL * d, dm.max_v_l, c.s, shared ? 1 : 0));
             g = G(b.dpm16, 8 * d, c.w->xo_w[l], c.w->xo_b[l], d, 8 * d);
             LN(g, p + ".norm2");
             CONE_TRY(tc_gemm_run(t, g, c.s));

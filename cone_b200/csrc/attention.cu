@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(MT * 64, NB <= 20 ? 2 : 1)
 dec_cross_attention_mem_kernel(const __half* __restrict__ mem, int64_t ldm, const __half* __restrict__ qqt, int64_t ldq,
                                __half* __restrict__ pm, int64_t ldp, const int32_t* __restrict__ vlen,
                                const int32_t* __restrict__ tlen, int nq, int Lv, int Lt,
-                               const __half* __restrict__ posk, int64_t ldposk, int table_lv) {
+                               const __half* __restrict__ posk, int64_t ldposk, int table_lv, int q_bcast) {
     // Two warps per 16-row block of the score matrix (ncu on the one-warp-per-block version: 6 warps per SM, every stall
     // a fixed-latency dependency): for the scores they split the key blocks (even / odd), exchange row maxima and
     // sums through shared memory, publish their halves of P there, and for P.M they split the 256 channels.
@@ -699,7 +699,7 @@ dec_cross_attention_mem_kernel(const __half* __restrict__ mem, int64_t ldm, cons
             __half* qd = Qt + r * XM_PAD + c;
             if (r < R) {
                 const int hh = r / nq, slot = r - hh * nq;
-                cp_async16(qd, qqt + (b * nq + slot) * ldq + D + hh * D + c);
+                cp_async16(qd, qqt + ((q_bcast ? 0 : b * nq) + slot) * ldq + D + hh * D + c);
             } else {
                 *reinterpret_cast<uint4*>(qd) = make_uint4(0u, 0u, 0u, 0u);
             }
@@ -713,7 +713,9 @@ dec_cross_attention_mem_kernel(const __half* __restrict__ mem, int64_t ldm, cons
     const int l8 = lane & 7, lq = lane >> 3;
     const int r_lo = mt * 16 + g, r_hi = r_lo + 8;           // this lane's two score rows
     const int h_lo = r_lo < R ? r_lo / nq : -1, h_hi = r_hi < R ? r_hi / nq : -1;
+    // output rows; the query rows are the same unless the queries are shared by all windows (q_bcast: rows 0..nq-1)
     const int64_t q_lo = r_lo < R ? (b * nq + (r_lo - h_lo * nq)) : 0, q_hi = r_hi < R ? (b * nq + (r_hi - h_hi * nq)) : 0;
+    const int64_t qs_lo = (q_bcast && r_lo < R) ? q_lo - b * nq : q_lo, qs_hi = (q_bcast && r_hi < R) ? q_hi - b * nq : q_hi;
 
     float sc[NJ][4];  // key block jb = 2 j + half
 #pragma unroll
@@ -750,8 +752,8 @@ dec_cross_attention_mem_kernel(const __half* __restrict__ mem, int64_t ldm, cons
             for (int u = 0; u < HP; ++u) {
                 const int hu = hh + u;  // hu > h_last: no row of this block belongs to it, its A fragments are zero
                 uint4 xl = make_uint4(0u, 0u, 0u, 0u), xh = xl;
-                if (h_lo == hu) xl = *reinterpret_cast<const uint4*>(qqt + q_lo * ldq + hu * HD + t4 * 8);
-                if (h_hi == hu) xh = *reinterpret_cast<const uint4*>(qqt + q_hi * ldq + hu * HD + t4 * 8);
+                if (h_lo == hu) xl = *reinterpret_cast<const uint4*>(qqt + qs_lo * ldq + hu * HD + t4 * 8);
+                if (h_hi == hu) xh = *reinterpret_cast<const uint4*>(qqt + qs_hi * ldq + hu * HD + t4 * 8);
                 a[u][0][0] = xl.x; a[u][0][1] = xh.x; a[u][0][2] = xl.y; a[u][0][3] = xh.y;
                 a[u][1][0] = xl.z; a[u][1][1] = xh.z; a[u][1][2] = xl.w; a[u][1][3] = xh.w;
                 const __half* pbase = posk + ((int64_t)vl * table_lv + half * 8 + g) * ldposk + hu * HD + t4 * 8;
@@ -972,7 +974,7 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
 // q | qt [B nq, 256 + 8 * 256] fp16 -> attention-pooled memory pm [B nq, 8 * 256] fp16 (see the kernel's comment)
 int dec_cross_attention_mem(const void* mem, int64_t ldm, const void* qqt, int64_t ldq, void* pm, int64_t ldp,
                             const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv, int Lt, const void* posk,
-                            int64_t ldposk, int table_lv, cudaStream_t s) {
+                            int64_t ldposk, int table_lv, cudaStream_t s, int q_bcast) {
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
     CONE_REQUIRE(nq >= 1 && nq <= 8 && S <= MAX_S, "dec_cross_attention_mem: unsupported nq=%d S=%d", nq, S);
@@ -993,7 +995,7 @@ int dec_cross_attention_mem(const void* mem, int64_t ldm, const void* qqt, int64
         }                                                                                                               \
         dec_cross_attention_mem_kernel<NBV, MTV><<<(unsigned)B, MTV * 64, smem, s>>>(                                   \
             static_cast<const __half*>(mem), ldm, static_cast<const __half*>(qqt), ldq, static_cast<__half*>(pm), ldp,  \
-            vlen, tlen, nq, Lv, Lt, static_cast<const __half*>(posk), ldposk, table_lv);                                \
+            vlen, tlen, nq, Lv, Lt, static_cast<const __half*>(posk), ldposk, table_lv, q_bcast);                       \
     } while (0)
 #define CONE_XMEM_MT(NBV)            \
     do {                             \

@@ -90,7 +90,8 @@ int dec_cross_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, 
 // memory (Wv and the output projection are applied by the next GEMM); posk = fp16 pos.Wk^T table
 int dec_cross_attention_mem(const void* mem, int64_t ldm, const void* qqt, int64_t ldq, void* pm, int64_t ldp,
                             const int32_t* vlen, const int32_t* tlen, int64_t B, int nq, int Lv, int Lt, const void* posk,
-                            int64_t ldposk, int table_lv, cudaStream_t s);
+                            int64_t ldposk, int table_lv, cudaStream_t s, int q_bcast = 0);
+// q_bcast = 1: the queries are the same for every window (decoder layer 0: tgt starts at zero) — qqt holds nq rows
 
 // ---------------------------------------------------------------- prefilter.cu
 int window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count, int n_queries,
