@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libcone_b200.so")
 
 PREC_FP32 = 0
 PREC_TC = 1
+PREC_TC_SPLIT = 2  # cone_linear only: 3-product split-fp16 GEMM (fp32-class accuracy on the tensor pipe)
 
 
 class ConeDims(C.Structure):

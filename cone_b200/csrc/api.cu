@@ -433,13 +433,32 @@ struct Ctx {
     const cone_weights* w;
     int prec;
     cudaStream_t s;
+    uint16_t* split_scratch = nullptr;  // [M, 3 K] fp16 operand staging of the 3-product GEMM (CONE_PREC_TC_SPLIT)
 };
+
+// y = epi(x W^T + b (+R)) with fp32-class accuracy on the fp16 tensor pipe: x and W are split into fp16 hi + lo parts and
+// the three significant products are accumulated in fp32 by one GEMM over 3 K columns (tc_gemm.cu, split3).
+// Used in tensor-core mode for the projections whose accuracy must not enter the fp16 error budget (input projections,
+// span head); the window-ranking GEMMs stay on the fp32 pipe so that rank-lists do not depend on the precision mode.
+int split_linear(const Ctx& c, const float* x, int64_t ldx, int64_t M, const float* W, const float* b, int N, int K,
+                 float* y, int64_t ldy, int relu, const float* R, int64_t ldr, uint16_t* scratch16) {
+    CONE_TRY(split3_f16_rows(x, ldx, scratch16, M, K, c.s));
+    TcGemmArgs g;
+    g.A16 = scratch16; g.lda = 3 * (int64_t)K; g.M = M; g.W = W; g.bias = b; g.N = N; g.K = K; g.split3 = 1;
+    g.C32 = y; g.ldc32 = ldy; g.relu = relu; g.R32 = R; g.ldr32 = ldr;
+    return tc_gemm_run(c.w->tc, g, c.s);
+}
 
 // y[M,N] = epi(x[M,K] * W^T + b (+R)) in the requested precision
 int linear(const Ctx& c, const float* x, int64_t ldx, int64_t M, const float* W, const float* b, int N, int K, float* y,
            int64_t ldy, int relu, const float* R = nullptr, int64_t ldr = 0) {
     if (c.prec == CONE_PREC_TC && tc_gemm_supported(M, N, K)) {
         return tc_gemm(c.w->tc, x, ldx, M, W, b, N, K, y, ldy, relu, R, ldr, c.s);
+    }
+    if (c.prec == CONE_PREC_TC_SPLIT) {
+        CONE_REQUIRE(tc_gemm_supported(M, N, 3 * K) && (K & 3) == 0, "split GEMM: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+        CONE_REQUIRE(c.split_scratch != nullptr, "split GEMM: no operand scratch");
+        return split_linear(c, x, ldx, M, W, b, N, K, y, ldy, relu, R, ldr, c.split_scratch);
     }
     GemmParams g;
     g.A = x; g.lda = ldx; g.W = W; g.ldw = K; g.C = y; g.ldc = ldy; g.bias = b; g.R = R; g.ldr = ldr;
@@ -455,19 +474,22 @@ int linear_named(const Ctx& c, const float* x, int64_t ldx, int64_t M, const std
 // LinearLayer x2 (cone/model.py:443-465, 55-72): LN -> Linear -> ReLU -> LN -> Linear
 struct ProjBuffers {
     float *ln_in, *h1, *ln_h1;
+    uint16_t* a3;  // split fp16 operand staging (tensor-core mode)
 };
 ProjBuffers plan_proj(Arena& a, int64_t rows, int din, int d) {
     ProjBuffers b;
     b.ln_in = a.get<float>(rows * din);
     b.h1 = a.get<float>(rows * d);
     b.ln_h1 = a.get<float>(rows * d);
+    b.a3 = a.get<uint16_t>(rows * 3 * (din > d ? din : d));
     return b;
 }
 int input_proj(const Ctx& cin, const char* name, const float* x, int64_t rows, int din, float* out, ProjBuffers& b) {
     // per-frame / per-query work, a few GFLOP per movie: kept in fp32 in every mode (error budget)
-    // (measured: fp16-operand tensor-core GEMMs here save 0.9 ms per step but raise the end-to-end error by 13-20 % rms and
-    // push 0.27 % of the values past 1e-3: profiles/r01_notes.md)
-    const Ctx c{cin.w, CONE_PREC_FP32, cin.s};
+    // (measured: plain fp16-operand tensor-core GEMMs here save 0.9 ms per step but raise the end-to-end error by 13-20 %
+    // rms and push 0.27 % of the values past 1e-3: profiles/r01_notes.md — hence the split GEMM in tensor-core mode)
+    const bool split = cin.prec == CONE_PREC_TC && (din % 64) == 0 && cin.w->tc != nullptr;
+    const Ctx c{cin.w, split ? CONE_PREC_TC_SPLIT : CONE_PREC_FP32, cin.s, b.a3};
     const int d = c.w->dims.hidden;
     const std::string p0 = std::string(name) + ".0", p1 = std::string(name) + ".1";
     CONE_TRY(layernorm_rows(x, nullptr, c.w->p(p0 + ".LayerNorm.weight"), c.w->p(p0 + ".LayerNorm.bias"), b.ln_in, rows,
@@ -495,6 +517,7 @@ struct CoreBuffers {
     uint16_t *src16, *qkv16, *att16, *h16;                             // [R, .] fp16 (tensor-core mode only)
     float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
     uint16_t *tgt16, *dqkin16, *dqkv16, *datt16, *dqt16, *dpm16, *dh16;      // [B*nq, .] fp16 (tensor-core mode only)
+    uint16_t* hs3 = nullptr;                                                 // [B*nq, 3 d] split operand of the span head
     int64_t *vid_base, *txt_base;
     int32_t *vlen, *tlen, *pad_len, *qidx;
     // tensor-core mode, optional: q|k|v of encoder layer 0 per FRAME and per TOKEN (the projection of a row does not
@@ -532,6 +555,7 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, i
         b.datt16 = a.get<uint16_t>(Q * d);
         b.dqt16 = a.get<uint16_t>(Q * 9 * d);  // q | q pushed through Wk_h^T per head
         b.dpm16 = a.get<uint16_t>(Q * 8 * d);  // attention-pooled memory per head
+        b.hs3 = a.get<uint16_t>(Q * 3 * d);
         b.dh16 = a.get<uint16_t>(Q * c.ffn);
     } else {
         b.t2 = a.get<float>(Q * d);
@@ -557,7 +581,9 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, i
 // heads on hs [Q, d]: class logits / foreground probability and sigmoid spans (cone/model.py:112-115,
 // cone/inference.py:47,52)
 int heads(const Ctx& cin, CoreBuffers& b, const float* hs, int64_t Q, float* logits, float* prob_fg, float* spans) {
-    const Ctx c{cin.w, CONE_PREC_FP32, cin.s};  // 5 rows per window: fp32 in every mode
+    // 5 rows per window: fp32 accuracy in every mode (split GEMM on the tensor pipe in tensor-core mode)
+    const bool split = cin.prec == CONE_PREC_TC && b.hs3 != nullptr && cin.w->tc != nullptr;
+    const Ctx c{cin.w, split ? CONE_PREC_TC_SPLIT : CONE_PREC_FP32, cin.s, b.hs3};
     const int d = c.w->dims.hidden;
     if (logits) CONE_TRY(rowdot_small(hs, d, c.w->p("class_embed.weight"), c.w->p("class_embed.bias"), logits, Q, 2, d, 0, c.s));
     if (prob_fg) CONE_TRY(rowdot_small(hs, d, c.w->p("class_embed.weight"), c.w->p("class_embed.bias"), prob_fg, Q, 2, d, 2, c.s));
@@ -890,6 +916,13 @@ extern "C" int cone_linear(const cone_weights* w, const float* x, const float* W
                            int32_t K, int relu, const float* residual, float* y, void* workspace, size_t workspace_bytes,
                            int precision, void* stream) {
     CONE_REQUIRE(w && x && W && y, "null argument");
+    if (precision == CONE_PREC_TC_SPLIT) {  // operator-level access to the 3-product GEMM (tests)
+        CONE_REQUIRE(workspace && workspace_bytes >= (size_t)M * 3 * K * 2, "cone_linear: split GEMM needs %zu bytes of workspace",
+                     (size_t)M * 3 * K * 2);
+        Ctx c{w, precision, (cudaStream_t)stream, static_cast<uint16_t*>(workspace)};
+        CONE_TRY(ensure_tc(w, CONE_PREC_TC, c.s));
+        return linear(c, x, K, M, W, bias, N, K, y, N, relu, residual, N);
+    }
     CONE_TRY(check_prec(precision));
     Ctx c{w, precision, (cudaStream_t)stream};
     CONE_TRY(ensure_tc(w, precision, c.s));

@@ -613,6 +613,34 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ x, int64_t ldx, __ha
     }
 }
 
+// fp32 -> split fp16 operand for the 3-product GEMM: x = hi + lo with hi = fp16(x), lo = fp16(x - hi).
+//   activations (weights = 0): row [hi | hi | lo]      weights (weights = 1): row [hi | lo | hi]
+// so that A'.W'^T = hi.hi + hi.lo + lo.hi: every product of two fp16 values is exact in the fp32 accumulator and the
+// dropped lo.lo term is 2^-22 relative — fp32-class accuracy on the fp16 tensor pipe.
+__global__ void split3_f16_kernel(const float* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t rows, int K4,
+                                  int weights) {
+    const int64_t total = rows * K4;
+    const int K = K4 * 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K4;
+        const int c = (int)(i % K4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __half hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float s = fminf(fmaxf(f[e], -65504.f), 65504.f);
+            hi[e] = __float2half_rn(s);
+            lo[e] = __float2half_rn(s - __half2float(hi[e]));
+        }
+        __half* row = y + r * (int64_t)(3 * K);
+        const uint2 H = *reinterpret_cast<const uint2*>(hi), L = *reinterpret_cast<const uint2*>(lo);
+        *reinterpret_cast<uint2*>(row + c) = H;
+        *reinterpret_cast<uint2*>(row + K + c) = weights ? L : H;
+        *reinterpret_cast<uint2*>(row + 2 * K + c) = weights ? H : L;
+    }
+}
+
 // ------------------------------------------------------------------------------------- host helpers
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -672,9 +700,10 @@ struct TcWeights {
     struct W16 {
         __half* ptr;
         CUtensorMap map;
-        int N, K, BN;
+        int N, K, BN;  // K = columns of the fp16 copy (3 x the fp32 K for a split copy)
     };
-    std::map<const float*, W16> cache;  // fp16 copies of nn.Linear weights, keyed by the fp32 device pointer
+    // fp16 copies of nn.Linear weights, keyed by the fp32 device pointer and the kind of copy (plain / split)
+    std::map<std::pair<const float*, int>, W16> cache;
     char* scratch = nullptr;
     size_t scratch_bytes = 0;
     int num_sms = kNumSMs;
@@ -725,19 +754,39 @@ int f32_to_f16_rows(const float* x, int64_t ldx, uint16_t* y, int64_t rows, int 
     return f32_to_f16(x, ldx, reinterpret_cast<__half*>(y), rows, cols, s);
 }
 
-static int get_w16(TcWeights* t, const float* W, int N, int K, cudaStream_t s, const TcWeights::W16** out) {
-    auto it = t->cache.find(W);
-    if (it == t->cache.end() || it->second.N != N || it->second.K != K) {
+static int split3(const float* x, int64_t ldx, __half* y, int64_t rows, int K, int weights, cudaStream_t s) {
+    if (rows == 0) return CONE_OK;
+    const int64_t total = rows * (K / 4);
+    const int64_t want = cdiv64(total, 256);
+    const unsigned grid = (unsigned)(want < (int64_t)kNumSMs * 16 ? want : (int64_t)kNumSMs * 16);
+    ProfScope ps(s, P_CONVERT, 0.0, 10.0 * (double)rows * K);
+    split3_f16_kernel<<<grid, 256, 0, s>>>(x, ldx, y, rows, K / 4, weights);
+    CONE_LAUNCH_CHECK("split3_f16");
+    return CONE_OK;
+}
+
+int split3_f16_rows(const float* x, int64_t ldx, uint16_t* y, int64_t rows, int K, cudaStream_t s) {
+    CONE_REQUIRE((K & 3) == 0 && (ldx & 3) == 0, "split3_f16_rows: K and ldx must be multiples of 4");
+    return split3(x, ldx, reinterpret_cast<__half*>(y), rows, K, 0, s);
+}
+
+// K = the fp32 weight's K; split = 1 makes the [N, 3 K] split copy of the 3-product GEMM
+static int get_w16(TcWeights* t, const float* W, int N, int K, int split, cudaStream_t s, const TcWeights::W16** out) {
+    const auto key = std::make_pair(W, split);
+    const int K16 = split ? 3 * K : K;
+    auto it = t->cache.find(key);
+    if (it == t->cache.end() || it->second.N != N || it->second.K != K16) {
         TcWeights::W16 w{};
         w.N = N;
-        w.K = K;
+        w.K = K16;
         w.BN = (N % 256 == 0) ? 256 : 128;
-        CONE_CUDA(cudaMalloc(&w.ptr, (size_t)N * K * 2));
-        CONE_TRY(f32_to_f16(W, K, w.ptr, N, K, s));
-        CONE_TRY(make_map(&w.map, w.ptr, false, N, K, K, BK, w.BN));
+        CONE_CUDA(cudaMalloc(&w.ptr, (size_t)N * K16 * 2));
+        if (split) CONE_TRY(split3(W, K, w.ptr, N, K, 1, s));
+        else CONE_TRY(f32_to_f16(W, K, w.ptr, N, K, s));
+        CONE_TRY(make_map(&w.map, w.ptr, false, N, K16, K16, BK, w.BN));
         if (it != t->cache.end()) cudaFree(it->second.ptr);
-        t->cache[W] = w;
-        it = t->cache.find(W);
+        t->cache[key] = w;
+        it = t->cache.find(key);
     }
     *out = &it->second;
     return CONE_OK;
@@ -747,13 +796,17 @@ static int get_w16(TcWeights* t, const float* W, int N, int K, cudaStream_t s, c
 // buffer, so device pointers and TMA descriptors (and any CUDA graph that captured them) stay valid.
 int tc_weights_refresh(TcWeights* t, cudaStream_t s) {
     if (!t) return CONE_OK;
-    for (auto& kv : t->cache) CONE_TRY(f32_to_f16(kv.first, kv.second.K, kv.second.ptr, kv.second.N, kv.second.K, s));
+    for (auto& kv : t->cache) {
+        if (kv.first.second) CONE_TRY(split3(kv.first.first, kv.second.K / 3, kv.second.ptr, kv.second.N, kv.second.K / 3, 1, s));
+        else CONE_TRY(f32_to_f16(kv.first.first, kv.second.K, kv.second.ptr, kv.second.N, kv.second.K, s));
+    }
     return CONE_OK;
 }
 
 int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     CONE_REQUIRE(t != nullptr, "tc_gemm: tensor-core weights not initialised");
-    CONE_REQUIRE(tc_gemm_supported(g.M, g.N, g.K), "tc_gemm: unsupported shape M=%lld N=%d K=%d", (long long)g.M, g.N, g.K);
+    const int K16 = g.split3 ? 3 * g.K : g.K;  // columns of the fp16 operands
+    CONE_REQUIRE(tc_gemm_supported(g.M, g.N, K16), "tc_gemm: unsupported shape M=%lld N=%d K=%d", (long long)g.M, g.N, K16);
     CONE_REQUIRE(g.M < (int64_t)1 << 31, "tc_gemm: more than 2^31 rows");
     CONE_REQUIRE((g.lda % 8) == 0 && (reinterpret_cast<uintptr_t>(g.A16) & 15) == 0, "tc_gemm: A must be 16-byte aligned");
     CONE_REQUIRE(g.C32 == nullptr || ((g.ldc32 % 4) == 0 && (reinterpret_cast<uintptr_t>(g.C32) & 15) == 0), "tc_gemm: C32 alignment");
@@ -761,12 +814,12 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     CONE_REQUIRE(g.R16 == nullptr || ((g.ldr16 % 8) == 0 && (reinterpret_cast<uintptr_t>(g.R16) & 15) == 0), "tc_gemm: R16 alignment");
     CONE_REQUIRE(g.R32 == nullptr || ((g.ldr32 % 4) == 0 && (reinterpret_cast<uintptr_t>(g.R32) & 15) == 0), "tc_gemm: R32 alignment");
     const TcWeights::W16* w = nullptr;
-    CONE_TRY(get_w16(t, g.W, g.N, g.K, s, &w));
+    CONE_TRY(get_w16(t, g.W, g.N, g.K, g.split3, s, &w));
     CONE_REQUIRE(g.ln_g == nullptr || g.N == w->BN, "tc_gemm: fused LayerNorm needs the whole row in one tile (N=%d)", g.N);
     CONE_REQUIRE(!(g.C16 && g.C32 && g.R16 && g.ln_g == nullptr),
                  "tc_gemm: fp16 + fp32 outputs with an fp16 residual need the LayerNorm epilogue");
     CUtensorMap mapA, mapR, mapC16, mapC32;
-    CONE_TRY(make_map(&mapA, g.A16, false, g.M, g.K, g.lda, BK, BM));
+    CONE_TRY(make_map(&mapA, g.A16, false, g.M, K16, g.lda, BK, BM));
     mapR = mapA;
     mapC16 = mapA;
     mapC32 = mapA;  // placeholders when unused (never dereferenced)
@@ -788,15 +841,15 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     const int n_tiles = g.N / w->BN;
     const int64_t tiles = m_tiles * n_tiles;
     // weights-resident variant: K = 256, BN = 256, at most num_sms / n_tiles CTAs per n-tile
-    const bool wres = w->BN == 256 && g.K == WRES_KBLOCKS * BK && n_tiles <= t->num_sms && !(g.C16 && g.C32);
+    const bool wres = w->BN == 256 && K16 == WRES_KBLOCKS * BK && n_tiles <= t->num_sms && !(g.C16 && g.C32);
     unsigned grid = (unsigned)(tiles < t->num_sms ? tiles : t->num_sms);
     if (wres) {
         const int64_t per_n = t->num_sms / n_tiles;
         grid = (unsigned)((m_tiles < per_n ? m_tiles : per_n) * n_tiles);
     }
     const double mn = (double)g.M * g.N;
-    ProfScope ps(s, P_GEMM_TC, 2.0 * mn * g.K,
-                 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + (g.C32 ? 4.0 : 0.0) * mn + (g.C16 ? 2.0 : 0.0) * mn +
+    ProfScope ps(s, P_GEMM_TC, 2.0 * mn * K16,
+                 2.0 * ((double)g.M * K16 + (double)g.N * K16) + (g.C32 ? 4.0 : 0.0) * mn + (g.C16 ? 2.0 : 0.0) * mn +
                      (g.R32 ? 4.0 : 0.0) * mn + (g.R16 ? 2.0 : 0.0) * mn);
 #define CONE_TC_LAUNCH(BNV, WR, MD)                                                                                 \
     do {                                                                                                                \
@@ -807,7 +860,7 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
             attr = true;                                                                                                \
         }                                                                                                               \
         tc_gemm_kernel<BNV, WR, MD><<<grid, TC_THREADS, tc_smem_bytes<BNV, WR, MD>(), s>>>(                             \
-            mapA, w->map, mapR, mapC16, mapC32, ep, g.M, g.N, g.K);                                                     \
+            mapA, w->map, mapR, mapC16, mapC32, ep, g.M, g.N, K16);                                                     \
     } while (0)
     const bool plain16 = w->BN == 256 && g.C16 && !g.C32 && !g.R16 && !g.R32 && !g.ln_g && g.bias;
     const bool ln16 = w->BN == 256 && g.C16 && !g.C32 && g.R16 && !g.R32 && g.ln_g && g.bias && !g.relu;

@@ -37,9 +37,14 @@ struct TcGemmArgs {
     int64_t ldr16 = 0;
     const float* ln_g = nullptr;
     const float* ln_b = nullptr;
+    // 3-product GEMM with fp32-class accuracy: A16 holds [hi | hi | lo] rows of 3 K columns (split3_f16_rows), the
+    // cached weight copy is [hi | lo | hi]; K stays the fp32 K
+    int split3 = 0;
 };
 int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s);
 
+// y[rows, 3 K] (fp16, dense) = [hi | hi | lo] with hi = fp16(x), lo = fp16(x - hi)
+int split3_f16_rows(const float* x, int64_t ldx, uint16_t* y, int64_t rows, int K, cudaStream_t s);
 // y[rows, cols] (fp16, dense) = saturating round-to-nearest of x[rows, ldx] (cols % 4 == 0)
 int f32_to_f16_rows(const float* x, int64_t ldx, uint16_t* y, int64_t rows, int cols, cudaStream_t s);
 

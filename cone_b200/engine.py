@@ -207,8 +207,9 @@ class ConeEngine:
         M, K = x.shape
         N = weight.shape[0]
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        prec = self.precision if precision is None else {"fp32": _lib.PREC_FP32, "tc": _lib.PREC_TC}[precision]
-        ws, nb = self._wsargs(M * K * 2 + 4096)
+        prec = self.precision if precision is None else {"fp32": _lib.PREC_FP32, "tc": _lib.PREC_TC,
+                                                          "split": _lib.PREC_TC_SPLIT}[precision]
+        ws, nb = self._wsargs(M * K * 6 + 4096)
         _lib.check(self.lib.cone_linear(self._handle, _ptr(x), _ptr(weight), _ptr(bias), M, N, K, int(relu),
                                         _ptr(residual), _ptr(y), ws, nb, prec, _stream()), "cone_linear")
         return y

@@ -36,6 +36,8 @@ extern "C" {
 /* compute precision of the dense projections */
 #define CONE_PREC_FP32 0 /* fp32 CUDA-core GEMMs: parity mode, 1e-5 vs the reference */
 #define CONE_PREC_TC 1   /* tcgen05 tensor-core GEMMs (fp16 operands, fp32 accumulate): 1e-3 */
+#define CONE_PREC_TC_SPLIT 2 /* cone_linear only: 3-product split-fp16 GEMM on tcgen05, fp32-class accuracy (what
+                                CONE_PREC_TC uses for the input projections and the span head) */
 
 /* Model / window hyper-parameters (cone/config.py:73-125; values per dataset in
  * cone/scripts/train_{ego4d,mad}.sh). */
