@@ -9,9 +9,11 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; tensors are row-major,
  *     contiguous, fp32 unless stated; the caller owns all buffers, outputs and the workspace;
- *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing
- *     (the weights handle is the only owner of hidden device memory) and keeps no global state,
- *     so calls on different streams with different workspaces are re-entrant;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and allocates nothing
+ *     per call: the weights handle is the only owner of hidden device memory (the packed state
+ *     dict, derived tables and, on first use of CONE_PREC_TC, fp16 weight copies).  Calls may be
+ *     queued on different streams with different workspaces; calls that share one weights handle
+ *     must come from one host thread at a time (the handle caches per-call scratch pointers);
  *   - return value 0 = OK, negative = error (CONE_ERR_*); cone_last_error() gives the message
  *     of the calling thread's last failure;
  *   - masks of the reference API are prefix masks (1 = valid, then 0 = pad), which is the only
