@@ -184,7 +184,7 @@ def run_ours(args):
     from cone_b200 import _lib
     from cone_b200.config import PRESETS
     from cone_b200.engine import ConeEngine
-    from cone_b200.inference import run_step, stage_step
+    from cone_b200.inference import stage_step
     from cone_b200.sharding import gather_predictions
     from cone_b200.synth import make_dataset
     from cone_b200.weights import init_state_dict

@@ -14,9 +14,8 @@ first use, so a query costs one H2D of its features, one graph launch and one D2
 from __future__ import annotations
 
 from types import SimpleNamespace
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import List, Optional, Tuple, Union
 
-import numpy as np
 import torch
 
 from .config import EGO4D, ConeConfig

@@ -10,7 +10,7 @@ import torch
 from cone_b200.weights import init_state_dict
 from oracle import cone_oracle as O
 from oracle.make_golden_localizer import CASES, localizer_case
-from helpers import GOLDEN, ROUND_TOL
+from helpers import GOLDEN
 
 DEV = "cuda:0"
 
