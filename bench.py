@@ -275,6 +275,13 @@ def run_ours(args):
     max_frames = max(s.frames.shape[0] for s in host_steps)
     fbuf = [torch.empty((max_frames, cfg.v_feat_dim), dtype=torch.float32, device=dev) for _ in range(2)]
     consumed = [None, None]  # event recorded on the main stream when the kernels reading fbuf[slot] have been queued
+    # ... and for the packed queries (same shapes in every step of this workload): no allocator call inside the timed
+    # loop (two runs on fresh boxes lost half of their end-to-end rate to cudaMalloc on the copy stream)
+    import dataclasses
+    same_shapes = all(all(getattr(s.qb, f.name).shape == getattr(host_steps[0].qb, f.name).shape
+                          for f in dataclasses.fields(s.qb) if isinstance(getattr(s.qb, f.name), torch.Tensor))
+                      for s in host_steps)
+    qbuf = [host_steps[0].qb.to(dev, non_blocking=False) for _ in range(2)] if same_shapes else None
 
     def prefetch(i):
         s = host_steps[i % len(host_steps)]
@@ -284,7 +291,16 @@ def run_ours(args):
                 copy_stream.wait_event(consumed[slot])
             frames_d = fbuf[slot][: s.frames.shape[0]]
             frames_d.copy_(s.frames, non_blocking=True)
-            qb = s.qb.to(dev)
+            if qbuf is None:
+                qb = s.qb.to(dev)
+            else:
+                dst, upd = qbuf[slot], {}
+                for f in dataclasses.fields(s.qb):
+                    t = getattr(s.qb, f.name)
+                    if isinstance(t, torch.Tensor):
+                        getattr(dst, f.name).copy_(t, non_blocking=True)
+                        upd[f.name] = getattr(dst, f.name)
+                qb = dataclasses.replace(s.qb, **upd)  # host metadata of this step, device tensors of the slot
         return s, frames_d, qb
 
     host_out = []
@@ -302,7 +318,8 @@ def run_ours(args):
     for i in range(args.steps):
         s, frames_d, qb = nxt
         main.wait_stream(copy_stream)
-        qb.record_stream(main)
+        if qbuf is None:
+            qb.record_stream(main)
         if i + 1 < args.steps:
             nxt = prefetch(i + 1)
         out = eng.ground(frames_d, qb)
