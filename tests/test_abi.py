@@ -79,3 +79,14 @@ def test_pack_queries_groups_by_video_and_keeps_eval_batches():
     n = min(len(q.tokens), cfg.max_q_l)
     assert np.array_equal(qb.tokens[j, :n].numpy(), q.tokens[:n])
     assert not qb.tokens[j, n:].any()
+
+
+def test_bench_algorithmic_flops_match_the_survey():
+    """transformer + heads FLOPs per query, 9.72 / 20.4 / 21.05 GFLOP (Ego4D / MAD-512 / MAD-768)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from cone_b200.config import MAD768
+    for cfg, want in ((EGO4D, 9.72e9), (MAD512, 20.4e9), (MAD768, 21.05e9)):
+        assert abs(bench.algorithmic_flops_per_query(cfg) / want - 1) < 0.01, cfg.name
