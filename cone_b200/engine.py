@@ -74,9 +74,23 @@ class QueryBatch:
                    for f in dataclasses.fields(self) if isinstance(getattr(self, f.name), torch.Tensor))
 
 
-def pack_queries(cfg: ConeConfig, video_lengths: Sequence[int], queries, first_dataset_index: int = 0) -> QueryBatch:
-    """Host tensors for a list of queries (objects with query_id, video_idx, tokens, cls) in DATASET order."""
+def pack_queries(cfg: ConeConfig, video_lengths: Sequence[int], queries, first_dataset_index: int = 0,
+                 dataset_indices: Optional[Sequence[int]] = None) -> QueryBatch:
+    """Host tensors for a list of queries (objects with query_id, video_idx, tokens, cls) in DATASET order.
+
+    `dataset_indices[i]` is the position of `queries[i]` in the whole dataset: the reference's DataLoader forms its
+    eval batches from consecutive DATASET indices (`cone/inference.py:306-315`), and a proposal is pooled over
+    windows padded to the longest window of its eval batch, so the batch id of a query must come
+    from its true index even when a step holds a non-contiguous selection (annotations not grouped by video, or a
+    rank's share of a multi-video step).  Default: the queries are consecutive from `first_dataset_index`."""
     nq = len(queries)
+    if dataset_indices is None:
+        ds_idx = np.arange(nq, dtype=np.int64) + int(first_dataset_index)
+    else:
+        ds_idx = np.asarray(dataset_indices, dtype=np.int64)
+        if ds_idx.shape != (nq,):
+            raise ValueError(f"dataset_indices must have one entry per query ({nq}), got shape {ds_idx.shape}")
+    batch_of, dense = np.unique(ds_idx // cfg.eval_bsz, return_inverse=True) if nq else (np.zeros(0), np.zeros(0, np.int64))
     order = np.argsort(np.asarray([q.video_idx for q in queries], dtype=np.int64), kind="stable")
     offs = np.zeros(len(video_lengths) + 1, dtype=np.int64)
     offs[1:] = np.cumsum(np.asarray(video_lengths, dtype=np.int64))
@@ -96,9 +110,8 @@ def pack_queries(cfg: ConeConfig, video_lengths: Sequence[int], queries, first_d
         video_offsets=torch.from_numpy(offs), q_first=torch.from_numpy(q_first),
         q_video_start=torch.from_numpy(offs[vid]), q_video_len=torch.from_numpy(np.diff(offs)[vid].astype(np.int32)),
         tokens=torch.from_numpy(tokens), tok_len=torch.from_numpy(tok_len), cls=torch.from_numpy(cls),
-        q_batch=torch.from_numpy(((order + first_dataset_index) // cfg.eval_bsz
-                                  - first_dataset_index // cfg.eval_bsz).astype(np.int32)),
-        n_batches=int((nq - 1 + first_dataset_index) // cfg.eval_bsz - first_dataset_index // cfg.eval_bsz + 1) if nq else 1,
+        q_batch=torch.from_numpy(np.asarray(dense, dtype=np.int64).reshape(-1)[order].astype(np.int32)),
+        n_batches=max(int(len(batch_of)), 1),
         max_video_frames=int(max(video_lengths)) if len(video_lengths) else 0,
         max_video_queries=int(per_video.max()) if nq else 0,
         total_scores=int((per_video.astype(np.int64) * np.diff(offs)).sum()), order=order,

@@ -47,8 +47,7 @@ def stage_step(cfg: ConeConfig, videos: Sequence[np.ndarray], queries, video_ids
     local = [dataclasses.replace(q, video_idx=vid_set[q.video_idx]) for _, q in sel]
     lens = [len(videos[v]) for v in video_ids]
     frames = torch.from_numpy(np.concatenate([videos[v] for v in video_ids], axis=0))
-    first = sel[0][0] if sel else 0
-    qb = pack_queries(cfg, lens, local, first_dataset_index=first)
+    qb = pack_queries(cfg, lens, local, dataset_indices=[i for i, _ in sel])
     if pin and torch.cuda.is_available():
         frames = frames.pin_memory()
         qb = qb.pin()

@@ -37,7 +37,7 @@ def encode_record(compress: bool = True, **arrays) -> bytes:
 def decode_video_record(buf) -> np.ndarray:
     """bytes -> raw features [L, Dv] float32 (ego4d_mad_dataloader.py:294-302 returns them un-normalised)."""
     with io.BytesIO(bytes(buf)) as r:
-        dump = np.load(r, allow_pickle=True)
+        dump = np.load(r, allow_pickle=False)
         if "features" not in dump:
             raise KeyError("video record has no 'features' array")
         return np.ascontiguousarray(dump["features"], dtype=np.float32)
@@ -47,7 +47,7 @@ def decode_query_record(buf) -> Tuple[np.ndarray, np.ndarray]:
     """bytes -> (token_features [n_tok, Dt], holistic feature [Dv]) float32, raw (ego4d_mad_dataloader.py:258-282):
     `cls_features` if present, else `eot_features`; a [1, Dv] holistic feature is squeezed."""
     with io.BytesIO(bytes(buf)) as r:
-        dump = np.load(r, allow_pickle=True)
+        dump = np.load(r, allow_pickle=False)
         tok = np.ascontiguousarray(dump["token_features"], dtype=np.float32)
         cls = dump["cls_features"] if "cls_features" in dump else dump["eot_features"]
         cls = np.asarray(cls, dtype=np.float32)
@@ -119,28 +119,61 @@ class StagedSteps:
         self.cfg, self.store, self.video_ids, self.queries, self.pin = cfg, video_store, list(video_ids), queries, pin
         self.plan = plan_steps(video_lengths, queries, max_frames_per_step)
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+        self._stop = threading.Event()
         self._thread = threading.Thread(target=self._produce, daemon=True)
         self._thread.start()
+
+    def _put(self, item) -> bool:
+        """Blocking put that gives up when the consumer has closed the iterator."""
+        while not self._stop.is_set():
+            try:
+                self._q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def _produce(self) -> None:
         try:
             for ids in self.plan:
+                if self._stop.is_set():
+                    return
                 # stage_step only indexes videos[v] for v in ids: a dict of this step's decoded arrays is enough
                 vids: Dict[int, np.ndarray] = {v: decode_video_record(self.store.get(self.video_ids[v])) for v in ids}
                 step = stage_step(self.cfg, vids, self.queries, ids, pin=self.pin)
-                self._q.put(step)
-            self._q.put(None)
+                if not self._put(step):
+                    return
+            self._put(None)
         except BaseException as e:  # surface decoding errors in the consumer thread
-            self._q.put(e)
+            self._put(e)
+
+    def close(self) -> None:
+        """Stop the producer (the consumer abandoned the iterator): staged pinned steps are dropped."""
+        self._stop.set()
+        while True:
+            try:
+                self._q.get_nowait()
+            except queue.Empty:
+                break
+        self._thread.join(timeout=5.0)
+
+    def __enter__(self) -> "StagedSteps":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
 
     def __iter__(self) -> Iterator[HostStep]:
-        while True:
-            item = self._q.get()
-            if item is None:
-                return
-            if isinstance(item, BaseException):
-                raise item
-            yield item
+        try:
+            while True:
+                item = self._q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:  # also runs when the consumer breaks out of its loop (generator close)
+            self.close()
 
 
 def ground_store(engine, video_store, query_store, annotations: Sequence[dict], video_lengths: Optional[Dict[str, int]] = None,

@@ -31,6 +31,21 @@ def _as_f32(x) -> torch.Tensor:
     return t.detach().to(torch.float32)
 
 
+def _video_key(obj, v: torch.Tensor):
+    """Identity of a video for the per-video cache.  NOT `id(obj)` alone: CPython reuses the ids of freed objects,
+    and the reference driver builds `video_feats` as a function-local that dies after every call
+    (run_on_video/run.py:54-57), so a second video could silently hit the first one's cache.  The cache therefore
+    keeps a strong reference to the object it was filled from (its id cannot be recycled while cached) and the key
+    also carries the storage address, the shape, the tensor version counter (every in-place edit of a torch tensor)
+    and a fingerprint of 16 evenly spaced rows (numpy arrays have no version counter: an in-place edit that misses
+    all sampled rows is not seen — call `set_video` after editing a numpy array in place)."""
+    ver = getattr(obj, "_version", None)
+    n = v.shape[0]
+    rows = sorted({(i * (n - 1)) // 15 for i in range(16)}) if n else []
+    sample = v[rows].contiguous().cpu().numpy().tobytes() if rows else b""
+    return (id(obj), int(v.data_ptr()), tuple(v.shape), ver, hash(sample))
+
+
 class CONELocalizator:
     def __init__(self, load_checkpoint_path: Union[str, dict] = "ckpt/model_best.ckpt", device: str = "cuda",
                  cfg: ConeConfig = EGO4D_DEMO, precision: str = "fp32", workspace_bytes: int = 1 << 30,
@@ -48,6 +63,7 @@ class CONELocalizator:
         self.max_v_l = cfg.max_v_l
         self.use_cuda_graph = use_cuda_graph
         self._video = None  # (key, xn, ctx, vidproj)
+        self._video_obj = None  # strong reference to the object the cache was filled from (see _video_key)
         self._graph = None
         self._static: Optional[SimpleNamespace] = None
 
@@ -77,9 +93,11 @@ class CONELocalizator:
                 # its launch geometry depends on the number of frames only, so it stays valid
                 for dst, src in zip(self._video[1:], (xn, ctx, vidproj)):
                     dst.copy_(src)
-                self._video = (id(video_feats),) + tuple(self._video[1:])
+                self._video = (_video_key(video_feats, v),) + tuple(self._video[1:])
+                self._video_obj = video_feats
                 return
-        self._video = (id(video_feats), xn, ctx, vidproj)
+        self._video = (_video_key(video_feats, v), xn, ctx, vidproj)
+        self._video_obj = video_feats
         self._graph = None
         self._static = None
 
@@ -97,7 +115,8 @@ class CONELocalizator:
     @torch.no_grad()
     def predict_moment(self, video_feats, text_feats: Tuple) -> List[List[float]]:
         """-> [[st, ed, fusion_score], ...] (<= max_after_nms rows), as the reference returns."""
-        if self._video is None or self._video[0] != id(video_feats):
+        if self._video is None or self._video_obj is not video_feats or \
+                self._video[0] != _video_key(video_feats, _as_f32(video_feats)):
             self.set_video(video_feats)
         tokens, cls = _as_f32(text_feats[0]).cpu(), _as_f32(text_feats[1]).cpu().reshape(-1)
         n_frames = self._video[1].shape[0]

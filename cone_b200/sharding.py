@@ -78,8 +78,13 @@ def reduce_counters(counters, group=None):
         return counters
     for t in (counters.hits, counters.window_hits, counters.n_queries):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    if counters.top1_iou:
-        local = torch.cat(counters.top1_iou)
+    # Whether the top-1 IoUs are gathered is decided COLLECTIVELY: a rank that received no videos or queries
+    # (world > n_videos, an empty query shard) has an empty list but must still enter the collectives.
+    dev = counters.hits.device
+    flag = torch.tensor([1 if counters.top1_iou else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()):
+        local = torch.cat(counters.top1_iou) if counters.top1_iou else torch.zeros((0, 3), dtype=torch.float64, device=dev)
         gathered = gather_predictions(local, local.new_zeros((local.shape[0], 1)), group=group)[0]
         counters.top1_iou = [gathered]
     return counters

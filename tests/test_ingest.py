@@ -88,3 +88,51 @@ def test_ground_store_equals_in_memory_path():
     assert a.keys() == b.keys()
     for k in a:
         assert a[k] == b[k]
+
+
+def test_staged_steps_producer_exits_when_the_consumer_stops_early():
+    """a consumer that breaks out of the loop must not leave the producer blocked on queue.put."""
+    cfg = EGO4D.replace(eval_bsz=2)
+    ds = make_dataset(cfg, 6, [100] * 6, 1, seed=9)
+    vs, qs = _stores(ds)
+    queries = ingest.load_queries(qs, ds.annotations(), {v: i for i, v in enumerate(ds.video_ids)})
+    steps = ingest.StagedSteps(cfg, vs, ds.video_ids, [100] * 6, queries, max_frames_per_step=100, depth=1, pin=False)
+    for s in steps:
+        break  # abandon after the first of six steps
+    steps._thread.join(timeout=5.0)
+    assert not steps._thread.is_alive()
+    with ingest.StagedSteps(cfg, vs, ds.video_ids, [100] * 6, queries, max_frames_per_step=100, depth=1, pin=False) as st2:
+        pass  # never iterated
+    assert not st2._thread.is_alive()
+
+
+def test_records_are_loaded_without_pickle():
+    import pickle
+
+    class Evil:
+        def __reduce__(self):
+            return (pytest.fail, ("pickle payload executed",))
+    rec = ingest.encode_record(features=np.array([Evil()], dtype=object))
+    with pytest.raises((ValueError, pickle.UnpicklingError)):
+        ingest.decode_video_record(rec)
+
+
+def test_eval_batch_ids_follow_true_dataset_indices():
+    """ADVICE r1: q_batch = dataset index // eval_bsz even when a step's queries are not contiguous in the dataset."""
+    from cone_b200.engine import pack_queries
+    cfg = EGO4D.replace(eval_bsz=4)
+    ds = make_dataset(cfg, 3, [100, 120, 90], [3, 3, 3], seed=2)
+    # interleave the annotations: dataset order v0 v1 v2 v0 v1 v2 ...
+    inter = [ds.queries[3 * v + j] for j in range(3) for v in range(3)]
+    step = stage_step(cfg, ds.videos, inter, [0, 2], pin=False)  # queries of videos 0 and 2: dataset idx 0,2,3,5,6,8
+    by_id = dict(zip(step.qb.query_ids, step.qb.q_batch.tolist()))
+    want = {}
+    for i, q in enumerate(inter):
+        if q.video_idx in (0, 2):
+            want[q.query_id] = i // 4
+    dense = {b: n for n, b in enumerate(sorted(set(want.values())))}
+    assert by_id == {k: dense[b] for k, b in want.items()}
+    assert step.qb.n_batches == len(dense) == 3
+    # contiguous default unchanged
+    qb = pack_queries(cfg, [100, 120, 90], ds.queries, first_dataset_index=6)
+    assert sorted(set(qb.q_batch.tolist())) == [0, 1, 2] and qb.n_batches == 3

@@ -89,3 +89,44 @@ def test_localizer_cuda_graph_replay_equals_eager():
         assert a == b and len(a) >= 1
     with pytest.raises(ValueError):
         graph.predict_moment(v, (rng.standard_normal((cfg.max_q_l + 1, cfg.t_feat_dim), dtype=np.float32), v[0]))
+
+
+def test_video_cache_key_is_not_the_object_id():
+    """CPython reuses ids of freed temporaries; the cache key must tell two such videos apart and must see
+    in-place edits (numpy fingerprint, torch version counter)."""
+    from cone_b200.localizer import _video_key, _as_f32
+    a = np.zeros((5, 4), dtype=np.float32)
+    ka = _video_key(a, _as_f32(a))
+    b = np.ones((5, 4), dtype=np.float32)
+    assert _video_key(b, _as_f32(b)) != ka
+    a[4] = 7.0  # in-place edit of a sampled row
+    assert _video_key(a, _as_f32(a)) != ka
+    t = torch.zeros((6, 4))
+    kt = _video_key(t, _as_f32(t))
+    t.add_(1.0)
+    assert _video_key(t, _as_f32(t)) != kt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_localizer_second_temporary_video_is_not_served_from_the_cache(graph):
+    """Two different videos passed as temporaries of the same shape (the reference driver's usage,
+    run_on_video/run.py:54-57): each call must be computed on its own video."""
+    from cone_b200.localizer import CONELocalizator
+    cfg, wseed, L, nt, seed = CASES["ego4d_900"]
+    sd = init_state_dict(cfg, wseed)
+    v1, tok, cls = localizer_case(cfg, L, nt, seed)
+    v2, _, _ = localizer_case(cfg, L, nt, seed + 17)
+    ref = CONELocalizator(sd, device=DEV, cfg=cfg, use_cuda_graph=False)
+    want1 = ref.predict_moment(v1, (tok, cls))
+    ref2 = CONELocalizator(sd, device=DEV, cfg=cfg, use_cuda_graph=False)
+    want2 = ref2.predict_moment(v2, (tok, cls))
+    assert want1 != want2
+    loc = CONELocalizator(sd, device=DEV, cfg=cfg, use_cuda_graph=graph)
+    got1 = loc.predict_moment(v1.copy(), (tok, cls))  # temporaries: freed right after each call
+    got2 = loc.predict_moment(v2.copy(), (tok, cls))
+    assert got1 == want1 and got2 == want2
+    buf = v1.copy()
+    assert loc.predict_moment(buf, (tok, cls)) == want1
+    buf[:] = v2  # in-place edit of the same array
+    assert loc.predict_moment(buf, (tok, cls)) == want2

@@ -68,3 +68,31 @@ def test_gather_predictions_without_process_group_is_identity():
     nms, cnt = torch.rand(4, 3, 5, 5, dtype=torch.float64), torch.ones(4, 3, dtype=torch.int32)
     a, b = gather_predictions(nms, cnt)
     assert a is nms and b is cnt
+
+
+def _counter_worker(rank, world, port, out_dir):
+    """rank 1 received no videos (world > n_videos): it must still enter the collectives of reduce_counters."""
+    from cone_b200.inference import new_counters
+    from cone_b200.sharding import reduce_counters
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = new_counters("cpu")
+    if rank == 0:
+        c.hits += 2
+        c.n_queries += 4
+        c.top1_iou.append(torch.arange(12, dtype=torch.float64).reshape(4, 3))
+    reduce_counters(c)
+    torch.save({"hits": c.hits, "n": c.n_queries, "iou": torch.cat(c.top1_iou)}, os.path.join(out_dir, f"c{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_reduce_counters_with_an_empty_rank_does_not_hang(tmp_path):
+    world = 2
+    mp.spawn(_counter_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(tmp_path / f"c{r}.pt")
+        assert int(res["n"].item()) == 4 and int(res["hits"].sum().item()) == 2 * res["hits"].numel()
+        assert torch.equal(res["iou"], torch.arange(12, dtype=torch.float64).reshape(4, 3))
