@@ -515,9 +515,11 @@ struct CoreBuffers {
     int Lv, Lt, hw;
     float *src, *srcpos, *qk, *v, *att, *tmp, *h;                      // [R, .] fp32 (srcpos..h: fp32 mode only)
     uint16_t *src16, *qkv16, *att16, *h16;                             // [R, .] fp16 (tensor-core mode only)
+    uint16_t* src16lo = nullptr;                                       // [R, d] fp16 low part of the residual stream
     float *tgt, *t2, *dqkin, *dqk, *dv, *datt, *dq, *dh, *hs, *hid1, *hid2;  // [B*nq, .]
-    uint16_t *tgt16, *dqkin16, *dqkv16, *datt16, *dqt16, *dpm16, *dh16;      // [B*nq, .] fp16 (tensor-core mode only)
+    uint16_t *dqt16, *dpm16;                                                 // [B*nq, .] fp16 (tensor-core mode only)
     uint16_t* hs3 = nullptr;                                                 // [B*nq, 3 d] split operand of the span head
+    uint16_t* dsplit16 = nullptr;                                            // [B*nq, 3 ffn] split operand staging of the decoder
     int64_t *vid_base, *txt_base;
     int32_t *vlen, *tlen, *pad_len, *qidx;
     // tensor-core mode, optional: q|k|v of encoder layer 0 per FRAME and per TOKEN (the projection of a row does not
@@ -526,6 +528,17 @@ struct CoreBuffers {
     const uint16_t* token_qkv = nullptr;
     int64_t n_frames = 0;
 };
+
+// The fused encoder tail (enc_tail.cu) replaces out_proj + norm1 + linear1 + linear2 + norm2 of the tensor-core mode;
+// CONE_FUSED_TAIL=0 in the environment selects the unfused three-GEMM chain (A/B measurements, fall-back).
+bool fused_tail_enabled(const cone_dims& c) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("CONE_FUSED_TAIL");
+        env = (e && e[0] == '0') ? 0 : 1;
+    }
+    return env == 1 && enc_tail_supported(c.hidden, c.ffn);
+}
 
 CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, int prec) {
     CoreBuffers b{};
@@ -536,9 +549,11 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, i
     b.src = a.get<float>(R * d);
     if (prec == CONE_PREC_TC) {
         b.src16 = a.get<uint16_t>(R * d);
+        b.src16lo = a.get<uint16_t>(R * d);
         b.qkv16 = a.get<uint16_t>(R * 3 * d);
         b.att16 = a.get<uint16_t>(R * d);
-        b.h16 = a.get<uint16_t>(R * b.hw);
+        // the [R, ffn] hidden activations only exist in the unfused chain (enc_tail.cu keeps them on chip)
+        b.h16 = fused_tail_enabled(c) ? nullptr : a.get<uint16_t>(R * b.hw);
     } else {
         b.srcpos = a.get<float>(R * d);
         b.qk = a.get<float>(R * 2 * d);
@@ -548,23 +563,19 @@ CoreBuffers plan_core(Arena& a, const cone_dims& c, int64_t B, int Lv, int Lt, i
         b.h = a.get<float>(R * b.hw);
     }
     b.tgt = a.get<float>(Q * d);
-    if (prec == CONE_PREC_TC) {  // the decoder chain keeps an fp32 residual stream and fp16 GEMM operands
-        b.tgt16 = a.get<uint16_t>(Q * d);
-        b.dqkin16 = a.get<uint16_t>(Q * d);
-        b.dqkv16 = a.get<uint16_t>(Q * 3 * d);
-        b.datt16 = a.get<uint16_t>(Q * d);
+    b.dqkin = a.get<float>(Q * d);
+    b.dqk = a.get<float>(Q * 2 * d);
+    b.dv = a.get<float>(Q * d);
+    b.datt = a.get<float>(Q * d);
+    b.dh = a.get<float>(Q * c.ffn);
+    if (prec == CONE_PREC_TC) {  // the decoder chain is fp32 between kernels; its GEMMs are 3-product split GEMMs
         b.dqt16 = a.get<uint16_t>(Q * 9 * d);  // q | q pushed through Wk_h^T per head
         b.dpm16 = a.get<uint16_t>(Q * 8 * d);  // attention-pooled memory per head
         b.hs3 = a.get<uint16_t>(Q * 3 * d);
-        b.dh16 = a.get<uint16_t>(Q * c.ffn);
+        b.dsplit16 = a.get<uint16_t>(Q * 3 * (c.ffn > d ? c.ffn : d));
     } else {
         b.t2 = a.get<float>(Q * d);
-        b.dqkin = a.get<float>(Q * d);
-        b.dqk = a.get<float>(Q * 2 * d);
-        b.dv = a.get<float>(Q * d);
-        b.datt = a.get<float>(Q * d);
         b.dq = a.get<float>(Q * d);
-        b.dh = a.get<float>(Q * c.ffn);
     }
     b.hs = a.get<float>(Q * d);
     b.hid1 = a.get<float>(Q * d);
@@ -647,6 +658,24 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
                 CONE_TRY(enc_self_attention_f16(b.qkv16, 3 * d, b.qkv16 + 2 * d, 3 * d, b.att16, d, b.vlen, b.tlen, b.B,
                                                 b.Lv, b.Lt, H, c.w->pos_qk[l], dm.max_v_l, c.s));
             }
+            const bool last_enc = (l == dm.enc_layers - 1);
+            if (fused_tail_enabled(dm)) {
+                // out_proj + norm1 + linear1 + relu + linear2 + norm2 in ONE kernel (enc_tail.cu): the residual stream is
+                // fp32-accurate (hi + lo fp16 across HBM, fp32 inside the kernel), the [R, ffn] hidden stays on chip
+                EncTailArgs e;
+                e.att16 = b.att16; e.lda = d;
+                e.res_hi = b.src16; e.res_lo = b.src16lo; e.ldr = d;
+                e.out_hi = b.src16; e.out_lo = last_enc ? nullptr : b.src16lo; e.ldo = d;  // the memory is read as fp16
+                if (saliency && last_enc) { e.C32 = b.src; e.ldc32 = d; }
+                e.M = R; e.d = d; e.ffn = ff;
+                e.Wo = c.w->p(p + ".self_attn.out_proj.weight"); e.bo = c.w->p(p + ".self_attn.out_proj.bias");
+                e.ln1_g = c.w->p(p + ".norm1.weight"); e.ln1_b = c.w->p(p + ".norm1.bias");
+                e.W1 = c.w->p(p + ".linear1.weight"); e.b1 = c.w->p(p + ".linear1.bias");
+                e.W2 = c.w->p(p + ".linear2.weight"); e.b2 = c.w->p(p + ".linear2.bias");
+                e.ln2_g = c.w->p(p + ".norm2.weight"); e.ln2_b = c.w->p(p + ".norm2.bias");
+                CONE_TRY(enc_tail_run(t, e, c.s));
+                continue;
+            }
             g = G(b.att16, d, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"), d, d);
             g.R16 = b.src16; g.ldr16 = d;
             g.ln_g = c.w->p(p + ".norm1.weight"); g.ln_b = c.w->p(p + ".norm1.bias");
@@ -659,7 +688,7 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
             g.R16 = b.src16; g.ldr16 = d;
             g.ln_g = c.w->p(p + ".norm2.weight"); g.ln_b = c.w->p(p + ".norm2.bias");
             g.C16 = b.src16; g.ldc16 = d;
-            if (saliency && l == dm.enc_layers - 1) { g.C32 = b.src; g.ldc32 = d; }  // fp32 memory for saliency_proj
+            if (saliency && last_enc) { g.C32 = b.src; g.ldc32 = d; }  // fp32 memory for saliency_proj
             CONE_TRY(tc_gemm_run(t, g, c.s));
         }
     }
@@ -682,7 +711,6 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
     // block, norm1, and the cross-attention queries — is the same for every window: in tensor-core mode it is computed
     // for ONE window (nq rows) and broadcast (identical bits: every row of these kernels is computed independently).
     CONE_CUDA(cudaMemsetAsync(b.tgt, 0, sizeof(float) * (tc ? nq : Q) * d, c.s));
-    if (tc) CONE_CUDA(cudaMemsetAsync(b.tgt16, 0, sizeof(uint16_t) * nq * d, c.s));
     const float* qpos = c.w->p("query_embed.weight");
     for (int l = 0; l < DL; ++l) {
         const std::string p = "transformer.decoder.layers." + std::to_string(l);
@@ -707,40 +735,46 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
             CONE_TRY(linear_named(c, b.dh, ff, Q, p + ".linear2", d, ff, b.t2, d, 0, b.tgt, d));
             CONE_TRY(layernorm_rows(b.t2, nullptr, c.w->p(p + ".norm3.weight"), c.w->p(p + ".norm3.bias"), b.tgt, Q, d, 1e-5f, c.s));
         } else {
-            // Tensor-core decoder chain: every GEMM operand is fp16 and is written by the kernel that produces it (no
-            // conversion passes); the residual stream stays fp32: the residual-adding GEMMs read it (R32), apply
-            // LayerNorm in their epilogue and write it back as fp32 (next residual) and fp16 (next operand).
+            // Tensor-core decoder chain.  5 rows per window against 150 in the encoder: the decoder is cheap, and its
+            // roundings reach the span / class heads without being averaged over keys, so it keeps fp32-class accuracy:
+            // fp32 activations between kernels, every GEMM a 3-product split-fp16 GEMM on tcgen05 (operands AND weights
+            // as fp16 hi + lo, tc_gemm.cu), LayerNorm + fp32 residual in the epilogues.  Only the cross-attention kernel
+            // itself works on fp16 (queries pushed through Wk^T, raw encoder memory, pooled memory).  Measured by
+            // emulation (profiles/tc_emulate.py): with fp16 decoder operands the end-to-end error of spans / probabilities
+            // is 1.8e-4 rms with a tail past 1e-3; with this chain 1.3e-4 rms and max 7-8e-4.
             TcWeights* t = c.w->tc;
             const bool shared = (l == 0);           // window-independent prefix of layer 0: one window's rows
             const int64_t Qs = shared ? nq : Q;
-            auto G = [&](const uint16_t* A, int64_t lda, const float* W, const float* bias, int N, int K) {
-                TcGemmArgs g;
-                g.A16 = A; g.lda = lda; g.M = Q; g.W = W; g.bias = bias; g.N = N; g.K = K;
-                return g;
+            // y = epi(x W^T + b): x fp32 [M, K] -> [hi | hi | lo] staging -> split GEMM; the caller fills the epilogue
+            auto SG = [&](const float* x, int64_t ldx, int64_t M, const float* W, const float* bias, int N, int K,
+                          TcGemmArgs& g) -> int {
+                CONE_TRY(split3_f16_rows(x, ldx, b.dsplit16, M, K, c.s));
+                g = TcGemmArgs();
+                g.A16 = b.dsplit16; g.lda = 3 * (int64_t)K; g.M = M; g.W = W; g.bias = bias; g.N = N; g.K = K; g.split3 = 1;
+                return CONE_OK;
             };
-            auto LN = [&](TcGemmArgs& g, const std::string& norm) {  // + residual, LayerNorm, dual output
+            auto LN = [&](TcGemmArgs& g, const std::string& norm) {  // + fp32 residual, LayerNorm, fp32 stream out
                 g.R32 = b.tgt; g.ldr32 = d;
                 g.ln_g = c.w->p(norm + ".weight"); g.ln_b = c.w->p(norm + ".bias");
                 g.C32 = b.tgt; g.ldc32 = d;
-                g.C16 = b.tgt16; g.ldc16 = d;
             };
-            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Qs, nq, d, c.s));
-            TcGemmArgs g = G(b.dqkin16, d, inw, inb, 2 * d, d);  // q | k of the self-attention
-            g.M = Qs; g.C16 = b.dqkv16; g.ldc16 = 3 * d;
+            TcGemmArgs g;
+            CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Qs, nq, d, c.s));
+            CONE_TRY(SG(b.dqkin, d, Qs, inw, inb, 2 * d, d, g));  // q | k of the self-attention
+            g.C32 = b.dqk; g.ldc32 = 2 * d;
             CONE_TRY(tc_gemm_run(t, g, c.s));
-            g = G(b.tgt16, d, inw + (size_t)2 * d * d, inb + 2 * d, d, d);  // v
-            g.M = Qs; g.C16 = b.dqkv16 + 2 * d; g.ldc16 = 3 * d;
+            CONE_TRY(SG(b.tgt, d, Qs, inw + (size_t)2 * d * d, inb + 2 * d, d, d, g));  // v
+            g.C32 = b.dv; g.ldc32 = d;
             CONE_TRY(tc_gemm_run(t, g, c.s));
-            CONE_TRY(dec_self_attention(b.dqkv16, 3 * d, b.dqkv16 + 2 * d, 3 * d, b.datt16, d, shared ? 1 : b.B, nq, H, 1, c.s));
-            g = G(b.datt16, d, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"), d, d);
+            CONE_TRY(dec_self_attention(b.dqk, 2 * d, b.dv, d, b.datt, d, shared ? 1 : b.B, nq, H, 0, c.s));
+            CONE_TRY(SG(b.datt, d, Qs, c.w->p(p + ".self_attn.out_proj.weight"), c.w->p(p + ".self_attn.out_proj.bias"), d, d, g));
             LN(g, p + ".norm1");
-            g.M = Qs;
             CONE_TRY(tc_gemm_run(t, g, c.s));
-            CONE_TRY(add_row_table_f16(b.tgt, qpos, b.dqkin16, Qs, nq, d, c.s));
+            CONE_TRY(add_row_table(b.tgt, qpos, b.dqkin, Qs, nq, d, c.s));
             // cross-attention on the raw memory: q | Wk_h^T q_h in one GEMM (N = 9 d), pooled memory per head out of the
             // attention kernel, Wv_h and the output projection folded into the next GEMM (K = 8 d)
-            g = G(b.dqkin16, d, c.w->xq_w[l], c.w->xq_b[l], 9 * d, d);
-            g.M = Qs; g.C16 = b.dqt16; g.ldc16 = 9 * d;
+            CONE_TRY(SG(b.dqkin, d, Qs, c.w->xq_w[l], c.w->xq_b[l], 9 * d, d, g));
+            g.C16 = b.dqt16; g.ldc16 = 9 * d;
             CONE_TRY(tc_gemm_run(t, g, c.s));
             if (shared) {  // the fp32 residual of every window = the shared rows (staged in b.hs, free until the heads)
                 CONE_CUDA(cudaMemcpyAsync(b.hs, b.tgt, sizeof(float) * nq * d, cudaMemcpyDeviceToDevice, c.s));
@@ -748,13 +782,15 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
             }
             CONE_TRY(dec_cross_attention_mem(b.src16, d, b.dqt16, 9 * d, b.dpm16, 8 * d, b.vlen, b.tlen, b.B, nq, b.Lv, b.Lt,
                                              c.w->pos_kdec16 + (size_t)l * d, (int64_t)DL * d, dm.max_v_l, c.s, shared ? 1 : 0));
-            g = G(b.dpm16, 8 * d, c.w->xo_w[l], c.w->xo_b[l], d, 8 * d);
+            // the pooled memory only exists in fp16: 2-product GEMM (weights hi + lo)
+            g = TcGemmArgs();
+            g.A16 = b.dpm16; g.lda = 8 * d; g.M = Q; g.W = c.w->xo_w[l]; g.bias = c.w->xo_b[l]; g.N = d; g.K = 8 * d; g.wsplit = 1;
             LN(g, p + ".norm2");
             CONE_TRY(tc_gemm_run(t, g, c.s));
-            g = G(b.tgt16, d, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d);
-            g.relu = 1; g.C16 = b.dh16; g.ldc16 = ff;
+            CONE_TRY(SG(b.tgt, d, Q, c.w->p(p + ".linear1.weight"), c.w->p(p + ".linear1.bias"), ff, d, g));
+            g.relu = 1; g.C32 = b.dh; g.ldc32 = ff;
             CONE_TRY(tc_gemm_run(t, g, c.s));
-            g = G(b.dh16, ff, c.w->p(p + ".linear2.weight"), c.w->p(p + ".linear2.bias"), d, ff);
+            CONE_TRY(SG(b.dh, ff, Q, c.w->p(p + ".linear2.weight"), c.w->p(p + ".linear2.bias"), d, ff, g));
             LN(g, p + ".norm3");
             CONE_TRY(tc_gemm_run(t, g, c.s));
         }
@@ -930,6 +966,44 @@ extern "C" int cone_linear(const cone_weights* w, const float* x, const float* W
     return linear(c, x, K, M, W, bias, N, K, y, N, relu, residual, N);
 }
 
+extern "C" int cone_encoder_tail(const cone_weights* w, int32_t layer, const float* att, const float* res, int64_t M,
+                                 float* out, int32_t cta_group, void* workspace, size_t workspace_bytes, void* stream) {
+    CONE_REQUIRE(w && att && res && out && workspace, "null argument");
+    const cone_dims& dm = w->dims;
+    CONE_REQUIRE(layer >= 0 && layer < dm.enc_layers, "cone_encoder_tail: layer %d out of range", layer);
+    CONE_REQUIRE(enc_tail_supported(dm.hidden, dm.ffn), "cone_encoder_tail: unsupported width");
+    CONE_REQUIRE(M >= 1, "cone_encoder_tail: no rows");
+    cudaStream_t s = (cudaStream_t)stream;
+    CONE_TRY(ensure_tc(w, CONE_PREC_TC, s));
+    const int d = dm.hidden;
+    Arena a(workspace, workspace_bytes);
+    uint16_t* att16 = a.get<uint16_t>(M * d);
+    uint16_t* rhi = a.get<uint16_t>(M * d);
+    uint16_t* rlo = a.get<uint16_t>(M * d);
+    uint16_t* ohi = a.get<uint16_t>(M * d);
+    uint16_t* olo = a.get<uint16_t>(M * d);
+    if (!a.fits()) {
+        set_error("cone_encoder_tail: workspace needs %zu bytes, got %zu", a.used, workspace_bytes);
+        return CONE_ERR_WORKSPACE;
+    }
+    CONE_TRY(f32_to_f16_rows(att, d, att16, M, d, s));
+    CONE_TRY(split_hilo_rows(res, rhi, rlo, M * d, s));
+    const std::string p = "transformer.encoder.layers." + std::to_string(layer);
+    EncTailArgs e;
+    e.att16 = att16; e.lda = d;
+    e.res_hi = rhi; e.res_lo = rlo; e.ldr = d;
+    e.out_hi = ohi; e.out_lo = olo; e.ldo = d;
+    e.M = M; e.d = d; e.ffn = dm.ffn;
+    e.Wo = w->p(p + ".self_attn.out_proj.weight"); e.bo = w->p(p + ".self_attn.out_proj.bias");
+    e.ln1_g = w->p(p + ".norm1.weight"); e.ln1_b = w->p(p + ".norm1.bias");
+    e.W1 = w->p(p + ".linear1.weight"); e.b1 = w->p(p + ".linear1.bias");
+    e.W2 = w->p(p + ".linear2.weight"); e.b2 = w->p(p + ".linear2.bias");
+    e.ln2_g = w->p(p + ".norm2.weight"); e.ln2_b = w->p(p + ".norm2.bias");
+    e.cta_group = cta_group;
+    CONE_TRY(enc_tail_run(w->tc, e, s));
+    return combine_hilo_rows(ohi, olo, out, M * d, s);
+}
+
 extern "C" int cone_frame_scores(const float* ctx, int32_t v_dim, const int64_t* video_offsets, const int32_t* q_first,
                                  int32_t n_videos, int32_t max_video_frames, int32_t max_video_queries,
                                  const float* cls_norm, float* score_out, const int64_t* score_offsets, int precision,
@@ -1060,7 +1134,10 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         }
         CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
                                         topk, Lt, Lv, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
-        if (precision == CONE_PREC_TC) {
+        if (precision == CONE_PREC_TC && fused_tail_enabled(dm)) {  // hi + lo of the projected rows (fp32-accurate residual)
+            CONE_TRY(gather_window_rows_f16(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src16, B, Lv, Lt, dm.hidden,
+                                            c.s, cb.src16lo));
+        } else if (precision == CONE_PREC_TC) {
             CONE_TRY(gather_window_rows_h2h(vidproj16, n_frames, cb.vid_base, txtproj16, cb.txt_base, cb.src16, B, Lv, Lt,
                                             dm.hidden, c.s));
         } else {
@@ -1103,7 +1180,7 @@ extern "C" int cone_forward(const cone_weights* w, const float* src_txt, const i
     CONE_CUDA(cudaMemcpyAsync(cb.tlen, txt_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, c.s));
     if (precision == CONE_PREC_TC) {
         CONE_TRY(gather_window_rows_f16(vidproj, (int64_t)B * Lv, cb.vid_base, txtproj, cb.txt_base, cb.src16, B, Lv, Lt,
-                                        dm.hidden, c.s));
+                                        dm.hidden, c.s, fused_tail_enabled(dm) ? cb.src16lo : nullptr));
     } else {
         CONE_TRY(gather_window_rows(vidproj, (int64_t)B * Lv, cb.vid_base, txtproj, cb.txt_base, cb.src, B, Lv, Lt, dm.hidden, c.s));
     }

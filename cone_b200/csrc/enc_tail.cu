@@ -1,0 +1,607 @@
+// Fused tail of a Moment-DETR encoder layer on the tensor cores (CONE_PREC_TC):
+//
+//     x   = LayerNorm1(res + att . Wo^T + bo)                      cone/transformer.py:239-241 (out_proj, norm1)
+//     out = LayerNorm2(x + relu(x . W1^T + b1) . W2^T + b2)        cone/transformer.py:242-245 (linear1/2, norm2)
+//
+// for a [M, 256] stream of window rows, ONE kernel: the LayerNorm1 output and the [M, 1024] FFN hidden never reach HBM
+// (the unfused chain wrote and re-read 7.2 KB per row and layer; this kernel moves 1.5-2.5 KB).
+//
+// sm_100a design.  Persistent, one CTA per SM, warp-specialised like tc_gemm.cu (warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-9 epilogue), 128 rows per CTA and tile.  With CG = 2 two CTAs of a cluster form a tcgen05 CTA pair
+// (`cta_group::2`, M = 256): every weight tile is split between the two CTAs' shared memories, so each SM streams HALF
+// of the 1.15 MB of weights per 128 rows from L2 — at one CTA per tile the weight stream alone (10 TB/s over 148 SMs)
+// would exceed what L2 delivers.
+//
+// Data flow of one tile (TMEM: Y = columns [0,256), Hreg = columns [256,512)):
+//   GEMM0   Hreg  = att . Wo^T   (K = 256)  + res_hi . I + res_lo . I     -- the residual rows ride the same TMA ring as
+//           the operands and are added by N = 64 MMAs against a 64 x 64 identity tile (exact: products with 1.0, fp32
+//           accumulation), so the epilogue never touches global memory for them
+//   epi-0   x = LN1(Hreg + bo): fp16 copy -> X tile in shared memory (A operand of GEMM1, UMMA K-major 128B-swizzle
+//           layout written by the epilogue threads), fp32 x + b2 -> Y (tcgen05.st): the fp32 residual of the FFN is
+//           the INITIAL VALUE of GEMM2's accumulator and never leaves the SM
+//   for each chunk c of 128 hidden columns (double buffered in TMEM and shared memory):
+//       GEMM1  Hreg[c & 1] = X . W1[c]^T          epi-h  relu(. + b1) -> fp16 -> H[c & 1] in shared memory
+//       GEMM2  Y += H[c & 1] . W2[:, c]^T
+//   epi-f   out = LN2(Y) -> fp16 hi (+ fp16 lo = out - hi: the residual stream crosses HBM as hi + lo, the operands of
+//           the next GEMMs read hi only) staged in the X / H regions -> TMA stores
+// The MMA warp issues GEMM0 of the NEXT tile right after the last GEMM2, so it overlaps the final epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "kernels.h"
+#include "tc_gemm.h"
+#include "tc_ptx.cuh"
+
+namespace cone {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int ET_THREADS = 320;
+constexpr int ET_D = 256;               // model width (rows of 256 fp16 = 4 k-blocks of 64)
+constexpr int SLOT_BYTES = 16384;       // one [128 x 64] fp16 box, 128-byte swizzle
+constexpr int NSLOT = 5;
+constexpr int XT_BYTES = 4 * SLOT_BYTES;   // X tile [128 x 256] fp16
+constexpr int HB_BYTES = 2 * SLOT_BYTES;   // one hidden chunk [128 x 128] fp16
+constexpr int I64_BYTES = 64 * 128;
+constexpr int OFF_X = 0;
+constexpr int OFF_H = OFF_X + XT_BYTES;
+constexpr int OFF_RING = OFF_H + 2 * HB_BYTES;
+constexpr int OFF_I64 = OFF_RING + NSLOT * SLOT_BYTES;
+constexpr int OFF_BAR = OFF_I64 + I64_BYTES;
+constexpr int N_BAR = 2 * NSLOT + 7;
+constexpr int OFF_LN = OFF_BAR + 8 * 32;           // room for 32 barriers
+constexpr int OFF_SLOT = OFF_LN + 8 * 32 * 8;      // LayerNorm partials [8 warps][32 lanes] float2
+constexpr int ET_SMEM = OFF_SLOT + 64 + 1024;      // + alignment slack
+static_assert(N_BAR <= 32, "barrier area");
+static_assert(ET_SMEM <= 232448, "enc_tail shared memory exceeds 227 KB");
+
+struct EtParams {
+    const float *bo, *ln1_g, *ln1_b, *b1, *b2, *ln2_g, *ln2_b;
+    float eps;
+    float* C32;      // optional fp32 copy of the output rows (saliency head)
+    int64_t ldc32;
+    int64_t M;
+    int nchunk;      // ffn / 128
+    int has_lo_in, has_lo_out;
+};
+
+__device__ __forceinline__ uint32_t et_idesc(int M, int N) {  // D fp32, A / B fp16 K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int CG>
+__global__ void __launch_bounds__(ET_THREADS, 1)
+enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant__ CUtensorMap tmRhi,
+                const __grid_constant__ CUtensorMap tmRlo, const __grid_constant__ CUtensorMap tmWo,
+                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                const __grid_constant__ CUtensorMap tmOhi, const __grid_constant__ CUtensorMap tmOlo, EtParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sX = smem + OFF_X;
+    uint8_t* sH = smem + OFF_H;
+    uint8_t* sRing = smem + OFF_RING;
+    uint8_t* sI = smem + OFF_I64;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* empty = full + NSLOT;
+    uint64_t* g0full = empty + NSLOT;
+    uint64_t* xready = g0full + 1;
+    uint64_t* yfull = xready + 1;
+    uint64_t* hfull = yfull + 1;    // [2]
+    uint64_t* hready = hfull + 2;   // [2]
+    float2* ln_part = reinterpret_cast<float2*>(smem + OFF_LN);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_SLOT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int64_t n_super = (P.M + 128 * CG - 1) / (128 * CG);
+    const int64_t st_begin = blockIdx.x / CG, st_step = gridDim.x / CG;
+    const int nchunk = P.nchunk;
+    const int nres = P.has_lo_in ? 8 : 4;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAtt)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
+        for (int i = 0; i < NSLOT; ++i) {
+            mbar_init(&full[i], CG);  // one arrive.expect_tx per CTA of the pair
+            mbar_init(&empty[i], 1);  // one tcgen05.commit
+        }
+        mbar_init(g0full, 1);
+        mbar_init(yfull, 1);
+        mbar_init(xready, 8 * CG);  // lane 0 of every epilogue warp of the pair
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&hfull[i], 1);
+            mbar_init(&hready[i], 8 * CG);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the whole TMEM: Y (256 columns) + two hidden-chunk accumulators / the GEMM0 accumulator (256)
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    }
+    // identity tile of the residual MMAs: this CTA's 64 / CG rows of I64 (row n holds a single 1.0 at k = n)
+    for (int i = threadIdx.x; i < I64_BYTES / 16; i += ET_THREADS) reinterpret_cast<uint4*>(sI)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < 64 / CG) {
+        const int nl = threadIdx.x, n = (64 / CG) * (int)rank + nl;
+        *reinterpret_cast<__half*>(sI + sw128(nl, n >> 3) + (n & 7) * 2) = __float2half_rn(1.0f);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();  // barrier inits and TMEM allocation of BOTH CTAs before any cross-CTA traffic
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmemY = tmem_base, tmemH = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producer
+            int slot = 0;
+            uint32_t ph = 0;
+            auto emit = [&](const CUtensorMap* map, int c0, int c1, uint32_t bytes) {
+                mbar_wait(&empty[slot], ph ^ 1);
+                if (CG == 1) {
+                    mbar_expect_tx(&full[slot], bytes);
+                    tma_load_2d(sRing + slot * SLOT_BYTES, map, &full[slot], c0, c1);
+                } else {
+                    mbar_expect_tx_leader(&full[slot], bytes);
+                    tma_load_2d_pair(sRing + slot * SLOT_BYTES, map, &full[slot], c0, c1);
+                }
+                if (++slot == NSLOT) {
+                    slot = 0;
+                    ph ^= 1;
+                }
+            };
+            auto emit_gemm0 = [&](int m0) {
+                for (int kb = 0; kb < 4; ++kb) {
+                    emit(&tmAtt, kb * 64, m0, SLOT_BYTES);
+                    if (CG == 1) {
+                        emit(&tmWo, kb * 64, 0, SLOT_BYTES);
+                        emit(&tmWo, kb * 64, 128, SLOT_BYTES);
+                    } else {
+                        emit(&tmWo, kb * 64, 128 * (int)rank, SLOT_BYTES);
+                    }
+                }
+                for (int kb = 0; kb < 4; ++kb) emit(&tmRhi, kb * 64, m0, SLOT_BYTES);
+                if (P.has_lo_in)
+                    for (int kb = 0; kb < 4; ++kb) emit(&tmRlo, kb * 64, m0, SLOT_BYTES);
+            };
+            auto emit_g1 = [&](int c) {
+                for (int kb = 0; kb < 4; ++kb) emit(&tmW1, kb * 64, c * 128 + (128 / CG) * (int)rank, SLOT_BYTES / CG);
+            };
+            auto emit_g2 = [&](int c) {
+                for (int kb = 0; kb < 2; ++kb) {
+                    if (CG == 1) {
+                        emit(&tmW2, c * 128 + kb * 64, 0, SLOT_BYTES);
+                        emit(&tmW2, c * 128 + kb * 64, 128, SLOT_BYTES);
+                    } else {
+                        emit(&tmW2, c * 128 + kb * 64, 128 * (int)rank, SLOT_BYTES);
+                    }
+                }
+            };
+            auto prefetch_rows = [&](int m0) {  // next tile's activation rows -> L2, a whole tile ahead of their TMA loads
+                for (int kb = 0; kb < 4; ++kb) {
+                    tma_prefetch_l2_2d(&tmAtt, kb * 64, m0);
+                    tma_prefetch_l2_2d(&tmRhi, kb * 64, m0);
+                    if (P.has_lo_in) tma_prefetch_l2_2d(&tmRlo, kb * 64, m0);
+                }
+            };
+            if (st_begin < n_super) emit_gemm0((int)((st_begin * CG + rank) * 128));
+            for (int64_t st = st_begin; st < n_super; st += st_step) {
+                const bool has_next = st + st_step < n_super;
+                const int m_next = (int)(((st + st_step) * CG + rank) * 128);
+                if (has_next) prefetch_rows(m_next);
+                emit_g1(0);
+                if (nchunk > 1) emit_g1(1);
+                for (int c = 0; c < nchunk; ++c) {
+                    emit_g2(c);
+                    if (c + 2 < nchunk) emit_g1(c + 2);
+                }
+                if (has_next) emit_gemm0(m_next);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {  // -------------------------------------------------------------------- MMA issuer
+            const uint32_t id256 = et_idesc(128 * CG, 256), id128 = et_idesc(128 * CG, 128), id64 = et_idesc(128 * CG, 64);
+            int slot = 0;
+            uint32_t ph = 0;
+            const uint32_t ring_addr = smem_u32(sRing), x_addr = smem_u32(sX), h_addr = smem_u32(sH), i_addr = smem_u32(sI);
+            auto take = [&]() -> int {  // next ring item has landed (in both CTAs of the pair)
+                mbar_wait(&full[slot], ph);
+                tc_fence_after();
+                const int s = slot;
+                if (++slot == NSLOT) {
+                    slot = 0;
+                    ph ^= 1;
+                }
+                return s;
+            };
+            auto mma = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, uint32_t acc) {
+                if (CG == 1) umma_f16(d, smem_desc_sw128(a_addr), smem_desc_sw128(b_addr), idesc, acc);
+                else umma_f16_pair(d, smem_desc_sw128(a_addr), smem_desc_sw128(b_addr), idesc, acc);
+            };
+            auto commit = [&](uint64_t* bar) {
+                if (CG == 1) umma_commit(bar);
+                else umma_commit_pair(bar);
+            };
+            auto gemm0 = [&]() {
+                for (int kb = 0; kb < 4; ++kb) {
+                    const int ia = take(), ib0 = take(), ib1 = (CG == 1) ? take() : 0;
+                    const uint32_t a = ring_addr + ia * SLOT_BYTES, b0 = ring_addr + ib0 * SLOT_BYTES,
+                                   b1 = ring_addr + ib1 * SLOT_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        if (CG == 1) {
+                            mma(tmemH, a + k * 32, b0 + k * 32, id128, acc);
+                            mma(tmemH + 128, a + k * 32, b1 + k * 32, id128, acc);
+                        } else {
+                            mma(tmemH, a + k * 32, b0 + k * 32, id256, acc);
+                        }
+                    }
+                    commit(&empty[ia]);
+                    commit(&empty[ib0]);
+                    if (CG == 1) commit(&empty[ib1]);
+                }
+                for (int j = 0; j < nres; ++j) {  // + res_hi (+ res_lo): 64 columns at a time against the identity tile
+                    const int ia = take();
+                    const uint32_t a = ring_addr + ia * SLOT_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma(tmemH + 64 * (j & 3), a + k * 32, i_addr + k * 32, id64, 1u);
+                    commit(&empty[ia]);
+                }
+                commit(g0full);
+            };
+            auto gemm1 = [&](int c) {  // hidden chunk c: Hreg[c & 1] = X . W1[c]^T
+                const uint32_t d = tmemH + 128 * (c & 1);
+                for (int kb = 0; kb < 4; ++kb) {
+                    const int ib = take();
+                    const uint32_t b = ring_addr + ib * SLOT_BYTES, a = x_addr + kb * SLOT_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma(d, a + k * 32, b + k * 32, id128, (kb > 0 || k > 0) ? 1u : 0u);
+                    commit(&empty[ib]);
+                }
+                commit(&hfull[c & 1]);
+            };
+            auto gemm2 = [&](int c) {  // Y += H[c & 1] . W2[:, c]^T
+                for (int kb = 0; kb < 2; ++kb) {
+                    const int ib0 = take(), ib1 = (CG == 1) ? take() : 0;
+                    const uint32_t a = h_addr + (c & 1) * HB_BYTES + kb * SLOT_BYTES, b0 = ring_addr + ib0 * SLOT_BYTES,
+                                   b1 = ring_addr + ib1 * SLOT_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (CG == 1) {
+                            mma(tmemY, a + k * 32, b0 + k * 32, id128, 1u);
+                            mma(tmemY + 128, a + k * 32, b1 + k * 32, id128, 1u);
+                        } else {
+                            mma(tmemY, a + k * 32, b0 + k * 32, id256, 1u);
+                        }
+                    }
+                    commit(&empty[ib0]);
+                    if (CG == 1) commit(&empty[ib1]);
+                }
+            };
+            uint32_t p = 0, hrph[2] = {0, 0};
+            if (st_begin < n_super) gemm0();
+            for (int64_t st = st_begin; st < n_super; st += st_step) {
+                if (CG == 1) mbar_wait(xready, p);
+                else mbar_wait_cluster(xready, p);
+                tc_fence_after();
+                gemm1(0);
+                if (nchunk > 1) gemm1(1);
+                for (int c = 0; c < nchunk; ++c) {
+                    const int b = c & 1;
+                    if (CG == 1) mbar_wait(&hready[b], hrph[b]);
+                    else mbar_wait_cluster(&hready[b], hrph[b]);
+                    hrph[b] ^= 1;
+                    tc_fence_after();
+                    gemm2(c);
+                    if (c + 2 < nchunk) gemm1(c + 2);
+                }
+                commit(yfull);
+                if (st + st_step < n_super) gemm0();  // overlaps the final epilogue of this tile
+                p ^= 1;
+            }
+        }
+    } else {  // ------------------------------------------------------------------------------------------ epilogue warps
+        const int ew = warp - 2;       // 0..7
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;      // which 128 of the 256 columns
+        const int partner = ew ^ 4;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t p = 0, hfph[2] = {0, 0};
+        auto arrive = [&](uint64_t* bar) {
+            if (CG == 1) mbar_arrive(bar);
+            else mbar_arrive_leader(bar);
+        };
+        // LayerNorm statistics of this lane's row: 128 columns here, 128 in the partner warp
+        auto row_stats = [&](float s1, float s2, float& mean, float& rstd) {
+            ln_part[ew * 32 + lane] = make_float2(s1, s2);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            const float2 o = ln_part[partner * 32 + lane];
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            s1 += o.x;
+            s2 += o.y;
+            mean = s1 * (1.f / ET_D);
+            rstd = rsqrtf(fmaxf(s2 * (1.f / ET_D) - mean * mean, 0.f) + P.eps);
+        };
+        for (int64_t st = st_begin; st < n_super; st += st_step) {
+            const int m0 = (int)((st * CG + rank) * 128);
+            // ---- epi-0: x = LN1(att.Wo^T + res + bo) -> X tile (fp16), Y (fp32, + b2)
+            mbar_wait(g0full, p);
+            tc_fence_after();
+            if (lane == 0) tma_store_wait_read<0>();  // the staged output of the previous tile has left X / H
+            __syncwarp();
+            {
+                const uint32_t tH = tmemH + lane_base + half * 128, tY = tmemY + lane_base + half * 128;
+                float s1 = 0.f, s2 = 0.f;
+                for (int c = 0; c < 4; ++c) {
+                    float x[32];
+                    tmem_ld_32x32(tH + 32 * c, x);
+                    tmem_ld_wait();
+                    const float4* b4 = reinterpret_cast<const float4*>(P.bo + half * 128 + 32 * c);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = __ldg(b4 + q);
+                        const float v0 = x[4 * q] + b.x, v1 = x[4 * q + 1] + b.y, v2 = x[4 * q + 2] + b.z, v3 = x[4 * q + 3] + b.w;
+                        s1 += (v0 + v1) + (v2 + v3);
+                        s2 = fmaf(v0, v0, s2); s2 = fmaf(v1, v1, s2); s2 = fmaf(v2, v2, s2); s2 = fmaf(v3, v3, s2);
+                    }
+                }
+                float mean, rstd;
+                row_stats(s1, s2, mean, rstd);
+                for (int c = 0; c < 4; ++c) {
+                    float x[32];
+                    tmem_ld_32x32(tH + 32 * c, x);
+                    tmem_ld_wait();
+                    const int col = half * 128 + 32 * c;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bo = __ldg(reinterpret_cast<const float4*>(P.bo + col) + q);
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln1_g + col) + q);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln1_b + col) + q);
+                        x[4 * q] = ((x[4 * q] + bo.x) - mean) * rstd * g.x + b.x;
+                        x[4 * q + 1] = ((x[4 * q + 1] + bo.y) - mean) * rstd * g.y + b.y;
+                        x[4 * q + 2] = ((x[4 * q + 2] + bo.z) - mean) * rstd * g.z + b.z;
+                        x[4 * q + 3] = ((x[4 * q + 3] + bo.w) - mean) * rstd * g.w + b.w;
+                    }
+                    uint8_t* xk = sX + (half * 2 + (c >> 1)) * SLOT_BYTES;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 v;
+                        v.x = pack_h2(x[8 * u], x[8 * u + 1]);
+                        v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
+                        v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
+                        v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
+                        *reinterpret_cast<uint4*>(xk + sw128(row, (c & 1) * 4 + u)) = v;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {  // Y starts as the fp32 residual of the FFN + linear2's bias
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.b2 + col) + q);
+                        x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+                    }
+                    tmem_st_32x32(tY + 32 * c, x);
+                }
+                tmem_st_wait();
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive(xready);
+            }
+            // ---- epi-h: hidden chunks
+            for (int c = 0; c < nchunk; ++c) {
+                const int b = c & 1;
+                mbar_wait(&hfull[b], hfph[b]);
+                hfph[b] ^= 1;
+                tc_fence_after();
+                float x[64];
+                tmem_ld_32x64(tmemH + lane_base + 128 * b + 64 * half, x);
+                tmem_ld_wait();
+                const float4* b4 = reinterpret_cast<const float4*>(P.b1 + c * 128 + half * 64);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float4 bb = __ldg(b4 + q);
+                    x[4 * q] = fmaxf(x[4 * q] + bb.x, 0.f);
+                    x[4 * q + 1] = fmaxf(x[4 * q + 1] + bb.y, 0.f);
+                    x[4 * q + 2] = fmaxf(x[4 * q + 2] + bb.z, 0.f);
+                    x[4 * q + 3] = fmaxf(x[4 * q + 3] + bb.w, 0.f);
+                }
+                uint8_t* hk = sH + b * HB_BYTES + half * SLOT_BYTES;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint4 v;
+                    v.x = pack_h2(x[8 * u], x[8 * u + 1]);
+                    v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
+                    v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
+                    v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
+                    *reinterpret_cast<uint4*>(hk + sw128(row, u)) = v;
+                }
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive(&hready[b]);
+            }
+            // ---- epi-f: out = LN2(Y) -> hi (+ lo) staged in X / H -> TMA stores
+            mbar_wait(yfull, p);
+            tc_fence_after();
+            {
+                const uint32_t tY = tmemY + lane_base + half * 128;
+                float s1 = 0.f, s2 = 0.f;
+                for (int c = 0; c < 4; ++c) {
+                    float x[32];
+                    tmem_ld_32x32(tY + 32 * c, x);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        s1 += (x[j] + x[j + 1]) + (x[j + 2] + x[j + 3]);
+                        s2 = fmaf(x[j], x[j], s2); s2 = fmaf(x[j + 1], x[j + 1], s2);
+                        s2 = fmaf(x[j + 2], x[j + 2], s2); s2 = fmaf(x[j + 3], x[j + 3], s2);
+                    }
+                }
+                float mean, rstd;
+                row_stats(s1, s2, mean, rstd);
+                const int64_t grow = (int64_t)m0 + row;
+                for (int c = 0; c < 4; ++c) {
+                    float x[32];
+                    tmem_ld_32x32(tY + 32 * c, x);
+                    tmem_ld_wait();
+                    const int col = half * 128 + 32 * c;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln2_g + col) + q);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln2_b + col) + q);
+                        x[4 * q] = (x[4 * q] - mean) * rstd * g.x + b.x;
+                        x[4 * q + 1] = (x[4 * q + 1] - mean) * rstd * g.y + b.y;
+                        x[4 * q + 2] = (x[4 * q + 2] - mean) * rstd * g.z + b.z;
+                        x[4 * q + 3] = (x[4 * q + 3] - mean) * rstd * g.w + b.w;
+                    }
+                    if (P.C32 != nullptr && grow < P.M) {
+                        float4* o4 = reinterpret_cast<float4*>(P.C32 + grow * P.ldc32 + col);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o4[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                    }
+                    const uint32_t off = (uint32_t)(half * 2 + (c >> 1)) * SLOT_BYTES;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float lo[8];
+                        uint4 v;
+                        uint32_t* vw = &v.x;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __half2 h = __floats2half2_rn(x[8 * u + 2 * e], x[8 * u + 2 * e + 1]);
+                            const float2 f = __half22float2(h);
+                            lo[2 * e] = x[8 * u + 2 * e] - f.x;
+                            lo[2 * e + 1] = x[8 * u + 2 * e + 1] - f.y;
+                            vw[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(sX + off + sw128(row, (c & 1) * 4 + u)) = v;
+                        if (P.has_lo_out) {
+                            uint4 w;
+                            w.x = pack_h2(lo[0], lo[1]);
+                            w.y = pack_h2(lo[2], lo[3]);
+                            w.z = pack_h2(lo[4], lo[5]);
+                            w.w = pack_h2(lo[6], lo[7]);
+                            *reinterpret_cast<uint4*>(sH + off + sw128(row, (c & 1) * 4 + u)) = w;
+                        }
+                    }
+                }
+                tc_fence_before();  // all reads of Y by this warp precede its next writes (epi-0 of the next tile)
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    for (int kbi = 0; kbi < 2; ++kbi) {
+                        const int kblock = half * 2 + kbi;
+                        const uint32_t off = (uint32_t)kblock * SLOT_BYTES + (uint32_t)quarter * 4096u;
+                        tma_store_2d(&tmOhi, sX + off, kblock * 64, m0 + quarter * 32);
+                        if (P.has_lo_out) tma_store_2d(&tmOlo, sH + off, kblock * 64, m0 + quarter * 32);
+                    }
+                    tma_store_commit();
+                }
+            }
+            p ^= 1;
+        }
+        if (lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last bulk stores
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's MMAs read this CTA's shared memory, its commits arrive here
+    if (warp == 1) {
+        tc_fence_after();
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+int enc_tail_supported(int d, int ffn) { return d == ET_D && ffn >= 128 && (ffn % 128) == 0; }
+
+int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
+    CONE_REQUIRE(t != nullptr, "enc_tail: tensor-core weights not initialised");
+    CONE_REQUIRE(enc_tail_supported(a.d, a.ffn), "enc_tail: unsupported width d=%d ffn=%d", a.d, a.ffn);
+    CONE_REQUIRE(a.M >= 1 && a.M < ((int64_t)1 << 31) - 512, "enc_tail: bad row count %lld", (long long)a.M);
+    CONE_REQUIRE(a.att16 && a.res_hi && a.out_hi, "enc_tail: null argument");
+    CONE_REQUIRE((a.lda % 8) == 0 && (a.ldr % 8) == 0 && (a.ldo % 8) == 0, "enc_tail: row pitches must be multiples of 8");
+    int cg = a.cta_group;
+    if (cg == 0) {
+        static int env_cg = -1;
+        if (env_cg < 0) {
+            const char* e = getenv("CONE_ENC_TAIL_CG");
+            env_cg = (e && e[0] == '1') ? 1 : 2;
+        }
+        cg = env_cg;
+    }
+    CONE_REQUIRE(cg == 1 || cg == 2, "enc_tail: cta_group must be 1 or 2");
+    const uint16_t *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    CONE_TRY(tc_weight_f16(t, a.Wo, a.d, a.d, s, &wo));
+    CONE_TRY(tc_weight_f16(t, a.W1, a.ffn, a.d, s, &w1));
+    CONE_TRY(tc_weight_f16(t, a.W2, a.d, a.ffn, s, &w2));
+    CUtensorMap mAtt, mRhi, mRlo, mWo, mW1, mW2, mOhi, mOlo;
+    CONE_TRY(tc_make_map(&mAtt, a.att16, false, a.M, a.d, a.lda, 64, 128));
+    CONE_TRY(tc_make_map(&mRhi, a.res_hi, false, a.M, a.d, a.ldr, 64, 128));
+    mRlo = mRhi;
+    if (a.res_lo) CONE_TRY(tc_make_map(&mRlo, a.res_lo, false, a.M, a.d, a.ldr, 64, 128));
+    CONE_TRY(tc_make_map(&mWo, wo, false, a.d, a.d, a.d, 64, 128));
+    CONE_TRY(tc_make_map(&mW1, w1, false, a.ffn, a.d, a.d, 64, 128 / cg));
+    CONE_TRY(tc_make_map(&mW2, w2, false, a.d, a.ffn, a.ffn, 64, 128));
+    CONE_TRY(tc_make_map(&mOhi, a.out_hi, false, a.M, a.d, a.ldo, 64, 32));
+    mOlo = mOhi;
+    if (a.out_lo) CONE_TRY(tc_make_map(&mOlo, a.out_lo, false, a.M, a.d, a.ldo, 64, 32));
+    EtParams P{};
+    P.bo = a.bo; P.ln1_g = a.ln1_g; P.ln1_b = a.ln1_b; P.b1 = a.b1; P.b2 = a.b2; P.ln2_g = a.ln2_g; P.ln2_b = a.ln2_b;
+    P.eps = 1e-5f;
+    P.C32 = a.C32; P.ldc32 = a.ldc32;
+    P.M = a.M;
+    P.nchunk = a.ffn / 128;
+    P.has_lo_in = a.res_lo != nullptr;
+    P.has_lo_out = a.out_lo != nullptr;
+    const int num_sms = tc_num_sms(t);
+    const int64_t n_super = cdiv64(a.M, 128 * cg);
+    int64_t clusters = num_sms / cg;
+    if (clusters > n_super) clusters = n_super;
+    const unsigned grid = (unsigned)(clusters * cg);
+    const double m = (double)a.M;
+    ProfScope ps(s, P_GEMM_TC, 2.0 * m * ((double)a.d * a.d + 2.0 * a.d * a.ffn),
+                 2.0 * m * a.d * (2.0 + (a.res_lo ? 1.0 : 0.0) + 1.0 + (a.out_lo ? 1.0 : 0.0)) + (a.C32 ? 4.0 * m * a.d : 0.0));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(ET_THREADS);
+    cfg.dynamicSmemBytes = ET_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cg == 1) {
+        static bool set1 = false;
+        if (!set1) {
+            CONE_CUDA(cudaFuncSetAttribute(enc_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ET_SMEM));
+            set1 = true;
+        }
+        CONE_CUDA(cudaLaunchKernelEx(&cfg, enc_tail_kernel<1>, mAtt, mRhi, mRlo, mWo, mW1, mW2, mOhi, mOlo, P));
+    } else {
+        static bool set2 = false;
+        if (!set2) {
+            CONE_CUDA(cudaFuncSetAttribute(enc_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ET_SMEM));
+            set2 = true;
+        }
+        CONE_CUDA(cudaLaunchKernelEx(&cfg, enc_tail_kernel<2>, mAtt, mRhi, mRlo, mWo, mW1, mW2, mOhi, mOlo, P));
+    }
+    CONE_LAUNCH_CHECK("enc_tail");
+    return CONE_OK;
+}
+
+}  // namespace cone

@@ -45,7 +45,11 @@ int gather_window_rows(const float* vidproj, int64_t n_vid_rows, const int64_t* 
 int add_pos_rows(const float* src, const float* pos_table, const int32_t* vlen, float* out, int64_t B, int Lv, int Lt,
                  int d, int table_lv, cudaStream_t s);
 int gather_window_rows_f16(const float* vidproj, int64_t n_vid_rows, const int64_t* vid_base, const float* txtproj,
-                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s);
+                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s,
+                           uint16_t* src16lo = nullptr);  // src16lo (nullable): fp16(value - fp16(value))
+// hi = fp16(x), lo = fp16(x - hi) (lo nullable) over n contiguous elements; and out = hi + lo
+int split_hilo_rows(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, cudaStream_t s);
+int combine_hilo_rows(const uint16_t* hi, const uint16_t* lo, float* out, int64_t n, cudaStream_t s);
 // same gather from fp16 source rows (bit-identical to rounding the fp32 rows)
 int gather_window_rows_h2h(const uint16_t* vid16, int64_t n_vid_rows, const int64_t* vid_base, const uint16_t* txt16,
                            const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s);

@@ -181,8 +181,8 @@ __global__ void add_pos_rows_f16_kernel(const float* __restrict__ src, const flo
 // gather straight into the fp16 operand of the first encoder layer: src16 = fp16(projected row)
 __global__ void gather_window_rows_f16_kernel(const float* __restrict__ vidproj, int64_t n_vid_rows,
                                               const int64_t* __restrict__ vid_base, const float* __restrict__ txtproj,
-                                              const int64_t* __restrict__ txt_base, __half* __restrict__ src16, int64_t B,
-                                              int Lv, int Lt, int d4) {
+                                              const int64_t* __restrict__ txt_base, __half* __restrict__ src16,
+                                              __half* __restrict__ src16lo, int64_t B, int Lv, int Lt, int d4) {
     const int S = Lv + Lt;
     const int64_t total = B * S * d4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -203,6 +203,44 @@ __global__ void gather_window_rows_f16_kernel(const float* __restrict__ vidproj,
         u.x = *reinterpret_cast<uint32_t*>(&h0);
         u.y = *reinterpret_cast<uint32_t*>(&h1);
         reinterpret_cast<uint2*>(src16)[i] = u;
+        if (src16lo) {  // lo = fp16(value - hi): the residual stream crosses HBM as hi + lo (enc_tail.cu)
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+            u.x = *reinterpret_cast<uint32_t*>(&l0);
+            u.y = *reinterpret_cast<uint32_t*>(&l1);
+            reinterpret_cast<uint2*>(src16lo)[i] = u;
+        }
+    }
+}
+
+// x fp32 -> hi = fp16(x), lo = fp16(x - hi); and back
+__global__ void split_hilo_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(hi)[i] = u;
+        if (lo) {
+            u.x = *reinterpret_cast<uint32_t*>(&l0);
+            u.y = *reinterpret_cast<uint32_t*>(&l1);
+            reinterpret_cast<uint2*>(lo)[i] = u;
+        }
+    }
+}
+__global__ void combine_hilo_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out,
+                                    int64_t n2) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        float2 a = __half22float2(reinterpret_cast<const __half2*>(hi)[i]);
+        if (lo) {
+            const float2 b = __half22float2(reinterpret_cast<const __half2*>(lo)[i]);
+            a.x += b.x;
+            a.y += b.y;
+        }
+        reinterpret_cast<float2*>(out)[i] = a;
     }
 }
 
@@ -338,12 +376,33 @@ int add_pos_rows_f16(const float* src, const float* pos_table, const int32_t* vl
 }
 
 int gather_window_rows_f16(const float* vidproj, int64_t n_vid_rows, const int64_t* vid_base, const float* txtproj,
-                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s) {
+                           const int64_t* txt_base, uint16_t* src16, int64_t B, int Lv, int Lt, int d, cudaStream_t s,
+                           uint16_t* src16lo) {
     if (B == 0) return CONE_OK;
-    ProfScope ps(s, P_ROWOPS, 0.0, 6.0 * (double)B * (Lv + Lt) * d);
+    ProfScope ps(s, P_ROWOPS, 0.0, (src16lo ? 8.0 : 6.0) * (double)B * (Lv + Lt) * d);
     gather_window_rows_f16_kernel<<<grid_for(B * (Lv + Lt) * (d / 4), 256), 256, 0, s>>>(
-        vidproj, n_vid_rows, vid_base, txtproj, txt_base, reinterpret_cast<__half*>(src16), B, Lv, Lt, d / 4);
+        vidproj, n_vid_rows, vid_base, txtproj, txt_base, reinterpret_cast<__half*>(src16),
+        reinterpret_cast<__half*>(src16lo), B, Lv, Lt, d / 4);
     CONE_LAUNCH_CHECK("gather_window_rows_f16");
+    return CONE_OK;
+}
+
+int split_hilo_rows(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, cudaStream_t s) {
+    if (n == 0) return CONE_OK;
+    CONE_REQUIRE((n & 3) == 0, "split_hilo_rows: element count must be a multiple of 4");
+    ProfScope ps(s, P_CONVERT, 0.0, 8.0 * (double)n);
+    split_hilo_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(x, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), n / 4);
+    CONE_LAUNCH_CHECK("split_hilo");
+    return CONE_OK;
+}
+
+int combine_hilo_rows(const uint16_t* hi, const uint16_t* lo, float* out, int64_t n, cudaStream_t s) {
+    if (n == 0) return CONE_OK;
+    CONE_REQUIRE((n & 1) == 0, "combine_hilo_rows: element count must be even");
+    ProfScope ps(s, P_CONVERT, 0.0, 8.0 * (double)n);
+    combine_hilo_kernel<<<grid_for(n / 2, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(hi),
+                                                            reinterpret_cast<const __half*>(lo), out, n / 2);
+    CONE_LAUNCH_CHECK("combine_hilo");
     return CONE_OK;
 }
 

@@ -26,8 +26,11 @@
 
 #include "kernels.h"
 #include "tc_gemm.h"
+#include "tc_ptx.cuh"
 
 namespace cone {
+
+using namespace ptx;
 
 namespace {
 
@@ -38,124 +41,6 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int TC_THREADS = 320;  // producer warp + MMA warp + 8 epilogue warps
 constexpr int BOX_BYTES = 32 * 128;   // one epilogue box: 32 rows x 128 bytes (64 fp16 or 32 fp32 columns)
-
-// ---------------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LAB_DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "LAB_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 bytes, 8-row atoms 1024 bytes apart
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset: next 8-row atom
-    d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
-    return d;
-}
-// 32 lanes x 32 columns of fp32 accumulators: thread i of the warp gets TMEM lane (base + i), 32 consecutive columns
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-// 32 lanes x 64 columns
-__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
-          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
-          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
-          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
-          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct TcEpilogue {
     const float* bias;   // [N] or null
@@ -169,14 +54,6 @@ struct TcEpilogue {
     const float* ln_b;
     float ln_eps;
 };
-
-// Byte offset of 16-byte unit `u` of row `r` in a [rows x 128 B] box with the TMA 128-byte swizzle.
-__device__ __forceinline__ uint32_t sw128(int r, int u) { return (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)); }
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
 
 __device__ __forceinline__ void add_bias64(float* x, const float* bias) {
 #pragma unroll
@@ -237,7 +114,7 @@ template <int BN, bool WRES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC16,
-               const __grid_constant__ CUtensorMap tmC32, TcEpilogue ep, int64_t M, int N, int K) {
+               const __grid_constant__ CUtensorMap tmC32, TcEpilogue ep, int64_t M, int N, int K, int a_wrap) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int HALF = BN / 2;  // columns per epilogue warp
     constexpr bool FAST = MODE == EPI_PLAIN16;
@@ -315,7 +192,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], WRES ? A_BYTES : A_BYTES + B_BYTES);
-                    tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], kb * BK, m0);
+                    tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], (kb * BK) % a_wrap, m0);  // a_wrap < K: A read twice
                     if (!WRES) tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], kb * BK, n0);
                     if (++stage == NSTAGE) {
                         stage = 0;
@@ -803,9 +680,25 @@ int tc_weights_refresh(TcWeights* t, cudaStream_t s) {
     return CONE_OK;
 }
 
+int tc_weight_f16(TcWeights* t, const float* W, int N, int K, cudaStream_t s, const uint16_t** out) {
+    CONE_REQUIRE(t != nullptr, "tc_weight_f16: tensor-core weights not initialised");
+    const TcWeights::W16* w = nullptr;
+    CONE_TRY(get_w16(t, W, N, K, 0, s, &w));
+    *out = reinterpret_cast<const uint16_t*>(w->ptr);
+    return CONE_OK;
+}
+
+int tc_make_map(CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                int box_rows) {
+    return make_map(map, base, f32, rows, cols, ld, box_cols, box_rows);
+}
+
+int tc_num_sms(const TcWeights* t) { return t ? t->num_sms : kNumSMs; }
+
 int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     CONE_REQUIRE(t != nullptr, "tc_gemm: tensor-core weights not initialised");
-    const int K16 = g.split3 ? 3 * g.K : g.K;  // columns of the fp16 operands
+    CONE_REQUIRE(!(g.split3 && g.wsplit), "tc_gemm: split3 and wsplit are exclusive");
+    const int K16 = g.split3 ? 3 * g.K : (g.wsplit ? 2 * g.K : g.K);  // contraction length on the tensor pipe
     CONE_REQUIRE(tc_gemm_supported(g.M, g.N, K16), "tc_gemm: unsupported shape M=%lld N=%d K=%d", (long long)g.M, g.N, K16);
     CONE_REQUIRE(g.M < (int64_t)1 << 31, "tc_gemm: more than 2^31 rows");
     CONE_REQUIRE((g.lda % 8) == 0 && (reinterpret_cast<uintptr_t>(g.A16) & 15) == 0, "tc_gemm: A must be 16-byte aligned");
@@ -814,12 +707,12 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     CONE_REQUIRE(g.R16 == nullptr || ((g.ldr16 % 8) == 0 && (reinterpret_cast<uintptr_t>(g.R16) & 15) == 0), "tc_gemm: R16 alignment");
     CONE_REQUIRE(g.R32 == nullptr || ((g.ldr32 % 4) == 0 && (reinterpret_cast<uintptr_t>(g.R32) & 15) == 0), "tc_gemm: R32 alignment");
     const TcWeights::W16* w = nullptr;
-    CONE_TRY(get_w16(t, g.W, g.N, g.K, g.split3, s, &w));
+    CONE_TRY(get_w16(t, g.W, g.N, g.K, g.split3 || g.wsplit, s, &w));
     CONE_REQUIRE(g.ln_g == nullptr || g.N == w->BN, "tc_gemm: fused LayerNorm needs the whole row in one tile (N=%d)", g.N);
     CONE_REQUIRE(!(g.C16 && g.C32 && g.R16 && g.ln_g == nullptr),
                  "tc_gemm: fp16 + fp32 outputs with an fp16 residual need the LayerNorm epilogue");
     CUtensorMap mapA, mapR, mapC16, mapC32;
-    CONE_TRY(make_map(&mapA, g.A16, false, g.M, K16, g.lda, BK, BM));
+    CONE_TRY(make_map(&mapA, g.A16, false, g.M, g.wsplit ? g.K : K16, g.lda, BK, BM));
     mapR = mapA;
     mapC16 = mapA;
     mapC32 = mapA;  // placeholders when unused (never dereferenced)
@@ -841,14 +734,16 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
     const int n_tiles = g.N / w->BN;
     const int64_t tiles = m_tiles * n_tiles;
     // weights-resident variant: K = 256, BN = 256, at most num_sms / n_tiles CTAs per n-tile
-    const bool wres = w->BN == 256 && K16 == WRES_KBLOCKS * BK && n_tiles <= t->num_sms && !(g.C16 && g.C32);
+    const bool wres = w->BN == 256 && K16 == WRES_KBLOCKS * BK && n_tiles <= t->num_sms && !(g.C16 && g.C32) && !g.wsplit;
+    const int a_wrap = g.wsplit ? g.K : K16;
     unsigned grid = (unsigned)(tiles < t->num_sms ? tiles : t->num_sms);
     if (wres) {
         const int64_t per_n = t->num_sms / n_tiles;
         grid = (unsigned)((m_tiles < per_n ? m_tiles : per_n) * n_tiles);
     }
     const double mn = (double)g.M * g.N;
-    ProfScope ps(s, P_GEMM_TC, 2.0 * mn * K16,
+    // FLOPs are the ALGORITHMIC count (2 M N K of the fp32 problem): the split GEMMs execute 2-3x that on the tensor pipe
+    ProfScope ps(s, P_GEMM_TC, 2.0 * mn * g.K,
                  2.0 * ((double)g.M * K16 + (double)g.N * K16) + (g.C32 ? 4.0 : 0.0) * mn + (g.C16 ? 2.0 : 0.0) * mn +
                      (g.R32 ? 4.0 : 0.0) * mn + (g.R16 ? 2.0 : 0.0) * mn);
 #define CONE_TC_LAUNCH(BNV, WR, MD)                                                                                 \
@@ -860,7 +755,7 @@ int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s) {
             attr = true;                                                                                                \
         }                                                                                                               \
         tc_gemm_kernel<BNV, WR, MD><<<grid, TC_THREADS, tc_smem_bytes<BNV, WR, MD>(), s>>>(                             \
-            mapA, w->map, mapR, mapC16, mapC32, ep, g.M, g.N, K16);                                                     \
+            mapA, w->map, mapR, mapC16, mapC32, ep, g.M, g.N, K16, a_wrap);                                                     \
     } while (0)
     const bool plain16 = w->BN == 256 && g.C16 && !g.C32 && !g.R16 && !g.R32 && !g.ln_g && g.bias;
     const bool ln16 = w->BN == 256 && g.C16 && !g.C32 && g.R16 && !g.R32 && g.ln_g && g.bias && !g.relu;

@@ -1,5 +1,7 @@
 // Tensor-core (tcgen05 + TMA + TMEM) GEMM path, CONE_PREC_TC.  See tc_gemm.cu.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace cone {
@@ -40,8 +42,42 @@ struct TcGemmArgs {
     // 3-product GEMM with fp32-class accuracy: A16 holds [hi | hi | lo] rows of 3 K columns (split3_f16_rows), the
     // cached weight copy is [hi | lo | hi]; K stays the fp32 K
     int split3 = 0;
+    // 2-product GEMM for an operand that only exists in fp16 (the attention-pooled memory): A16 holds K columns and is
+    // read twice against the first two thirds [hi | lo] of the split weight copy — the weights keep fp32-class accuracy
+    int wsplit = 0;
 };
 int tc_gemm_run(TcWeights* t, const TcGemmArgs& g, cudaStream_t s);
+
+// ---- shared with enc_tail.cu
+// fp16 copy [N, K] of an fp32 nn.Linear weight, cached in (and owned by) the handle
+int tc_weight_f16(TcWeights* t, const float* W, int N, int K, cudaStream_t s, const uint16_t** out);
+// 2-D tensor map of a row-major [rows, cols] tensor with row pitch ld (elements); box = [box_cols x box_rows] with a
+// 128-byte inner extent, 128-byte swizzle
+int tc_make_map(CUtensorMap* map, const void* base, bool f32, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                int box_rows);
+int tc_num_sms(const TcWeights* t);
+
+// Fused encoder-layer tail (enc_tail.cu): out = LN2(x + FFN(x)), x = LN1(res + att . Wo^T + bo), rows of d = 256.
+// The residual stream is fp16 hi (+ optional fp16 lo = value - hi); out_hi / out_lo may alias res_hi / res_lo.
+struct EncTailArgs {
+    const uint16_t* att16 = nullptr;   // [M, d] attention output
+    int64_t lda = 0;
+    const uint16_t* res_hi = nullptr;  // [M, d]
+    const uint16_t* res_lo = nullptr;  // nullable
+    int64_t ldr = 0;
+    uint16_t* out_hi = nullptr;
+    uint16_t* out_lo = nullptr;        // nullable
+    int64_t ldo = 0;
+    float* C32 = nullptr;              // nullable fp32 copy of the output
+    int64_t ldc32 = 0;
+    int64_t M = 0;
+    int d = 0, ffn = 0;
+    const float *Wo = nullptr, *bo = nullptr, *ln1_g = nullptr, *ln1_b = nullptr;
+    const float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    int cta_group = 0;                 // 1 or 2; 0 = default (2, or env CONE_ENC_TAIL_CG)
+};
+int enc_tail_supported(int d, int ffn);
+int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s);
 
 // y[rows, 3 K] (fp16, dense) = [hi | hi | lo] with hi = fp16(x), lo = fp16(x - hi)
 int split3_f16_rows(const float* x, int64_t ldx, uint16_t* y, int64_t rows, int K, cudaStream_t s);

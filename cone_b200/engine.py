@@ -201,6 +201,17 @@ class ConeEngine:
         _lib.check(self.lib.cone_l2_normalize(_ptr(x), _ptr(out), rows, x.shape[-1], eps, _stream()), "cone_l2_normalize")
         return out
 
+    def encoder_tail(self, layer: int, att: torch.Tensor, res: torch.Tensor, cta_group: int = 0) -> torch.Tensor:
+        """norm2(x + FFN(x)), x = norm1(res + out_proj(att)) of encoder layer `layer` (cone/transformer.py:239-245) on
+        [M, 256] fp32 rows through the fused tensor-core kernel."""
+        att, res = _need(att, torch.float32, "att"), _need(res, torch.float32, "res")
+        out = torch.empty_like(res)
+        M = att.shape[0]
+        ws, n = self._wsargs(10 * M * att.shape[1] + (1 << 20))
+        _lib.check(self.lib.cone_encoder_tail(self._handle, layer, _ptr(att), _ptr(res), M, _ptr(out), cta_group, ws, n,
+                                              _stream()), "cone_encoder_tail")
+        return out
+
     def adapter(self, x: torch.Tensor, residual: bool = False, precision: Optional[str] = None) -> torch.Tensor:
         """`model.adapter_layer(x)` (cone/model.py:80); `residual=True` gives `adapter_layer(x) + x`."""
         x = _need(x, torch.float32, "x")

@@ -107,6 +107,16 @@ int cone_linear(const cone_weights* w, const float* x, const float* W, const flo
                 int32_t K, int relu, const float* residual, float* y, void* workspace, size_t workspace_bytes,
                 int precision, void* stream);
 
+/* Tail of one encoder layer as the tensor-core mode runs it (cone/transformer.py:239-245):
+ *     x   = norm1(res + out_proj(att))            out = norm2(x + linear2(relu(linear1(x))))
+ * for encoder layer `layer` of the handle, on M rows of width 256: ONE fused tcgen05 kernel (csrc/enc_tail.cu).
+ * Operator-level parity surface: att / res / out are fp32 [M, 256] device arrays here (att is rounded to fp16 as
+ * the attention kernel's output is, res travels as fp16 hi + lo); inside cone_ground_windows / cone_forward the
+ * same kernel runs directly on the fp16 streams.  cta_group: 1, 2 (tcgen05 CTA pair) or 0 = default.
+ * workspace >= 10 * M * 256 bytes. */
+int cone_encoder_tail(const cone_weights* w, int32_t layer, const float* att, const float* res, int64_t M, float* out,
+                      int32_t cta_group, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- A3  stage 1 (cone/inference.py:276-299).
  * Frame scores `einsum('db,b->d')` (inference.py:284) for all queries of a set of videos in one
  * grouped GEMM: queries must be grouped by video.  ctx [n_frames_total, Dv]; video_offsets

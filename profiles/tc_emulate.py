@@ -172,12 +172,12 @@ def batches(sd, cfg, ds):
     return out
 
 
-def run(configs, seeds=((21, 33), (5, 7), (9, 11)), cfg=None):
+def run(configs, seeds=((21, 33), (5, 7), (9, 11)), cfg=None, mad=False):
     cfg = cfg or EGO4D.replace(eval_bsz=8)
     cases = []
     for ws, dsd in seeds:
         sd = init_state_dict(cfg, ws)
-        ds = make_dataset(cfg, 4, [900, 455, 91, 1300], 4, seed=dsd)
+        ds = make_dataset(cfg, 1, [45000], 64, seed=dsd) if mad else make_dataset(cfg, 4, [900, 455, 91, 1300], 4, seed=dsd)
         bt = batches(sd, cfg, ds)
         with torch.no_grad():
             ref = [Emu(sd, cfg, set()).forward(*b) for b in bt]
@@ -200,13 +200,13 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     RES = {"ln1_res", "ln2_res", "src_res"}
     DEC = {"w_dec", "d_op", "d_qkv"}
+    DECX = {"w_dec", "w_decx", "d_op", "d_qkv"}
     cf = [("all fp16 (current pipeline)", ALL, ()),
           ("fp32 residuals", ALL - RES, ()),
-          ("res + dec weights split", ALL - RES - {"w_dec", "w_decx"}, ()),
           ("res + dec weights + d_op", ALL - RES - {"w_dec", "w_decx", "d_op"}, ()),
-          ("res + dec weights + d_op + d_qkv", ALL - RES - {"w_dec", "w_decx", "d_op", "d_qkv"}, ()),
-          ("res + all enc/dec weights split", ALL - RES - {"w_dec", "w_decx", "w_enc", "w_ffn"}, ()),
-          ("dec weights split only", ALL - {"w_dec", "w_decx"}, ()),
+          ("res + dec w/op/qkv", ALL - RES - DECX, ()),
+          ("res + dec w/op/qkv + qx + pm", ALL - RES - DECX - {"d_qx", "d_pm"}, ()),
+          ("enc only, fp32 res", ALL - RES - DEC - {"w_decx", "d_qx", "d_pm", "d_p", "mem"}, ()),
           ]
     if len(sys.argv) > 1 and sys.argv[1] == "ablate":
         cf = [("all fp16 (current pipeline)", ALL, ())]
@@ -214,4 +214,7 @@ if __name__ == "__main__":
             cf.append((f"all but {k}", ALL - {k}, ()))
         for k in sorted(ALL):
             cf.append((f"only {k}", {k}, ()))
-    run(cf)
+    if len(sys.argv) > 1 and sys.argv[1] == "mad":
+        run(cf, seeds=((5, 11),), cfg=MAD768, mad=True)
+    else:
+        run(cf)

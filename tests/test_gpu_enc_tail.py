@@ -1,0 +1,71 @@
+"""The fused encoder-layer tail (csrc/enc_tail.cu: out_proj + norm1 + linear1 + relu + linear2 + norm2 in one tcgen05
+kernel, `cone/transformer.py:239-245`) against plain PyTorch references of the same op:
+  * an fp64 evaluation with the kernel's operand roundings emulated (fp16 attention output, fp16 weights, fp16 copy of
+    the norm1 output as linear1's operand, fp16 hidden) -> only accumulation order differs: 3e-4 absolute on O(1) rows;
+  * the exact fp64 op -> the fp16-operand error class (1e-2 on O(1) rows, rms far below).
+Both tcgen05 forms are covered: cta_group 1 and the CTA pair (cta_group 2, M = 256 per MMA)."""
+import numpy as np
+import pytest
+import torch
+
+from cone_b200.config import EGO4D
+from cone_b200.engine import ConeEngine
+from cone_b200.weights import init_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def h(x):
+    return x.half().double()
+
+
+def reference(sd, layer, att, res, emulate):
+    p = f"transformer.encoder.layers.{layer}"
+    W = lambda k: (h(sd[k]) if emulate else sd[k].double())
+    F = torch.nn.functional
+    a = h(att) if emulate else att.double()
+    x = a @ W(p + ".self_attn.out_proj.weight").t() + sd[p + ".self_attn.out_proj.bias"].double() + res.double()
+    x = F.layer_norm(x, (256,), sd[p + ".norm1.weight"].double(), sd[p + ".norm1.bias"].double(), 1e-5)
+    xo = h(x.float()) if emulate else x
+    hid = torch.relu(xo @ W(p + ".linear1.weight").t() + sd[p + ".linear1.bias"].double())
+    if emulate:
+        hid = h(hid.float())
+    y = hid @ W(p + ".linear2.weight").t() + sd[p + ".linear2.bias"].double() + x
+    return F.layer_norm(y, (256,), sd[p + ".norm2.weight"].double(), sd[p + ".norm2.bias"].double(), 1e-5)
+
+
+def run_case(eng, sd, M, cg, layer=1, seed=0):
+    g = torch.Generator().manual_seed(1000 * seed + M)
+    att = torch.randn(M, 256, generator=g) * 0.7
+    res = torch.randn(M, 256, generator=g) * 1.3
+    got = eng.encoder_tail(layer, att.to(DEV), res.to(DEV), cta_group=cg).cpu().double()
+    e_emu = (got - reference(sd, layer, att, res, True)).abs()
+    e_exact = (got - reference(sd, layer, att, res, False)).abs()
+    return float(e_emu.max()), float(e_exact.max()), float(e_exact.pow(2).mean().sqrt())
+
+
+@pytest.fixture(scope="module")
+def eng_sd():
+    sd = init_state_dict(EGO4D, 7)
+    return ConeEngine(EGO4D, sd, device=DEV, precision="tc", workspace_bytes=1 << 30), {k: v.cpu() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M", [1, 100, 128, 129, 257, 5000, 128 * 148 * 2 + 77])
+def test_encoder_tail_vs_torch(eng_sd, M, cg):
+    eng, sd = eng_sd
+    emu, exact, rms = run_case(eng, sd, M, cg, layer=M % 2)
+    assert emu <= 3e-4, (M, cg, emu)
+    assert exact <= 1e-2 and rms <= 1.5e-3, (M, cg, exact, rms)
+
+
+def test_encoder_tail_pair_equals_single_cta(eng_sd):
+    """cta_group 1 and 2 run the same MMAs in the same order on the same operands: bit-identical outputs."""
+    eng, sd = eng_sd
+    g = torch.Generator().manual_seed(5)
+    att, res = torch.randn(3000, 256, generator=g).to(DEV), torch.randn(3000, 256, generator=g).to(DEV)
+    a = eng.encoder_tail(0, att, res, cta_group=1)
+    b = eng.encoder_tail(0, att, res, cta_group=2)
+    assert torch.equal(a, b)
+    assert torch.equal(a, eng.encoder_tail(0, att, res, cta_group=2))  # and deterministic

@@ -12,7 +12,7 @@ from cone_b200.inference import ground_dataset, output_to_host, run_step, stage_
 from cone_b200.synth import make_dataset
 from cone_b200.weights import init_state_dict
 from oracle import cone_oracle as O
-from helpers import FP32_TOL, assert_close
+from helpers import FP32_TOL, TC_TOL, Hatch, assert_close, oracle_window_scores, ranklist_near_tie
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -68,24 +68,37 @@ def test_mad768_full_step_properties_and_oracle_subsample():
     # oracle on 6 of the 640 queries (same movie, same weights)
     sub = ds.queries[:3] + ds.queries[-3:]
     ora = O.eval_pipeline(sd, cfg, ds.videos, sub)
-    n_ok = 0
+    hatch = Hatch("mad768_full_step", "top-k window list differs from the oracle (near-tie audited)", 0)
     for q in sub:
         r, o = res[q.query_id], ora[q.query_id]
         if r["ranklist"][: cfg.topk_window] != o["ranklist"][: cfg.topk_window]:
-            continue  # near-tie between different frames at the top-k boundary (tie audit in test_gpu_parity)
-        n_ok += 1
+            assert ranklist_near_tie(oracle_window_scores(sd, cfg, ds, q), r["ranklist"], o["ranklist"], cfg.topk_window), q.query_id
+            hatch.use(q.query_id)
+            continue
         assert_close(r["pred_spans"], np.stack(o["pred_spans"]), FP32_TOL, "pred_spans")
         assert_close(r["prob_fg"], np.stack(o["prob_fg"]), FP32_TOL, "prob_fg")
-    assert n_ok >= len(sub) - 1
-    # reduced-precision mode on the same step: identical windows (the pre-filter is fp32 in both), values within 1e-3
+    hatch.close(len(sub))
+    # reduced-precision mode on the same step: window lists identical to the fp32 path (the pre-filter is fp32 in
+    # both), all 288 000 values against the fp32 PATH OF THIS REPO (an internal consistency check — the comparison with
+    # the oracle on this shape is tests/test_gpu_tc.py::test_tc_vs_oracle_on_the_benchmark_config), identical R@K
     eng_tc = ConeEngine(cfg, sd, device=DEV, precision="tc", workspace_bytes=40 << 30)
-    out_tc = run_step(eng_tc, step)
+    out_tc = run_step(eng_tc, step, want_rows=True)
     assert torch.equal(out_tc.ranklist, out1.ranklist) and torch.equal(out_tc.win_start, out1.win_start)
+    assert torch.equal(out_tc.win_len, out1.win_len)
     valid = (out1.win_len > 0)[:, :, None].expand_as(out1.prob_fg)
+    worst = 0.0
     for a, b in ((out_tc.pred_spans, out1.pred_spans), (out_tc.prob_fg, out1.prob_fg)):
         d = (a - b).abs()
         d = d[valid.unsqueeze(-1).expand_as(d) if d.dim() == 4 else valid]
-        assert float((d <= 1e-3).float().mean()) >= 0.999 and float(d.max()) <= 3e-3
+        worst = max(worst, float(d.max()))
+    print(f"[tc-vs-fp32] mad768 640 queries: max |tc - fp32| over spans / probabilities {worst:.3e}")
+    assert worst <= 1.2 * TC_TOL  # 10x the sample of the oracle test: the extreme of ~1.3e-4 rms errors, measured 7-9e-4
+    from cone_b200.inference import recall_at_k
+    gt = {q.query_id: list(q.timestamps) for q in ds.queries}
+    res_tc = output_to_host(cfg, step, out_tc)
+    for mode in ("fusion", "proposal", "matching"):
+        a, b = recall_at_k(res_tc, gt, mode=mode), recall_at_k(res, gt, mode=mode)
+        assert np.array_equal(np.round(a * 640), np.round(b * 640)), (mode, a, b)
 
 
 def test_ego4d_val_scale_multi_step_vs_oracle_subsample():
@@ -108,12 +121,16 @@ def test_ego4d_val_scale_multi_step_vs_oracle_subsample():
     sub_v = [0, 1]
     sub_q = [q for q in ds.queries if q.video_idx in sub_v]
     ora = O.eval_pipeline(sd, cfg, ds.videos[:2], sub_q)
+    hatch = Hatch("ego4d_val_scale", "top-k window list differs from the oracle (near-tie audited)", 0)
     for q in sub_q:
         r, o = res[q.query_id], ora[q.query_id]
         if r["ranklist"][: cfg.topk_window] != o["ranklist"][: cfg.topk_window]:
+            assert ranklist_near_tie(oracle_window_scores(sd, cfg, ds, q), r["ranklist"], o["ranklist"], cfg.topk_window), q.query_id
+            hatch.use(q.query_id)
             continue
         assert_close(r["pred_spans"], np.stack(o["pred_spans"]), FP32_TOL, "pred_spans")
         assert_close(r["prob_fg"], np.stack(o["prob_fg"]), FP32_TOL, "prob_fg")
+    hatch.close(len(sub_q))
 
 
 def test_long_video_stress_prefilter_and_nms():
@@ -128,11 +145,15 @@ def test_long_video_stress_prefilter_and_nms():
     nw = cfg.num_window(180000)
     assert nw == 2905
     ctx = O.stage0_video_context(sd, torch.from_numpy(O.l2_normalize_np(ds.videos[0])))
+    hatch = Hatch("long_video_stress", "top-30 of 2905 windows differs from the oracle (near-tie audited)", 0)
     for q in ds.queries[:4]:  # stage 0/1 of the oracle only: the full rank-list of 2905 windows
-        rl, _ = O.stage1_ranklist(ctx, torch.from_numpy(O.l2_normalize_np(q.cls)), cfg.max_v_l)
+        rl, fs = O.stage1_ranklist(ctx, torch.from_numpy(O.l2_normalize_np(q.cls)), cfg.max_v_l)
         got = res[q.query_id]["ranklist"]
         assert sorted(got) == list(range(nw))
-        assert got[: cfg.topk_window] == rl[: cfg.topk_window] or got[:5] == rl[:5]
+        if got[: cfg.topk_window] != rl[: cfg.topk_window]:
+            assert ranklist_near_tie(O.window_scores(fs, cfg.max_v_l).numpy(), got, rl, cfg.topk_window), q.query_id
+            hatch.use(q.query_id)
+    hatch.close(4)
     for q in ds.queries[::7]:
         for mode, col in (("fusion", 4), ("proposal", 2), ("matching", 3)):
             _nms_invariants(cfg, res[q.query_id][mode], col)

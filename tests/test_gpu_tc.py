@@ -7,17 +7,20 @@ import numpy as np
 import pytest
 import torch
 
-from cone_b200.config import EGO4D, MAD512
+from cone_b200.config import EGO4D, MAD512, MAD768
 from cone_b200.engine import ConeEngine
 from cone_b200.inference import ground_dataset, recall_at_k
 from cone_b200.synth import make_dataset
 from cone_b200.weights import init_state_dict
 from oracle import cone_oracle as O
-from helpers import assert_close, assert_match_close, dense_case
+from helpers import TC_TOL, Hatch, assert_close, assert_match_close, dense_case, oracle_window_scores, ranklist_near_tie
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TC_TOL = 1e-3  # north_star: "within 1e-3 relative in bf16" (reduced-precision mode), relative to the O(1) output scale
+# TC_TOL = 1e-3: north_star's reduced-precision bound, asserted on the MAXIMUM over all compared values (helpers.py
+# states how "relative" is read).  The tensor-core mode keeps it by construction: fp32-accurate residual stream in the
+# encoder (enc_tail.cu), fp32-class split GEMMs in the decoder and for the input projections / span head; what is left
+# is the fp16 rounding of the encoder's GEMM operands (1.3e-4 rms, profiles/tc_emulate.py).
 
 
 @pytest.fixture(scope="module")
@@ -98,39 +101,56 @@ def test_tc_forward_other_window_sizes_and_slot_counts(max_v_l, nq, wseed):
         want = O.cone_forward(sd, txt, tm, vid, vm)
     vl, tl = vm.sum(1).int().to(DEV), tm.sum(1).int().to(DEV)
     logits, spans, _, _, _ = e.forward(txt.to(DEV), tl, vid.to(DEV), vl)
-    assert_close(spans.cpu(), want["pred_spans"], 1.5 * TC_TOL, "pred_spans")
-    assert_close(torch.softmax(logits, -1).cpu(), torch.softmax(want["pred_logits"], -1), 1.5 * TC_TOL, "class probabilities")
+    assert_close(spans.cpu(), want["pred_spans"], TC_TOL, "pred_spans")
+    assert_close(torch.softmax(logits, -1).cpu(), torch.softmax(want["pred_logits"], -1), TC_TOL, "class probabilities")
 
 
-def test_tc_end_to_end_vs_oracle():
-    cfg = EGO4D.replace(eval_bsz=8)
-    sd = init_state_dict(cfg, 21)
-    e = ConeEngine(cfg, sd, device=DEV, precision="tc", workspace_bytes=3 << 30)
-    ds = make_dataset(cfg, 4, [900, 455, 91, 1300], 4, seed=33)
+def _tc_vs_oracle(cfg, sd, ds, name, workspace=3 << 30, hatch_limit=0):
+    """Tensor-core path against the CPU oracle on the same inputs: identical top-k windows (counted near-tie hatch),
+    every span / probability within TC_TOL, matching scores within TC_TOL away from floor/ceil boundaries, identical
+    R@{1,5} at IoU {0.3, 0.5}.  Returns the error array."""
+    e = ConeEngine(cfg, sd, device=DEV, precision="tc", workspace_bytes=workspace)
     res = ground_dataset(e, ds.videos, ds.queries)
     ora = O.eval_pipeline(sd, cfg, ds.videos, ds.queries)
-    n_ok = 0
+    hatch = Hatch(name, "top-k window list differs from the oracle (near-tie audited)", hatch_limit)
     errs = []
     for q in ds.queries:
         r, o = res[q.query_id], ora[q.query_id]
-        # the window pre-filter stays fp32 in every mode: rank-lists are bit-stable
         if r["ranklist"][: cfg.topk_window] != o["ranklist"][: cfg.topk_window]:
+            assert ranklist_near_tie(oracle_window_scores(sd, cfg, ds, q), r["ranklist"], o["ranklist"], cfg.topk_window), q.query_id
+            hatch.use(q.query_id)
             continue
-        n_ok += 1
+        assert r["windows"] == o["windows"]
         errs.append(np.abs(r["pred_spans"] - np.stack(o["pred_spans"])).ravel())
         errs.append(np.abs(r["prob_fg"] - np.stack(o["prob_fg"])).ravel())
-    assert n_ok >= len(ds.queries) - 2
-    # fp16 operands carry 11 significant bits: the error of a span / probability is ~2.3e-4 rms (measured on the GPU and
-    # by emulating the rounding in the oracle), so over thousands of values the bound is statistical.  The
-    # tail sits right at north_star's 1e-3 (3-4 of 3360 values between 1.0e-3 and 1.2e-3 on this seed, none on two
-    # other seeds: profiles/r01_notes.md), so the assertions are: 99.8 % within 1e-3, nothing beyond 1.5e-3,
-    # rms <= 2.6e-4, 99th percentile <= 8e-4.
-    e = np.concatenate(errs)
-    assert e.size > 3000
-    assert np.mean(e <= TC_TOL) >= 0.998, f"{np.mean(e <= TC_TOL):.4%} of values within {TC_TOL}"
-    assert e.max() <= 1.5 * TC_TOL, e.max()
-    assert np.sqrt(np.mean(e ** 2)) <= 2.6e-4
-    assert np.percentile(e, 99) <= 8e-4
-    gt = {q.query_id: list(q.timestamps) for q in ds.queries}
-    want = O.recall_at_k_iou({q.query_id: ora[q.query_id]["fusion"] for q in ds.queries}, gt)
-    assert np.abs(recall_at_k(res, gt) - want).max() <= 1.0 / len(ds.queries) + 1e-9
+        assert_match_close(r["match"], np.stack(o["match"]), np.stack(o["pred_spans"]), [n for _, n in r["windows"]], TC_TOL)
+    used = hatch.close(len(ds.queries))
+    err = np.concatenate(errs)
+    print(f"[tc-vs-oracle] {name}: n {err.size} max {err.max():.3e} rms {np.sqrt(np.mean(err ** 2)):.3e} "
+          f"p99 {np.percentile(err, 99):.3e} over1e-3 {int((err > TC_TOL).sum())}")
+    assert err.max() <= TC_TOL, f"{name}: max error {err.max():.3e} > {TC_TOL}"
+    if used == 0:  # identical windows for every query: the final metric must be identical too (north_star)
+        gt = {q.query_id: list(q.timestamps) for q in ds.queries}
+        n = len(ds.queries)
+        for mode in ("fusion", "proposal", "matching"):
+            want = O.recall_at_k_iou({q.query_id: ora[q.query_id][mode] for q in ds.queries}, gt)
+            got = recall_at_k(res, gt, mode=mode)
+            assert np.array_equal(np.round(got * n), np.round(want * n)), (name, mode, got, want)
+    return err
+
+
+@pytest.mark.parametrize("wseed,dseed", [(21, 33), (5, 7), (9, 11)])
+def test_tc_end_to_end_vs_oracle(wseed, dseed):
+    cfg = EGO4D.replace(eval_bsz=8)
+    err = _tc_vs_oracle(cfg, init_state_dict(cfg, wseed), make_dataset(cfg, 4, [900, 455, 91, 1300], 4, seed=dseed),
+                        f"tc_end_to_end[{wseed},{dseed}]")
+    assert err.size > 3000 and np.sqrt(np.mean(err ** 2)) <= 2.0e-4
+
+
+def test_tc_vs_oracle_on_the_benchmark_config():
+    """The benchmarked mode on the benchmarked shape (MAD-768: 45 000-frame movie, 768-d, top-30 windows of 125 frames)
+    against the ORACLE (not against this repo's fp32 path) on 64 queries = 28 800 spans / probabilities."""
+    cfg = MAD768
+    err = _tc_vs_oracle(cfg, init_state_dict(cfg, 5), make_dataset(cfg, 1, [45000], 64, seed=11), "tc_mad768_64q",
+                        workspace=16 << 30)
+    assert err.size >= 64 * 30 * 5 * 3
