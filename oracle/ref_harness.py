@@ -1,8 +1,10 @@
 """Runs the UNMODIFIED reference (`/root/reference`, houzhijian/CONE) on in-memory synthetic data.
 
-TEST INFRASTRUCTURE ONLY, and only usable where `/root/reference` exists (the build container);
-the GPU box never imports this.  It is how the oracle is pinned: `python -m oracle.make_golden`
-calls `run_reference_eval_epoch` and freezes the reference's own outputs under `tests/golden/`.
+TEST / BENCH INFRASTRUCTURE ONLY.  Usable where `/root/reference` exists (the build container) or
+where `oracle/vendor_ref.py` has placed the reference's files under `oracle/_ref` (they travel to the
+GPU box with the snapshot).  It is how the oracle is pinned: `python -m oracle.make_golden`
+calls `run_reference_eval_epoch` and freezes the reference's own outputs under `tests/golden/`; it is also
+what `bench.py --impl reference` times and what `tests/test_gpu_dropin.py` drives.
 
 Mechanics:
 * `lmdb` and `terminaltables` are absent here and there is no network: three-line stub modules are
@@ -26,11 +28,25 @@ from typing import Dict, List
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("CONE_REFERENCE_ROOT", "/root/reference")
+def _reference_root() -> str:
+    """`/root/reference` in the build container; on the GPU box the byte-identical files that `oracle/vendor_ref.py`
+    placed under `oracle/_ref` (hash-checked against their manifest)."""
+    env = os.environ.get("CONE_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/cone/inference.py"):
+        return "/root/reference"
+    from oracle import vendor_ref
+    if vendor_ref.verify():
+        return vendor_ref.DEST
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "cone"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "cone", "inference.py"))
 
 
 def _install_stubs() -> None:
@@ -264,6 +280,35 @@ def run_reference_eval_epoch(cfg, sd, ds, capture_frame_scores: int = 0) -> Dict
                 a = (a / a.norm(dim=2, keepdim=True))[0]
                 c = torch.from_numpy(O.l2_normalize_np(q.cls))
                 out[q.query_id]["frame_score"] = torch.einsum("db,b->d", a, c).detach().numpy()
+    return out
+
+
+def run_eval_epoch_files(cfg, ds, model, device: str = "cpu", timer=None) -> Dict[str, object]:
+    """The reference's own `eval_epoch` (inference.py:227-499), unmodified, driven with ANY model object that has the
+    reference's surface (the reference `CONE`, or `cone_b200.CONE` substituted as INTEGRATION.md §1 describes), on
+    in-memory data.  Returns what the reference writes and returns: {"ranklists", "fusion" / "proposal" / "matching"
+    (query_id -> predicted_times of the three prediction files), "recall" (its R@K table, fractions), "seconds"}."""
+    import time
+    ref_inf = import_reference()
+    with tempfile.TemporaryDirectory() as td:
+        eval_path = os.path.join(td, "val.jsonl")
+        with open(eval_path, "w") as f:
+            for row in ds.annotations():
+                f.write(json.dumps(row) + "\n")
+        opt = make_opt(cfg, td, eval_path, device=device)
+        pre, se = _make_datasets(ref_inf, ds, opt)
+        t0 = time.perf_counter()
+        with _stable_sort(ref_inf), torch.no_grad():
+            results, _, _, _ = ref_inf.eval_epoch(model, pre, se, opt, "inference_mad_val_test_preds.jsonl",
+                                                  epoch_i=0, criterion=None, tb_writer=None)
+        seconds = time.perf_counter() - t0
+        out: Dict[str, object] = {"ranklists": {k: list(v) for k, v in se.query_id2windowidx.items()}, "seconds": seconds}
+        base = os.path.join(td, "inference_mad_val_test_preds.jsonl")
+        for name, path in (("fusion", base), ("proposal", base.replace("preds", "proposal_preds")),
+                           ("matching", base.replace("preds", "matching_preds"))):
+            with open(path) as f:
+                out[name] = {json.loads(line)["query_id"]: json.loads(line)["predicted_times"] for line in f}
+        out["recall"] = (results / 100.0).tolist() if hasattr(results, "tolist") else results
     return out
 
 
