@@ -175,8 +175,22 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 if (P.has_lo_in)
                     for (int kb = 0; kb < 4; ++kb) emit(&tmRlo, kb * 64, m0, SLOT_BYTES);
             };
-            auto emit_g1 = [&](int c) {
-                for (int kb = 0; kb < 4; ++kb) emit(&tmW1, kb * 64, c * 128 + (128 / CG) * (int)rank, SLOT_BYTES / CG);
+            auto emit_g1 = [&](int c) {  // CG = 2: this CTA's 64 rows of the chunk, TWO k-blocks per 16 KB slot
+                if (CG == 1) {
+                    for (int kb = 0; kb < 4; ++kb) emit(&tmW1, kb * 64, c * 128, SLOT_BYTES);
+                } else {
+                    for (int kp = 0; kp < 2; ++kp) {
+                        mbar_wait(&empty[slot], ph ^ 1);
+                        mbar_expect_tx_leader(&full[slot], SLOT_BYTES);
+                        tma_load_2d_pair(sRing + slot * SLOT_BYTES, &tmW1, &full[slot], (2 * kp) * 64, c * 128 + 64 * (int)rank);
+                        tma_load_2d_pair(sRing + slot * SLOT_BYTES + SLOT_BYTES / 2, &tmW1, &full[slot], (2 * kp + 1) * 64,
+                                         c * 128 + 64 * (int)rank);
+                        if (++slot == NSLOT) {
+                            slot = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
             };
             auto emit_g2 = [&](int c) {
                 for (int kb = 0; kb < 2; ++kb) {
@@ -263,12 +277,25 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             };
             auto gemm1 = [&](int c) {  // hidden chunk c: Hreg[c & 1] = X . W1[c]^T
                 const uint32_t d = tmemH + 128 * (c & 1);
-                for (int kb = 0; kb < 4; ++kb) {
-                    const int ib = take();
-                    const uint32_t b = ring_addr + ib * SLOT_BYTES, a = x_addr + kb * SLOT_BYTES;
+                if (CG == 1) {
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const int ib = take();
+                        const uint32_t b = ring_addr + ib * SLOT_BYTES, a = x_addr + kb * SLOT_BYTES;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) mma(d, a + k * 32, b + k * 32, id128, (kb > 0 || k > 0) ? 1u : 0u);
-                    commit(&empty[ib]);
+                        for (int k = 0; k < 4; ++k) mma(d, a + k * 32, b + k * 32, id128, (kb > 0 || k > 0) ? 1u : 0u);
+                        commit(&empty[ib]);
+                    }
+                } else {
+                    for (int kp = 0; kp < 2; ++kp) {  // one slot = k-blocks 2 kp, 2 kp + 1 of this CTA's 64 rows
+                        const int ib = take();
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint32_t b = ring_addr + ib * SLOT_BYTES + kk * (SLOT_BYTES / 2), a = x_addr + (2 * kp + kk) * SLOT_BYTES;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) mma(d, a + k * 32, b + k * 32, id128, (kp > 0 || kk > 0 || k > 0) ? 1u : 0u);
+                        }
+                        commit(&empty[ib]);
+                    }
                 }
                 commit(&hfull[c & 1]);
             };
@@ -293,15 +320,13 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             uint32_t p = 0, hrph[2] = {0, 0};
             if (st_begin < n_super) gemm0();
             for (int64_t st = st_begin; st < n_super; st += st_step) {
-                if (CG == 1) mbar_wait(xready, p);
-                else mbar_wait_cluster(xready, p);
+                mbar_wait(xready, p);
                 tc_fence_after();
                 gemm1(0);
                 if (nchunk > 1) gemm1(1);
                 for (int c = 0; c < nchunk; ++c) {
                     const int b = c & 1;
-                    if (CG == 1) mbar_wait(&hready[b], hrph[b]);
-                    else mbar_wait_cluster(&hready[b], hrph[b]);
+                    mbar_wait(&hready[b], hrph[b]);
                     hrph[b] ^= 1;
                     tc_fence_after();
                     gemm2(c);
@@ -571,7 +596,7 @@ int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
     if (clusters > n_super) clusters = n_super;
     const unsigned grid = (unsigned)(clusters * cg);
     const double m = (double)a.M;
-    ProfScope ps(s, P_GEMM_TC, 2.0 * m * ((double)a.d * a.d + 2.0 * a.d * a.ffn),
+    ProfScope ps(s, P_ENC_TAIL, 2.0 * m * ((double)a.d * a.d + 2.0 * a.d * a.ffn),
                  2.0 * m * a.d * (2.0 + (a.res_lo ? 1.0 : 0.0) + 1.0 + (a.out_lo ? 1.0 : 0.0)) + (a.C32 ? 4.0 * m * a.d : 0.0));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

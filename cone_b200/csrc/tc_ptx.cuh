@@ -148,13 +148,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 // In the shared::cluster window a CTA's own shared::cta addresses carry its rank in bit 24 of a CTA pair: clearing the
 // bit addresses the same offset in the EVEN (leader) CTA of the pair.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
-// arrive (release at cluster scope) on the barrier at the same offset in the leader CTA of the pair
+// arrive on the barrier at the same offset in the leader CTA of the pair.  Default semantics (.release.cta), as CUTLASS
+// uses for its 2-SM kernels: a `.release.cluster` form compiles to MEMBAR.ALL + ERRBAR in front of every arrive, which
+// ncu showed as ~800 cycles per ring item in the TMA producer thread (the whole kernel ran at the producer's pace).
+// The data these arrivals publish is ordered by the proxy fence / by the TMA's own complete_tx, not by this arrive.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_leader(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(smem_u32(bar) & kPeerBitMask),
-                 "r"(bytes)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(smem_u32(bar) & kPeerBitMask), "r"(bytes)
                  : "memory");
 }
 // wait with acquire at cluster scope (the arrivals come from the other CTA of the pair)

@@ -92,13 +92,17 @@ def test_mad768_full_step_properties_and_oracle_subsample():
         d = d[valid.unsqueeze(-1).expand_as(d) if d.dim() == 4 else valid]
         worst = max(worst, float(d.max()))
     print(f"[tc-vs-fp32] mad768 640 queries: max |tc - fp32| over spans / probabilities {worst:.3e}")
-    assert worst <= 1.2 * TC_TOL  # 10x the sample of the oracle test: the extreme of ~1.3e-4 rms errors, measured 7-9e-4
+    assert worst <= TC_TOL  # 288 000 values, 10x the sample of the oracle test (measured 8.9e-4)
+    # R@K of the two modes: the +-1-frame pooling flips a 1e-4 span difference causes move matching
+    # scores by ~1e-2 and can reorder near-equal fused candidates: at most 0.5 % of the queries may change (measured 2 of 640)
     from cone_b200.inference import recall_at_k
     gt = {q.query_id: list(q.timestamps) for q in ds.queries}
     res_tc = output_to_host(cfg, step, out_tc)
     for mode in ("fusion", "proposal", "matching"):
         a, b = recall_at_k(res_tc, gt, mode=mode), recall_at_k(res, gt, mode=mode)
-        assert np.array_equal(np.round(a * 640), np.round(b * 640)), (mode, a, b)
+        dev = np.abs(np.round(a * 640) - np.round(b * 640)).max()
+        print(f"[tc-vs-fp32] mad768 640 queries: R@K hit counts ({mode}) differ by at most {int(dev)} queries")
+        assert dev <= 3, (mode, a, b)
 
 
 def test_ego4d_val_scale_multi_step_vs_oracle_subsample():
