@@ -51,10 +51,11 @@ constexpr int OFF_H = OFF_X + XT_BYTES;
 constexpr int OFF_RING = OFF_H + 2 * HB_BYTES;
 constexpr int OFF_I64 = OFF_RING + NSLOT * SLOT_BYTES;
 constexpr int OFF_BAR = OFF_I64 + I64_BYTES;
-constexpr int N_BAR = 2 * NSLOT + 7;
+constexpr int N_BAR = 2 * NSLOT + 11;
 constexpr int OFF_LN = OFF_BAR + 8 * 32;           // room for 32 barriers
 constexpr int OFF_SLOT = OFF_LN + 8 * 32 * 8;      // LayerNorm partials [8 warps][32 lanes] float2
-constexpr int ET_SMEM = OFF_SLOT + 64 + 1024;      // + alignment slack
+constexpr int OFF_PAR = OFF_SLOT + 64;             // bo, ln1_g, ln1_b, b2, ln2_g, ln2_b: 6 x 256 floats
+constexpr int ET_SMEM = OFF_PAR + 6 * ET_D * 4 + 1024;  // + alignment slack
 static_assert(N_BAR <= 32, "barrier area");
 static_assert(ET_SMEM <= 232448, "enc_tail shared memory exceeds 227 KB");
 
@@ -90,9 +91,14 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
     uint64_t* xready = g0full + 1;
     uint64_t* yfull = xready + 1;
     uint64_t* hfull = yfull + 1;    // [2]
-    uint64_t* hready = hfull + 2;   // [2]
+    uint64_t* hready = hfull + 2;   // [2] fp16 chunk in shared memory
+    uint64_t* htfree = hready + 2;  // [2] chunk accumulator read out of TMEM
+    uint64_t* hsfree = htfree + 2;  // [2] GEMM2 has finished reading the shared-memory chunk buffer
     float2* ln_part = reinterpret_cast<float2*>(smem + OFF_LN);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_SLOT);
+    float* sPar = reinterpret_cast<float*>(smem + OFF_PAR);  // epilogue vectors (broadcast LDS instead of global loads)
+    const float *s_bo = sPar, *s_g1 = sPar + ET_D, *s_b1 = sPar + 2 * ET_D, *s_b2 = sPar + 3 * ET_D, *s_g2 = sPar + 4 * ET_D,
+                *s_bb2 = sPar + 5 * ET_D;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -116,6 +122,8 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
         for (int i = 0; i < 2; ++i) {
             mbar_init(&hfull[i], 1);
             mbar_init(&hready[i], 8 * CG);
+            mbar_init(&htfree[i], 8 * CG);
+            mbar_init(&hsfree[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -127,6 +135,14 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
+    }
+    for (int i = threadIdx.x; i < ET_D; i += ET_THREADS) {
+        sPar[i] = P.bo[i];
+        sPar[ET_D + i] = P.ln1_g[i];
+        sPar[2 * ET_D + i] = P.ln1_b[i];
+        sPar[3 * ET_D + i] = P.b2[i];
+        sPar[4 * ET_D + i] = P.ln2_g[i];
+        sPar[5 * ET_D + i] = P.ln2_b[i];
     }
     // identity tile of the residual MMAs: this CTA's 64 / CG rows of I64 (row n holds a single 1.0 at k = n)
     for (int i = threadIdx.x; i < I64_BYTES / 16; i += ET_THREADS) reinterpret_cast<uint4*>(sI)[i] = make_uint4(0, 0, 0, 0);
@@ -216,9 +232,9 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 if (has_next) prefetch_rows(m_next);
                 emit_g1(0);
                 if (nchunk > 1) emit_g1(1);
-                for (int c = 0; c < nchunk; ++c) {
-                    emit_g2(c);
+                for (int c = 0; c < nchunk; ++c) {  // the order the MMA warp consumes: GEMM1(c + 2) before GEMM2(c)
                     if (c + 2 < nchunk) emit_g1(c + 2);
+                    emit_g2(c);
                 }
                 if (has_next) emit_gemm0(m_next);
             }
@@ -317,7 +333,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     if (CG == 1) commit(&empty[ib1]);
                 }
             };
-            uint32_t p = 0, hrph[2] = {0, 0};
+            uint32_t p = 0, hrph[2] = {0, 0}, htph[2] = {0, 0};
             if (st_begin < n_super) gemm0();
             for (int64_t st = st_begin; st < n_super; st += st_step) {
                 mbar_wait(xready, p);
@@ -326,11 +342,17 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 if (nchunk > 1) gemm1(1);
                 for (int c = 0; c < nchunk; ++c) {
                     const int b = c & 1;
+                    // chunk c's accumulator is in the epilogue's registers: GEMM1 of chunk c + 2 may overwrite it and keeps
+                    // the tensor pipe busy while chunk c is still being converted
+                    mbar_wait(&htfree[b], htph[b]);
+                    htph[b] ^= 1;
+                    tc_fence_after();
+                    if (c + 2 < nchunk) gemm1(c + 2);
                     mbar_wait(&hready[b], hrph[b]);
                     hrph[b] ^= 1;
                     tc_fence_after();
                     gemm2(c);
-                    if (c + 2 < nchunk) gemm1(c + 2);
+                    if (c + 2 < nchunk) commit(&hsfree[b]);  // the epilogue writes chunk c + 2 into the same buffer
                 }
                 commit(yfull);
                 if (st + st_step < n_super) gemm0();  // overlaps the final epilogue of this tile
@@ -344,7 +366,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
         const int partner = ew ^ 4;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        uint32_t p = 0, hfph[2] = {0, 0};
+        uint32_t p = 0, hfph[2] = {0, 0}, hsph[2] = {0, 0};
         auto arrive = [&](uint64_t* bar) {
             if (CG == 1) mbar_arrive(bar);
             else mbar_arrive_leader(bar);
@@ -362,60 +384,58 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
         };
         for (int64_t st = st_begin; st < n_super; st += st_step) {
             const int m0 = (int)((st * CG + rank) * 128);
-            // ---- epi-0: x = LN1(att.Wo^T + res + bo) -> X tile (fp16), Y (fp32, + b2)
+            // ---- epi-0: x = LN1(att.Wo^T + res + bo) -> X tile (fp16), Y (fp32, + b2).  The row's 128 columns of this
+            // warp stay in registers between the statistics and the normalisation (one TMEM read, no second pass).
             mbar_wait(g0full, p);
             tc_fence_after();
             if (lane == 0) tma_store_wait_read<0>();  // the staged output of the previous tile has left X / H
             __syncwarp();
             {
                 const uint32_t tH = tmemH + lane_base + half * 128, tY = tmemY + lane_base + half * 128;
+                float x[128];
+                tmem_ld_32x64(tH, x);
+                tmem_ld_32x64(tH + 64, x + 64);
+                tmem_ld_wait();
                 float s1 = 0.f, s2 = 0.f;
-                for (int c = 0; c < 4; ++c) {
-                    float x[32];
-                    tmem_ld_32x32(tH + 32 * c, x);
-                    tmem_ld_wait();
-                    const float4* b4 = reinterpret_cast<const float4*>(P.bo + half * 128 + 32 * c);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = __ldg(b4 + q);
-                        const float v0 = x[4 * q] + b.x, v1 = x[4 * q + 1] + b.y, v2 = x[4 * q + 2] + b.z, v3 = x[4 * q + 3] + b.w;
-                        s1 += (v0 + v1) + (v2 + v3);
-                        s2 = fmaf(v0, v0, s2); s2 = fmaf(v1, v1, s2); s2 = fmaf(v2, v2, s2); s2 = fmaf(v3, v3, s2);
-                    }
+                for (int q = 0; q < 32; ++q) {
+                    const float4 b = reinterpret_cast<const float4*>(s_bo + half * 128)[q];
+                    x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+                    s1 += (x[4 * q] + x[4 * q + 1]) + (x[4 * q + 2] + x[4 * q + 3]);
+                    s2 = fmaf(x[4 * q], x[4 * q], s2); s2 = fmaf(x[4 * q + 1], x[4 * q + 1], s2);
+                    s2 = fmaf(x[4 * q + 2], x[4 * q + 2], s2); s2 = fmaf(x[4 * q + 3], x[4 * q + 3], s2);
                 }
                 float mean, rstd;
                 row_stats(s1, s2, mean, rstd);
+#pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float x[32];
-                    tmem_ld_32x32(tH + 32 * c, x);
-                    tmem_ld_wait();
                     const int col = half * 128 + 32 * c;
+                    float* xc = x + 32 * c;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 bo = __ldg(reinterpret_cast<const float4*>(P.bo + col) + q);
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln1_g + col) + q);
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln1_b + col) + q);
-                        x[4 * q] = ((x[4 * q] + bo.x) - mean) * rstd * g.x + b.x;
-                        x[4 * q + 1] = ((x[4 * q + 1] + bo.y) - mean) * rstd * g.y + b.y;
-                        x[4 * q + 2] = ((x[4 * q + 2] + bo.z) - mean) * rstd * g.z + b.z;
-                        x[4 * q + 3] = ((x[4 * q + 3] + bo.w) - mean) * rstd * g.w + b.w;
+                        const float4 g = reinterpret_cast<const float4*>(s_g1 + col)[q];
+                        const float4 b = reinterpret_cast<const float4*>(s_b1 + col)[q];
+                        xc[4 * q] = (xc[4 * q] - mean) * rstd * g.x + b.x;
+                        xc[4 * q + 1] = (xc[4 * q + 1] - mean) * rstd * g.y + b.y;
+                        xc[4 * q + 2] = (xc[4 * q + 2] - mean) * rstd * g.z + b.z;
+                        xc[4 * q + 3] = (xc[4 * q + 3] - mean) * rstd * g.w + b.w;
                     }
                     uint8_t* xk = sX + (half * 2 + (c >> 1)) * SLOT_BYTES;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint4 v;
-                        v.x = pack_h2(x[8 * u], x[8 * u + 1]);
-                        v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
-                        v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
-                        v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
+                        v.x = pack_h2(xc[8 * u], xc[8 * u + 1]);
+                        v.y = pack_h2(xc[8 * u + 2], xc[8 * u + 3]);
+                        v.z = pack_h2(xc[8 * u + 4], xc[8 * u + 5]);
+                        v.w = pack_h2(xc[8 * u + 6], xc[8 * u + 7]);
                         *reinterpret_cast<uint4*>(xk + sw128(row, (c & 1) * 4 + u)) = v;
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {  // Y starts as the fp32 residual of the FFN + linear2's bias
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.b2 + col) + q);
-                        x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+                        const float4 b = reinterpret_cast<const float4*>(s_b2 + col)[q];
+                        xc[4 * q] += b.x; xc[4 * q + 1] += b.y; xc[4 * q + 2] += b.z; xc[4 * q + 3] += b.w;
                     }
-                    tmem_st_32x32(tY + 32 * c, x);
+                    tmem_st_32x32(tY + 32 * c, xc);
                 }
                 tmem_st_wait();
                 fence_async_smem();
@@ -423,7 +443,9 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 __syncwarp();
                 if (lane == 0) arrive(xready);
             }
-            // ---- epi-h: hidden chunks
+            // ---- epi-h: hidden chunks.  Two hand-offs per chunk: `htfree` as soon as the accumulator is in registers (the
+            // MMA warp may overwrite it with chunk c + 2 while this chunk is still being converted), `hready` once the fp16
+            // chunk is in shared memory (GEMM2 of this chunk may start).
             for (int c = 0; c < nchunk; ++c) {
                 const int b = c & 1;
                 mbar_wait(&hfull[b], hfph[b]);
@@ -431,15 +453,25 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 tc_fence_after();
                 float x[64];
                 tmem_ld_32x64(tmemH + lane_base + 128 * b + 64 * half, x);
-                tmem_ld_wait();
                 const float4* b4 = reinterpret_cast<const float4*>(P.b1 + c * 128 + half * 64);
+                float4 bias[16];  // issued while the TMEM load is in flight
+#pragma unroll
+                for (int q = 0; q < 16; ++q) bias[q] = __ldg(b4 + q);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive(&htfree[b]);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const float4 bb = __ldg(b4 + q);
+                    const float4 bb = bias[q];
                     x[4 * q] = fmaxf(x[4 * q] + bb.x, 0.f);
                     x[4 * q + 1] = fmaxf(x[4 * q + 1] + bb.y, 0.f);
                     x[4 * q + 2] = fmaxf(x[4 * q + 2] + bb.z, 0.f);
                     x[4 * q + 3] = fmaxf(x[4 * q + 3] + bb.w, 0.f);
+                }
+                if (c >= 2) {  // GEMM2 of chunk c - 2 has finished reading this shared-memory buffer
+                    mbar_wait(&hsfree[b], hsph[b]);
+                    hsph[b] ^= 1;
                 }
                 uint8_t* hk = sH + b * HB_BYTES + half * SLOT_BYTES;
 #pragma unroll
@@ -452,7 +484,6 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     *reinterpret_cast<uint4*>(hk + sw128(row, u)) = v;
                 }
                 fence_async_smem();
-                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive(&hready[b]);
             }
@@ -461,39 +492,38 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             tc_fence_after();
             {
                 const uint32_t tY = tmemY + lane_base + half * 128;
+                float x[128];
+                tmem_ld_32x64(tY, x);
+                tmem_ld_32x64(tY + 64, x + 64);
+                tmem_ld_wait();
+                tc_fence_before();  // Y is in registers: this warp's next writes to it are epi-0 of the next tile
                 float s1 = 0.f, s2 = 0.f;
-                for (int c = 0; c < 4; ++c) {
-                    float x[32];
-                    tmem_ld_32x32(tY + 32 * c, x);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        s1 += (x[j] + x[j + 1]) + (x[j + 2] + x[j + 3]);
-                        s2 = fmaf(x[j], x[j], s2); s2 = fmaf(x[j + 1], x[j + 1], s2);
-                        s2 = fmaf(x[j + 2], x[j + 2], s2); s2 = fmaf(x[j + 3], x[j + 3], s2);
-                    }
+                for (int j = 0; j < 128; j += 4) {
+                    s1 += (x[j] + x[j + 1]) + (x[j + 2] + x[j + 3]);
+                    s2 = fmaf(x[j], x[j], s2); s2 = fmaf(x[j + 1], x[j + 1], s2);
+                    s2 = fmaf(x[j + 2], x[j + 2], s2); s2 = fmaf(x[j + 3], x[j + 3], s2);
                 }
                 float mean, rstd;
                 row_stats(s1, s2, mean, rstd);
                 const int64_t grow = (int64_t)m0 + row;
+#pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float x[32];
-                    tmem_ld_32x32(tY + 32 * c, x);
-                    tmem_ld_wait();
                     const int col = half * 128 + 32 * c;
+                    float* xc = x + 32 * c;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln2_g + col) + q);
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln2_b + col) + q);
-                        x[4 * q] = (x[4 * q] - mean) * rstd * g.x + b.x;
-                        x[4 * q + 1] = (x[4 * q + 1] - mean) * rstd * g.y + b.y;
-                        x[4 * q + 2] = (x[4 * q + 2] - mean) * rstd * g.z + b.z;
-                        x[4 * q + 3] = (x[4 * q + 3] - mean) * rstd * g.w + b.w;
+                        const float4 g = reinterpret_cast<const float4*>(s_g2 + col)[q];
+                        const float4 b = reinterpret_cast<const float4*>(s_bb2 + col)[q];
+                        xc[4 * q] = (xc[4 * q] - mean) * rstd * g.x + b.x;
+                        xc[4 * q + 1] = (xc[4 * q + 1] - mean) * rstd * g.y + b.y;
+                        xc[4 * q + 2] = (xc[4 * q + 2] - mean) * rstd * g.z + b.z;
+                        xc[4 * q + 3] = (xc[4 * q + 3] - mean) * rstd * g.w + b.w;
                     }
                     if (P.C32 != nullptr && grow < P.M) {
                         float4* o4 = reinterpret_cast<float4*>(P.C32 + grow * P.ldc32 + col);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) o4[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                        for (int q = 0; q < 8; ++q) o4[q] = make_float4(xc[4 * q], xc[4 * q + 1], xc[4 * q + 2], xc[4 * q + 3]);
                     }
                     const uint32_t off = (uint32_t)(half * 2 + (c >> 1)) * SLOT_BYTES;
 #pragma unroll
@@ -503,10 +533,10 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                         uint32_t* vw = &v.x;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const __half2 h = __floats2half2_rn(x[8 * u + 2 * e], x[8 * u + 2 * e + 1]);
+                            const __half2 h = __floats2half2_rn(xc[8 * u + 2 * e], xc[8 * u + 2 * e + 1]);
                             const float2 f = __half22float2(h);
-                            lo[2 * e] = x[8 * u + 2 * e] - f.x;
-                            lo[2 * e + 1] = x[8 * u + 2 * e + 1] - f.y;
+                            lo[2 * e] = xc[8 * u + 2 * e] - f.x;
+                            lo[2 * e + 1] = xc[8 * u + 2 * e + 1] - f.y;
                             vw[e] = *reinterpret_cast<const uint32_t*>(&h);
                         }
                         *reinterpret_cast<uint4*>(sX + off + sw128(row, (c & 1) * 4 + u)) = v;
@@ -520,7 +550,6 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                         }
                     }
                 }
-                tc_fence_before();  // all reads of Y by this warp precede its next writes (epi-0 of the next tile)
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {

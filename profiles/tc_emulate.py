@@ -135,13 +135,13 @@ class Emu:
         hs = None
         for l in range(cfg.dec_layers):
             p = f"transformer.decoder.layers.{l}"
-            qk = self.r("d_op", tgt + qpos)
-            t2 = self.mha_plain(p + ".self_attn", qk, qk, self.r("d_op", tgt), None, "w_dec", "d_op", "d_p")
+            qk = self.r("d_in", tgt + qpos)
+            t2 = self.mha_plain(p + ".self_attn", qk, qk, self.r("d_in", tgt), None, "w_dec", "d_att", "d_p")
             tgt = O._ln(sd, p + ".norm1", tgt + t2)
-            t2 = self.mha_plain(p + ".multihead_attn", self.r("d_op", tgt + qpos), mem + pos, mem, pad, "w_decx", "d_pm", "d_p", "d_qx")
+            t2 = self.mha_plain(p + ".multihead_attn", self.r("d_inx", tgt + qpos), mem + pos, mem, pad, "w_decx", "d_pm", "d_p", "d_qx")
             tgt = O._ln(sd, p + ".norm2", tgt + t2)
-            hid = self.r("d_op", F.relu(F.linear(self.r("d_op", tgt), self.W(p + ".linear1.weight", "w_dec"), sd[p + ".linear1.bias"])))
-            t2 = F.linear(hid, self.W(p + ".linear2.weight", "w_dec"), sd[p + ".linear2.bias"])
+            hid = self.r("d_hid", F.relu(F.linear(self.r("d_fin", tgt), self.W(p + ".linear1.weight", "w_dffn"), sd[p + ".linear1.bias"])))
+            t2 = F.linear(hid, self.W(p + ".linear2.weight", "w_dffn"), sd[p + ".linear2.bias"])
             tgt = O._ln(sd, p + ".norm3", tgt + t2)
             hs = O._ln(sd, "transformer.decoder.norm", tgt)
         logits = F.linear(hs, sd["class_embed.weight"], sd["class_embed.bias"])
@@ -149,8 +149,8 @@ class Emu:
         return logits, spans
 
 
-ALL = {"src", "src_res", "w_enc", "w_ffn", "qkv", "p", "att", "ln_op", "ln1_res", "ln2_res", "hid", "w_dec", "w_decx", "d_op", "d_qkv", "d_qx",
-       "d_p", "d_pm", "mem"}
+ALL = {"src", "src_res", "w_enc", "w_ffn", "qkv", "p", "att", "ln_op", "ln1_res", "ln2_res", "hid", "w_dec", "w_decx", "w_dffn",
+       "d_in", "d_inx", "d_att", "d_hid", "d_fin", "d_qkv", "d_qx", "d_p", "d_pm", "mem"}
 
 
 def batches(sd, cfg, ds):
@@ -200,13 +200,16 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     RES = {"ln1_res", "ln2_res", "src_res"}
     DEC = {"w_dec", "d_op", "d_qkv"}
-    DECX = {"w_dec", "w_decx", "d_op", "d_qkv"}
-    cf = [("all fp16 (current pipeline)", ALL, ()),
-          ("fp32 residuals", ALL - RES, ()),
-          ("res + dec weights + d_op", ALL - RES - {"w_dec", "w_decx", "d_op"}, ()),
-          ("res + dec w/op/qkv", ALL - RES - DECX, ()),
-          ("res + dec w/op/qkv + qx + pm", ALL - RES - DECX - {"d_qx", "d_pm"}, ()),
-          ("enc only, fp32 res", ALL - RES - DEC - {"w_decx", "d_qx", "d_pm", "d_p", "mem"}, ()),
+    DOP = {"d_in", "d_inx", "d_att", "d_hid", "d_fin"}
+    NOW = ALL - RES - {"w_dec", "w_decx", "w_dffn", "d_qkv"} - DOP      # the chain as built: only d_qx, d_pm, d_p in the decoder
+    cf = [("as built (split decoder, fp32 res)", NOW, ()),
+          ("as built, src_res fp16", NOW | {"src_res"}, ()),
+          ("+ d_hid fp16", NOW | {"d_hid"}, ()),
+          ("+ d_hid, w_dffn fp16", NOW | {"d_hid", "w_dffn"}, ()),
+          ("+ d_hid, w_dffn, d_fin fp16 (FFN plain)", NOW | {"d_hid", "w_dffn", "d_fin"}, ()),
+          ("+ self-attn plain (w_dec,d_in,d_att,d_qkv)", NOW | {"w_dec", "d_in", "d_att", "d_qkv"}, ()),
+          ("+ cross q plain (w_decx, d_inx)", NOW | {"w_decx", "d_inx"}, ()),
+          ("+ d_inx only", NOW | {"d_inx"}, ()),
           ]
     if len(sys.argv) > 1 and sys.argv[1] == "ablate":
         cf = [("all fp16 (current pipeline)", ALL, ())]
