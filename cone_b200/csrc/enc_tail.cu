@@ -156,8 +156,11 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
     __syncthreads();
     if (CG == 2) cluster_sync_all();  // barrier inits and TMEM allocation of BOTH CTAs before any cross-CTA traffic
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmemY = tmem_base, tmemH = tmem_base + 256;
+    // All 512 columns are allocated by the only CTA on this SM: the allocation starts at lane 0 / column 0.  Using the
+    // literal keeps every TMEM address a compile-time constant (uniform registers in the MMA warp).
+    if (*tmem_slot != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
+    constexpr uint32_t tmemY = tmem_base, tmemH = tmem_base + 256;
 
     if (warp == 0) {
         if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producer
@@ -240,11 +243,14 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {  // -------------------------------------------------------------------- MMA issuer
+        if (leader) {  // ------------------------------------------------------------------------------------ MMA issuer
+            // The WHOLE warp runs this role (uniform control flow, waits included); one elected lane issues the
+            // tcgen05 instructions.  Descriptors are built from warp-uniform values only.
             const uint32_t id256 = et_idesc(128 * CG, 256), id128 = et_idesc(128 * CG, 128), id64 = et_idesc(128 * CG, 64);
             int slot = 0;
             uint32_t ph = 0;
             const uint32_t ring_addr = smem_u32(sRing), x_addr = smem_u32(sX), h_addr = smem_u32(sH), i_addr = smem_u32(sI);
+            const uint64_t desc_hi = smem_desc_sw128(0);  // everything but the 14-bit start-address field
             auto take = [&]() -> int {  // next ring item has landed (in both CTAs of the pair)
                 mbar_wait(&full[slot], ph);
                 tc_fence_after();
@@ -255,28 +261,36 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 }
                 return s;
             };
-            auto mma = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, uint32_t acc) {
-                if (CG == 1) umma_f16(d, smem_desc_sw128(a_addr), smem_desc_sw128(b_addr), idesc, acc);
-                else umma_f16_pair(d, smem_desc_sw128(a_addr), smem_desc_sw128(b_addr), idesc, acc);
+            auto desc = [&](uint32_t addr) -> uint64_t { return desc_hi | (uint64_t)((addr & 0x3FFFF) >> 4); };
+            auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool acc_first) {
+                // the four K = 16 steps of one 64-column k-block
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (acc_first || k > 0) ? 1u : 0u;
+                        if (CG == 1) umma_f16(d, desc(a_addr + k * 32), desc(b_addr + k * 32), idesc, acc);
+                        else umma_f16_pair(d, desc(a_addr + k * 32), desc(b_addr + k * 32), idesc, acc);
+                    }
+                }
+                __syncwarp();
             };
             auto commit = [&](uint64_t* bar) {
-                if (CG == 1) umma_commit(bar);
-                else umma_commit_pair(bar);
+                if (elect_one_sync()) {
+                    if (CG == 1) umma_commit(bar);
+                    else umma_commit_pair(bar);
+                }
+                __syncwarp();
             };
             auto gemm0 = [&]() {
                 for (int kb = 0; kb < 4; ++kb) {
                     const int ia = take(), ib0 = take(), ib1 = (CG == 1) ? take() : 0;
                     const uint32_t a = ring_addr + ia * SLOT_BYTES, b0 = ring_addr + ib0 * SLOT_BYTES,
                                    b1 = ring_addr + ib1 * SLOT_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                        if (CG == 1) {
-                            mma(tmemH, a + k * 32, b0 + k * 32, id128, acc);
-                            mma(tmemH + 128, a + k * 32, b1 + k * 32, id128, acc);
-                        } else {
-                            mma(tmemH, a + k * 32, b0 + k * 32, id256, acc);
-                        }
+                    if (CG == 1) {
+                        mma4(tmemH, a, b0, id128, kb > 0);
+                        mma4(tmemH + 128, a, b1, id128, kb > 0);
+                    } else {
+                        mma4(tmemH, a, b0, id256, kb > 0);
                     }
                     commit(&empty[ia]);
                     commit(&empty[ib0]);
@@ -284,9 +298,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 }
                 for (int j = 0; j < nres; ++j) {  // + res_hi (+ res_lo): 64 columns at a time against the identity tile
                     const int ia = take();
-                    const uint32_t a = ring_addr + ia * SLOT_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) mma(tmemH + 64 * (j & 3), a + k * 32, i_addr + k * 32, id64, 1u);
+                    mma4(tmemH + 64 * (j & 3), ring_addr + ia * SLOT_BYTES, i_addr, id64, true);
                     commit(&empty[ia]);
                 }
                 commit(g0full);
@@ -296,20 +308,14 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 if (CG == 1) {
                     for (int kb = 0; kb < 4; ++kb) {
                         const int ib = take();
-                        const uint32_t b = ring_addr + ib * SLOT_BYTES, a = x_addr + kb * SLOT_BYTES;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) mma(d, a + k * 32, b + k * 32, id128, (kb > 0 || k > 0) ? 1u : 0u);
+                        mma4(d, x_addr + kb * SLOT_BYTES, ring_addr + ib * SLOT_BYTES, id128, kb > 0);
                         commit(&empty[ib]);
                     }
                 } else {
                     for (int kp = 0; kp < 2; ++kp) {  // one slot = k-blocks 2 kp, 2 kp + 1 of this CTA's 64 rows
                         const int ib = take();
-#pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint32_t b = ring_addr + ib * SLOT_BYTES + kk * (SLOT_BYTES / 2), a = x_addr + (2 * kp + kk) * SLOT_BYTES;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) mma(d, a + k * 32, b + k * 32, id128, (kp > 0 || kk > 0 || k > 0) ? 1u : 0u);
-                        }
+                        mma4(d, x_addr + (2 * kp) * SLOT_BYTES, ring_addr + ib * SLOT_BYTES, id128, kp > 0);
+                        mma4(d, x_addr + (2 * kp + 1) * SLOT_BYTES, ring_addr + ib * SLOT_BYTES + SLOT_BYTES / 2, id128, true);
                         commit(&empty[ib]);
                     }
                 }
@@ -320,14 +326,11 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     const int ib0 = take(), ib1 = (CG == 1) ? take() : 0;
                     const uint32_t a = h_addr + (c & 1) * HB_BYTES + kb * SLOT_BYTES, b0 = ring_addr + ib0 * SLOT_BYTES,
                                    b1 = ring_addr + ib1 * SLOT_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (CG == 1) {
-                            mma(tmemY, a + k * 32, b0 + k * 32, id128, 1u);
-                            mma(tmemY + 128, a + k * 32, b1 + k * 32, id128, 1u);
-                        } else {
-                            mma(tmemY, a + k * 32, b0 + k * 32, id256, 1u);
-                        }
+                    if (CG == 1) {
+                        mma4(tmemY, a, b0, id128, true);
+                        mma4(tmemY + 128, a, b1, id128, true);
+                    } else {
+                        mma4(tmemY, a, b0, id256, true);
                     }
                     commit(&empty[ib0]);
                     if (CG == 1) commit(&empty[ib1]);

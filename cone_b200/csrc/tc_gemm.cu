@@ -202,9 +202,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ------------------------------------------------------------------ MMA issuer
+        {  // ---------------------------------------------------------------------------------- MMA issuer
+            // The whole warp runs the role (uniform control flow); one elected lane issues tcgen05.mma / commit, so that
+            // descriptors and addresses stay in uniform registers (a lane-0-only role made the compiler wrap every MMA
+            // in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~120 issue cycles per MMA, tc_ptx.cuh).
             // instruction descriptor: D fp32, A/B fp16 K-major, N = BN, M = 128
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint64_t desc_hi = smem_desc_sw128(0);
+            const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // warp-uniform for the compiler
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -213,25 +218,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int64_t t = t_begin; t < t_end; t += t_step) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base_u + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
                     const uint32_t b_addr = smem_u32(sB + (WRES ? kb : stage) * B_BYTES);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t da = smem_desc_sw128(a_addr + k * UMMA_K * 2);
-                        const uint64_t db = smem_desc_sw128(b_addr + k * UMMA_K * 2);
-                        umma_f16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t da = desc_hi | (uint64_t)(((a_addr + k * UMMA_K * 2) & 0x3FFFF) >> 4);
+                            const uint64_t db = desc_hi | (uint64_t)(((b_addr + k * UMMA_K * 2) & 0x3FFFF) >> 4);
+                            umma_f16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+                        if (kb == num_k - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
                     }
-                    umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+                    __syncwarp();
                     if (++stage == NSTAGE) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;

@@ -135,6 +135,24 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One lane of a fully converged warp (elect.sync): the issue pattern of tcgen05.mma / commit.  The whole warp runs the
+// control flow so that addresses and descriptors stay in uniform registers; a role written as `if (lane == 0) { ... }`
+// makes every operand "divergent" for the compiler, which then wraps each UTCHMMA in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY waterfall of ~23 instructions (~120 cycles per MMA measured: the MMA warp, not the tensor pipe, paced
+// the kernel).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // ---- thread-block-cluster / cta_group::2 forms (enc_tail.cu) --------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
