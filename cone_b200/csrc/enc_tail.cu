@@ -7,7 +7,7 @@
 // (the unfused chain wrote and re-read 7.2 KB per row and layer; this kernel moves 1.5-2.5 KB).
 //
 // sm_100a design.  Persistent, one CTA per SM, warp-specialised like tc_gemm.cu (warp 0 TMA producer, warp 1 MMA issuer,
-// warps 2-9 epilogue), 128 rows per CTA and tile.  With CG = 2 two CTAs of a cluster form a tcgen05 CTA pair
+// warps 2-17 epilogue), 128 rows per CTA and tile.  With CG = 2 two CTAs of a cluster form a tcgen05 CTA pair
 // (`cta_group::2`, M = 256): every weight tile is split between the two CTAs' shared memories, so each SM streams HALF
 // of the 1.15 MB of weights per 128 rows from L2 — at one CTA per tile the weight stream alone (10 TB/s over 148 SMs)
 // would exceed what L2 delivers.
@@ -39,7 +39,8 @@ using namespace ptx;
 
 namespace {
 
-constexpr int ET_THREADS = 320;
+constexpr int ET_THREADS = 576;           // producer warp + MMA warp + 16 epilogue warps
+constexpr int ET_EPI_WARPS = 16;
 constexpr int ET_D = 256;               // model width (rows of 256 fp16 = 4 k-blocks of 64)
 constexpr int SLOT_BYTES = 16384;       // one [128 x 64] fp16 box, 128-byte swizzle
 constexpr int NSLOT = 5;
@@ -53,9 +54,9 @@ constexpr int OFF_I64 = OFF_RING + NSLOT * SLOT_BYTES;
 constexpr int OFF_BAR = OFF_I64 + I64_BYTES;
 constexpr int N_BAR = 2 * NSLOT + 11;
 constexpr int OFF_LN = OFF_BAR + 8 * 32;           // room for 32 barriers
-constexpr int OFF_SLOT = OFF_LN + 8 * 32 * 8;      // LayerNorm partials [8 warps][32 lanes] float2
+constexpr int OFF_SLOT = OFF_LN + ET_EPI_WARPS * 32 * 8;  // LayerNorm partials [16 warps][32 lanes] float2
 constexpr int OFF_PAR = OFF_SLOT + 64;             // bo, ln1_g, ln1_b, b2, ln2_g, ln2_b: 6 x 256 floats
-constexpr int ET_SMEM = OFF_PAR + 6 * ET_D * 4 + 1024;  // + alignment slack
+constexpr int ET_SMEM = OFF_PAR + 6 * ET_D * 4;    // no alignment slack: the kernel traps if the window is not 1 KB aligned
 static_assert(N_BAR <= 32, "barrier area");
 static_assert(ET_SMEM <= 232448, "enc_tail shared memory exceeds 227 KB");
 
@@ -80,7 +81,8 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                 const __grid_constant__ CUtensorMap tmOhi, const __grid_constant__ CUtensorMap tmOlo, EtParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // the 128-byte-swizzle atoms need 1 KB alignment
     uint8_t* sX = smem + OFF_X;
     uint8_t* sH = smem + OFF_H;
     uint8_t* sRing = smem + OFF_RING;
@@ -118,11 +120,11 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
         }
         mbar_init(g0full, 1);
         mbar_init(yfull, 1);
-        mbar_init(xready, 8 * CG);  // lane 0 of every epilogue warp of the pair
+        mbar_init(xready, ET_EPI_WARPS * CG);  // lane 0 of every epilogue warp of the pair
         for (int i = 0; i < 2; ++i) {
             mbar_init(&hfull[i], 1);
-            mbar_init(&hready[i], 8 * CG);
-            mbar_init(&htfree[i], 8 * CG);
+            mbar_init(&hready[i], ET_EPI_WARPS * CG);
+            mbar_init(&htfree[i], ET_EPI_WARPS * CG);
             mbar_init(&hsfree[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -363,10 +365,13 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             }
         }
     } else {  // ------------------------------------------------------------------------------------------ epilogue warps
-        const int ew = warp - 2;       // 0..7
+        // 16 warps: four per TMEM lane quarter, each owning a quarter of the columns (64 of the 256-wide row in the
+        // LayerNorm epilogues, 32 of a 128-wide hidden chunk).  These phases are dependent chains (TMEM load -> math ->
+        // convert -> store) that two warps per scheduler cannot keep busy: with 8 warps ncu showed 15 500 cycles per tile
+        // in the two LayerNorm epilogues alone, during which the tensor pipe only has GEMM0 to do.
+        const int ew = warp - 2;       // 0..15
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;      // which 128 of the 256 columns
-        const int partner = ew ^ 4;
+        const int part = ew >> 2;      // which quarter of the columns
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t p = 0, hfph[2] = {0, 0}, hsph[2] = {0, 0};
@@ -374,72 +379,81 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             if (CG == 1) mbar_arrive(bar);
             else mbar_arrive_leader(bar);
         };
-        // LayerNorm statistics of this lane's row: 128 columns here, 128 in the partner warp
+        // LayerNorm statistics of this lane's row: 64 columns here, 64 in each of the three partner warps
         auto row_stats = [&](float s1, float s2, float& mean, float& rstd) {
             ln_part[ew * 32 + lane] = make_float2(s1, s2);
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            const float2 o = ln_part[partner * 32 + lane];
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            s1 += o.x;
-            s2 += o.y;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+            s1 = 0.f;
+            s2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 o = ln_part[((ew & 3) + 4 * q) * 32 + lane];
+                s1 += o.x;
+                s2 += o.y;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
             mean = s1 * (1.f / ET_D);
             rstd = rsqrtf(fmaxf(s2 * (1.f / ET_D) - mean * mean, 0.f) + P.eps);
         };
+        // sum and sum of squares of 64 values, four independent chains
+        auto stats64 = [&](const float* x, float& s1, float& s2) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+                a0 += x[j]; a1 += x[j + 1]; a2 += x[j + 2]; a3 += x[j + 3];
+                q0 = fmaf(x[j], x[j], q0); q1 = fmaf(x[j + 1], x[j + 1], q1);
+                q2 = fmaf(x[j + 2], x[j + 2], q2); q3 = fmaf(x[j + 3], x[j + 3], q3);
+            }
+            s1 = (a0 + a1) + (a2 + a3);
+            s2 = (q0 + q1) + (q2 + q3);
+        };
         for (int64_t st = st_begin; st < n_super; st += st_step) {
             const int m0 = (int)((st * CG + rank) * 128);
-            // ---- epi-0: x = LN1(att.Wo^T + res + bo) -> X tile (fp16), Y (fp32, + b2).  The row's 128 columns of this
-            // warp stay in registers between the statistics and the normalisation (one TMEM read, no second pass).
+            const int col = 64 * part;  // first of this warp's 64 columns in the LayerNorm epilogues
+            // ---- epi-0: x = LN1(att.Wo^T + res + bo) -> X tile (fp16), Y (fp32, + b2); one TMEM read, values in registers
             mbar_wait(g0full, p);
             tc_fence_after();
             if (lane == 0) tma_store_wait_read<0>();  // the staged output of the previous tile has left X / H
             __syncwarp();
             {
-                const uint32_t tH = tmemH + lane_base + half * 128, tY = tmemY + lane_base + half * 128;
-                float x[128];
-                tmem_ld_32x64(tH, x);
-                tmem_ld_32x64(tH + 64, x + 64);
+                float x[64];
+                tmem_ld_32x64(tmemH + lane_base + col, x);
                 tmem_ld_wait();
-                float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float4 b = reinterpret_cast<const float4*>(s_bo + half * 128)[q];
+                for (int q = 0; q < 16; ++q) {
+                    const float4 b = reinterpret_cast<const float4*>(s_bo + col)[q];
                     x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
-                    s1 += (x[4 * q] + x[4 * q + 1]) + (x[4 * q + 2] + x[4 * q + 3]);
-                    s2 = fmaf(x[4 * q], x[4 * q], s2); s2 = fmaf(x[4 * q + 1], x[4 * q + 1], s2);
-                    s2 = fmaf(x[4 * q + 2], x[4 * q + 2], s2); s2 = fmaf(x[4 * q + 3], x[4 * q + 3], s2);
                 }
-                float mean, rstd;
+                float s1, s2, mean, rstd;
+                stats64(x, s1, s2);
                 row_stats(s1, s2, mean, rstd);
+                const float nm = -mean * rstd;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int col = half * 128 + 32 * c;
-                    float* xc = x + 32 * c;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 g = reinterpret_cast<const float4*>(s_g1 + col)[q];
-                        const float4 b = reinterpret_cast<const float4*>(s_b1 + col)[q];
-                        xc[4 * q] = (xc[4 * q] - mean) * rstd * g.x + b.x;
-                        xc[4 * q + 1] = (xc[4 * q + 1] - mean) * rstd * g.y + b.y;
-                        xc[4 * q + 2] = (xc[4 * q + 2] - mean) * rstd * g.z + b.z;
-                        xc[4 * q + 3] = (xc[4 * q + 3] - mean) * rstd * g.w + b.w;
-                    }
-                    uint8_t* xk = sX + (half * 2 + (c >> 1)) * SLOT_BYTES;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 v;
-                        v.x = pack_h2(xc[8 * u], xc[8 * u + 1]);
-                        v.y = pack_h2(xc[8 * u + 2], xc[8 * u + 3]);
-                        v.z = pack_h2(xc[8 * u + 4], xc[8 * u + 5]);
-                        v.w = pack_h2(xc[8 * u + 6], xc[8 * u + 7]);
-                        *reinterpret_cast<uint4*>(xk + sw128(row, (c & 1) * 4 + u)) = v;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {  // Y starts as the fp32 residual of the FFN + linear2's bias
-                        const float4 b = reinterpret_cast<const float4*>(s_b2 + col)[q];
-                        xc[4 * q] += b.x; xc[4 * q + 1] += b.y; xc[4 * q + 2] += b.z; xc[4 * q + 3] += b.w;
-                    }
-                    tmem_st_32x32(tY + 32 * c, xc);
+                for (int q = 0; q < 16; ++q) {
+                    const float4 g = reinterpret_cast<const float4*>(s_g1 + col)[q];
+                    const float4 b = reinterpret_cast<const float4*>(s_b1 + col)[q];
+                    x[4 * q] = fmaf(fmaf(x[4 * q], rstd, nm), g.x, b.x);
+                    x[4 * q + 1] = fmaf(fmaf(x[4 * q + 1], rstd, nm), g.y, b.y);
+                    x[4 * q + 2] = fmaf(fmaf(x[4 * q + 2], rstd, nm), g.z, b.z);
+                    x[4 * q + 3] = fmaf(fmaf(x[4 * q + 3], rstd, nm), g.w, b.w);
                 }
+                uint8_t* xk = sX + part * SLOT_BYTES;  // k-block `part` of the X tile
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint4 v;
+                    v.x = pack_h2(x[8 * u], x[8 * u + 1]);
+                    v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
+                    v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
+                    v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
+                    *reinterpret_cast<uint4*>(xk + sw128(row, u)) = v;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {  // Y starts as the fp32 residual of the FFN + linear2's bias
+                    const float4 b = reinterpret_cast<const float4*>(s_b2 + col)[q];
+                    x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+                }
+                tmem_st_32x32(tmemY + lane_base + col, x);
+                tmem_st_32x32(tmemY + lane_base + col + 32, x + 32);
                 tmem_st_wait();
                 fence_async_smem();
                 tc_fence_before();
@@ -454,18 +468,18 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 mbar_wait(&hfull[b], hfph[b]);
                 hfph[b] ^= 1;
                 tc_fence_after();
-                float x[64];
-                tmem_ld_32x64(tmemH + lane_base + 128 * b + 64 * half, x);
-                const float4* b4 = reinterpret_cast<const float4*>(P.b1 + c * 128 + half * 64);
-                float4 bias[16];  // issued while the TMEM load is in flight
+                float x[32];
+                tmem_ld_32x32(tmemH + lane_base + 128 * b + 32 * part, x);
+                const float4* b4 = reinterpret_cast<const float4*>(P.b1 + c * 128 + 32 * part);
+                float4 bias[8];  // issued while the TMEM load is in flight
 #pragma unroll
-                for (int q = 0; q < 16; ++q) bias[q] = __ldg(b4 + q);
+                for (int q = 0; q < 8; ++q) bias[q] = __ldg(b4 + q);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive(&htfree[b]);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     const float4 bb = bias[q];
                     x[4 * q] = fmaxf(x[4 * q] + bb.x, 0.f);
                     x[4 * q + 1] = fmaxf(x[4 * q + 1] + bb.y, 0.f);
@@ -476,15 +490,15 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     mbar_wait(&hsfree[b], hsph[b]);
                     hsph[b] ^= 1;
                 }
-                uint8_t* hk = sH + b * HB_BYTES + half * SLOT_BYTES;
+                uint8_t* hk = sH + b * HB_BYTES + (part >> 1) * SLOT_BYTES;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     uint4 v;
                     v.x = pack_h2(x[8 * u], x[8 * u + 1]);
                     v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
                     v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
                     v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
-                    *reinterpret_cast<uint4*>(hk + sw128(row, u)) = v;
+                    *reinterpret_cast<uint4*>(hk + sw128(row, (part & 1) * 4 + u)) = v;
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -494,74 +508,59 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             mbar_wait(yfull, p);
             tc_fence_after();
             {
-                const uint32_t tY = tmemY + lane_base + half * 128;
-                float x[128];
-                tmem_ld_32x64(tY, x);
-                tmem_ld_32x64(tY + 64, x + 64);
+                float x[64];
+                tmem_ld_32x64(tmemY + lane_base + col, x);
                 tmem_ld_wait();
                 tc_fence_before();  // Y is in registers: this warp's next writes to it are epi-0 of the next tile
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int j = 0; j < 128; j += 4) {
-                    s1 += (x[j] + x[j + 1]) + (x[j + 2] + x[j + 3]);
-                    s2 = fmaf(x[j], x[j], s2); s2 = fmaf(x[j + 1], x[j + 1], s2);
-                    s2 = fmaf(x[j + 2], x[j + 2], s2); s2 = fmaf(x[j + 3], x[j + 3], s2);
-                }
-                float mean, rstd;
+                float s1, s2, mean, rstd;
+                stats64(x, s1, s2);
                 row_stats(s1, s2, mean, rstd);
+                const float nm = -mean * rstd;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float4 g = reinterpret_cast<const float4*>(s_g2 + col)[q];
+                    const float4 b = reinterpret_cast<const float4*>(s_bb2 + col)[q];
+                    x[4 * q] = fmaf(fmaf(x[4 * q], rstd, nm), g.x, b.x);
+                    x[4 * q + 1] = fmaf(fmaf(x[4 * q + 1], rstd, nm), g.y, b.y);
+                    x[4 * q + 2] = fmaf(fmaf(x[4 * q + 2], rstd, nm), g.z, b.z);
+                    x[4 * q + 3] = fmaf(fmaf(x[4 * q + 3], rstd, nm), g.w, b.w);
+                }
                 const int64_t grow = (int64_t)m0 + row;
+                if (P.C32 != nullptr && grow < P.M) {
+                    float4* o4 = reinterpret_cast<float4*>(P.C32 + grow * P.ldc32 + col);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int col = half * 128 + 32 * c;
-                    float* xc = x + 32 * c;
+                    for (int q = 0; q < 16; ++q) o4[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                }
+                const uint32_t off = (uint32_t)part * SLOT_BYTES;  // k-block `part` of the staged [128 x 256] tile
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 g = reinterpret_cast<const float4*>(s_g2 + col)[q];
-                        const float4 b = reinterpret_cast<const float4*>(s_bb2 + col)[q];
-                        xc[4 * q] = (xc[4 * q] - mean) * rstd * g.x + b.x;
-                        xc[4 * q + 1] = (xc[4 * q + 1] - mean) * rstd * g.y + b.y;
-                        xc[4 * q + 2] = (xc[4 * q + 2] - mean) * rstd * g.z + b.z;
-                        xc[4 * q + 3] = (xc[4 * q + 3] - mean) * rstd * g.w + b.w;
+                for (int u = 0; u < 8; ++u) {
+                    float lo[8];
+                    uint4 v;
+                    uint32_t* vw = &v.x;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 h = __floats2half2_rn(x[8 * u + 2 * e], x[8 * u + 2 * e + 1]);
+                        const float2 f = __half22float2(h);
+                        lo[2 * e] = x[8 * u + 2 * e] - f.x;
+                        lo[2 * e + 1] = x[8 * u + 2 * e + 1] - f.y;
+                        vw[e] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    if (P.C32 != nullptr && grow < P.M) {
-                        float4* o4 = reinterpret_cast<float4*>(P.C32 + grow * P.ldc32 + col);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) o4[q] = make_float4(xc[4 * q], xc[4 * q + 1], xc[4 * q + 2], xc[4 * q + 3]);
-                    }
-                    const uint32_t off = (uint32_t)(half * 2 + (c >> 1)) * SLOT_BYTES;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float lo[8];
-                        uint4 v;
-                        uint32_t* vw = &v.x;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __half2 h = __floats2half2_rn(xc[8 * u + 2 * e], xc[8 * u + 2 * e + 1]);
-                            const float2 f = __half22float2(h);
-                            lo[2 * e] = xc[8 * u + 2 * e] - f.x;
-                            lo[2 * e + 1] = xc[8 * u + 2 * e + 1] - f.y;
-                            vw[e] = *reinterpret_cast<const uint32_t*>(&h);
-                        }
-                        *reinterpret_cast<uint4*>(sX + off + sw128(row, (c & 1) * 4 + u)) = v;
-                        if (P.has_lo_out) {
-                            uint4 w;
-                            w.x = pack_h2(lo[0], lo[1]);
-                            w.y = pack_h2(lo[2], lo[3]);
-                            w.z = pack_h2(lo[4], lo[5]);
-                            w.w = pack_h2(lo[6], lo[7]);
-                            *reinterpret_cast<uint4*>(sH + off + sw128(row, (c & 1) * 4 + u)) = w;
-                        }
+                    *reinterpret_cast<uint4*>(sX + off + sw128(row, u)) = v;
+                    if (P.has_lo_out) {
+                        uint4 w;
+                        w.x = pack_h2(lo[0], lo[1]);
+                        w.y = pack_h2(lo[2], lo[3]);
+                        w.z = pack_h2(lo[4], lo[5]);
+                        w.w = pack_h2(lo[6], lo[7]);
+                        *reinterpret_cast<uint4*>(sH + off + sw128(row, u)) = w;
                     }
                 }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    for (int kbi = 0; kbi < 2; ++kbi) {
-                        const int kblock = half * 2 + kbi;
-                        const uint32_t off = (uint32_t)kblock * SLOT_BYTES + (uint32_t)quarter * 4096u;
-                        tma_store_2d(&tmOhi, sX + off, kblock * 64, m0 + quarter * 32);
-                        if (P.has_lo_out) tma_store_2d(&tmOlo, sH + off, kblock * 64, m0 + quarter * 32);
-                    }
+                    const uint32_t boff = off + (uint32_t)quarter * 4096u;
+                    tma_store_2d(&tmOhi, sX + boff, part * 64, m0 + quarter * 32);
+                    if (P.has_lo_out) tma_store_2d(&tmOlo, sH + boff, part * 64, m0 + quarter * 32);
                     tma_store_commit();
                 }
             }
