@@ -251,8 +251,10 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             const uint32_t id256 = et_idesc(128 * CG, 256), id128 = et_idesc(128 * CG, 128), id64 = et_idesc(128 * CG, 64);
             int slot = 0;
             uint32_t ph = 0;
-            const uint32_t ring_addr = smem_u32(sRing), x_addr = smem_u32(sX), h_addr = smem_u32(sH), i_addr = smem_u32(sI);
-            const uint64_t desc_hi = smem_desc_sw128(0);  // everything but the 14-bit start-address field
+            // descriptor `lo` words (start address >> 4): byte offsets below are added as (bytes >> 4)
+            const uint32_t ring_addr = desc_lo_sw128(smem_u32(sRing)), x_addr = desc_lo_sw128(smem_u32(sX)),
+                           h_addr = desc_lo_sw128(smem_u32(sH)), i_addr = desc_lo_sw128(smem_u32(sI));
+            constexpr uint32_t SLOT16 = SLOT_BYTES >> 4, HB16 = HB_BYTES >> 4;
             auto take = [&]() -> int {  // next ring item has landed (in both CTAs of the pair)
                 mbar_wait(&full[slot], ph);
                 tc_fence_after();
@@ -263,15 +265,14 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 }
                 return s;
             };
-            auto desc = [&](uint32_t addr) -> uint64_t { return desc_hi | (uint64_t)((addr & 0x3FFFF) >> 4); };
-            auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool acc_first) {
-                // the four K = 16 steps of one 64-column k-block
+            auto mma4 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc_first) {
+                // the four K = 16 steps of one 64-column k-block: +32 bytes = +2 in the start-address field
                 if (elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t acc = (acc_first || k > 0) ? 1u : 0u;
-                        if (CG == 1) umma_f16(d, desc(a_addr + k * 32), desc(b_addr + k * 32), idesc, acc);
-                        else umma_f16_pair(d, desc(a_addr + k * 32), desc(b_addr + k * 32), idesc, acc);
+                        if (CG == 1) umma_f16_lo(d, a_lo + 2 * k, b_lo + 2 * k, idesc, acc);
+                        else umma_f16_pair_lo(d, a_lo + 2 * k, b_lo + 2 * k, idesc, acc);
                     }
                 }
                 __syncwarp();
@@ -286,8 +287,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             auto gemm0 = [&]() {
                 for (int kb = 0; kb < 4; ++kb) {
                     const int ia = take(), ib0 = take(), ib1 = (CG == 1) ? take() : 0;
-                    const uint32_t a = ring_addr + ia * SLOT_BYTES, b0 = ring_addr + ib0 * SLOT_BYTES,
-                                   b1 = ring_addr + ib1 * SLOT_BYTES;
+                    const uint32_t a = ring_addr + ia * SLOT16, b0 = ring_addr + ib0 * SLOT16, b1 = ring_addr + ib1 * SLOT16;
                     if (CG == 1) {
                         mma4(tmemH, a, b0, id128, kb > 0);
                         mma4(tmemH + 128, a, b1, id128, kb > 0);
@@ -300,7 +300,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 }
                 for (int j = 0; j < nres; ++j) {  // + res_hi (+ res_lo): 64 columns at a time against the identity tile
                     const int ia = take();
-                    mma4(tmemH + 64 * (j & 3), ring_addr + ia * SLOT_BYTES, i_addr, id64, true);
+                    mma4(tmemH + 64 * (j & 3), ring_addr + ia * SLOT16, i_addr, id64, true);
                     commit(&empty[ia]);
                 }
                 commit(g0full);
@@ -310,14 +310,14 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 if (CG == 1) {
                     for (int kb = 0; kb < 4; ++kb) {
                         const int ib = take();
-                        mma4(d, x_addr + kb * SLOT_BYTES, ring_addr + ib * SLOT_BYTES, id128, kb > 0);
+                        mma4(d, x_addr + kb * SLOT16, ring_addr + ib * SLOT16, id128, kb > 0);
                         commit(&empty[ib]);
                     }
                 } else {
                     for (int kp = 0; kp < 2; ++kp) {  // one slot = k-blocks 2 kp, 2 kp + 1 of this CTA's 64 rows
                         const int ib = take();
-                        mma4(d, x_addr + (2 * kp) * SLOT_BYTES, ring_addr + ib * SLOT_BYTES, id128, kp > 0);
-                        mma4(d, x_addr + (2 * kp + 1) * SLOT_BYTES, ring_addr + ib * SLOT_BYTES + SLOT_BYTES / 2, id128, true);
+                        mma4(d, x_addr + (2 * kp) * SLOT16, ring_addr + ib * SLOT16, id128, kp > 0);
+                        mma4(d, x_addr + (2 * kp + 1) * SLOT16, ring_addr + ib * SLOT16 + SLOT16 / 2, id128, true);
                         commit(&empty[ib]);
                     }
                 }
@@ -326,8 +326,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             auto gemm2 = [&](int c) {  // Y += H[c & 1] . W2[:, c]^T
                 for (int kb = 0; kb < 2; ++kb) {
                     const int ib0 = take(), ib1 = (CG == 1) ? take() : 0;
-                    const uint32_t a = h_addr + (c & 1) * HB_BYTES + kb * SLOT_BYTES, b0 = ring_addr + ib0 * SLOT_BYTES,
-                                   b1 = ring_addr + ib1 * SLOT_BYTES;
+                    const uint32_t a = h_addr + (c & 1) * HB16 + kb * SLOT16, b0 = ring_addr + ib0 * SLOT16, b1 = ring_addr + ib1 * SLOT16;
                     if (CG == 1) {
                         mma4(tmemY, a, b0, id128, true);
                         mma4(tmemY + 128, a, b1, id128, true);

@@ -208,7 +208,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~120 issue cycles per MMA, tc_ptx.cuh).
             // instruction descriptor: D fp32, A/B fp16 K-major, N = BN, M = 128
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            const uint64_t desc_hi = smem_desc_sw128(0);
+            const uint32_t a_lo0 = desc_lo_sw128(smem_u32(sA)), b_lo0 = desc_lo_sw128(smem_u32(sB));
             const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // warp-uniform for the compiler
             int stage = 0;
             uint32_t phase = 0;
@@ -222,15 +222,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + (WRES ? kb : stage) * B_BYTES);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(WRES ? kb : stage) * (B_BYTES >> 4);
                     if (elect_one_sync()) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t da = desc_hi | (uint64_t)(((a_addr + k * UMMA_K * 2) & 0x3FFFF) >> 4);
-                            const uint64_t db = desc_hi | (uint64_t)(((b_addr + k * UMMA_K * 2) & 0x3FFFF) >> 4);
-                            umma_f16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        }
+                        for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes per K = 16 step = +2 in the start-address field
+                            umma_f16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
                         if (kb == num_k - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
                     }

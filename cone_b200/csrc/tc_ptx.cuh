@@ -153,6 +153,40 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// Descriptor-lean MMA issue.  A shared-memory matrix descriptor is {lo = start address >> 4 in bits 0-13 | LBO << 16,
+// hi = SBO | version | swizzle}: only the 14-bit start-address field changes between the K = 16 steps of a k-block (+2
+// per 32 bytes) and between tiles, so the issuing warp keeps `lo` words and adds small constants instead of re-deriving
+// every 64-bit descriptor from a byte address (4 uniform-datapath ops per operand per MMA in the SASS of the plain form).
+constexpr uint32_t kDescHiSw128 = (uint32_t)((((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) >> 32);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+        : "memory");
+}
+
 // ---- thread-block-cluster / cta_group::2 forms (enc_tail.cu) --------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

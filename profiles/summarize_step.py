@@ -63,7 +63,19 @@ print(out)
 print(f"\ntotal device time of the captured launches: {tot / 1e3:.2f} ms over {len(launch)} launches")
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write(out + f"\n\ntotal device time of the captured launches: {tot / 1e3:.2f} ms over {len(launch)} launches\n")
-if len(sys.argv) > 3 and traffic:
-    json.dump({"gemm_tc": traffic["gemm_tc_bytes"] / traffic["gemm_tc_launches"], "launches": traffic["gemm_tc_launches"],
-               "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, average per tc_gemm_kernel launch of one bench.py step "
-                         "(default workload: 640 queries x 30 windows)"}, open(sys.argv[3], "w"))
+if len(sys.argv) > 3:
+    # DRAM traffic of the step and per kernel category (bench.py's profile categories), for bench.py's `roofline.traffic`
+    cats = {"enc_tail": "enc_tail_kernel", "gemm_tc": "tc_gemm_kernel", "enc_attention": "enc_attention_f16_kernel",
+            "dec_attention": "dec_cross_attention_mem_kernel", "gemm_fp32": "sgemm_nt_kernel"}
+    kern = {}
+    for cat, pat in cats.items():
+        ds = [d for d in launch.values() if pat in d["name"]]
+        if ds:
+            by = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in ds)
+            kern[cat] = {"launches": len(ds), "dram_bytes_per_launch": by / len(ds),
+                         "time_us_per_launch": sum(d.get("gpu__time_duration.sum", 0) for d in ds) / len(ds)}
+    step_bytes = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in launch.values())
+    json.dump({"step_dram_bytes": step_bytes, "kernels": kern, "launches": len(launch),
+               "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE bench.py step (default "
+                         "workload: 640 queries x 30 windows; --step 1 of a `--steps 1 --warmup 1` capture)"},
+              open(sys.argv[3], "w"), indent=1)
