@@ -39,8 +39,9 @@ using namespace ptx;
 
 namespace {
 
-constexpr int ET_THREADS = 576;           // producer warp + MMA warp + 16 epilogue warps
+constexpr int ET_THREADS = 608;           // producer warp + MMA warp A + 16 epilogue warps + MMA warp B
 constexpr int ET_EPI_WARPS = 16;
+constexpr int ET_MMA_B_WARP = 18;
 constexpr int ET_D = 256;               // model width (rows of 256 fp16 = 4 k-blocks of 64)
 constexpr int SLOT_BYTES = 16384;       // one [128 x 64] fp16 box, 128-byte swizzle
 constexpr int NSLOT = 5;
@@ -244,10 +245,17 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 if (has_next) emit_gemm0(m_next);
             }
         }
-    } else if (warp == 1) {
-        if (leader) {  // ------------------------------------------------------------------------------------ MMA issuer
-            // The WHOLE warp runs this role (uniform control flow, waits included); one elected lane issues the
-            // tcgen05 instructions.  Descriptors are built from warp-uniform values only.
+    } else if (warp == 1 || warp == ET_MMA_B_WARP) {
+        if (leader) {  // ------------------------------------------------------------------------------------ MMA issuers
+            // TWO issuing warps.  ncu on the single-issuer version: operands always landed (0 retries on the ring's `full`
+            // barriers), epilogue hand-offs always ready (0 retries on htfree / hready), tensor pipe 51 % busy — the issuing
+            // warp itself (barrier try_wait ~90 cycles even when complete, commit, descriptor set-up: ~190 warp-operations
+            // per tile) was the critical path.  Warp A issues GEMM0 and the GEMM1 chunks, warp B the GEMM2 chunks; they
+            // never touch the same accumulator and every dependency between them goes through the epilogue's barriers.
+            // Both walk the ring in the producer's order and skip the items that belong to the other warp.
+            // The WHOLE warp runs the role (uniform control flow, waits included); one elected lane issues the tcgen05
+            // instructions, so that descriptors stay in uniform registers.
+            const bool is_a = (warp == 1);
             const uint32_t id256 = et_idesc(128 * CG, 256), id128 = et_idesc(128 * CG, 128), id64 = et_idesc(128 * CG, 64);
             int slot = 0;
             uint32_t ph = 0;
@@ -255,6 +263,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             const uint32_t ring_addr = desc_lo_sw128(smem_u32(sRing)), x_addr = desc_lo_sw128(smem_u32(sX)),
                            h_addr = desc_lo_sw128(smem_u32(sH)), i_addr = desc_lo_sw128(smem_u32(sI));
             constexpr uint32_t SLOT16 = SLOT_BYTES >> 4, HB16 = HB_BYTES >> 4;
+            constexpr int G0_ITEMS_W = (CG == 1) ? 12 : 8, G1_ITEMS = (CG == 1) ? 4 : 2, G2_ITEMS = (CG == 1) ? 4 : 2;
             auto take = [&]() -> int {  // next ring item has landed (in both CTAs of the pair)
                 mbar_wait(&full[slot], ph);
                 tc_fence_after();
@@ -264,6 +273,13 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     ph ^= 1;
                 }
                 return s;
+            };
+            auto skip = [&](int n) {  // items consumed by the other issuing warp
+                for (int i = 0; i < n; ++i)
+                    if (++slot == NSLOT) {
+                        slot = 0;
+                        ph ^= 1;
+                    }
             };
             auto mma4 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc_first) {
                 // the four K = 16 steps of one 64-column k-block: +32 bytes = +2 in the start-address field
@@ -337,33 +353,48 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     if (CG == 1) commit(&empty[ib1]);
                 }
             };
-            uint32_t p = 0, hrph[2] = {0, 0}, htph[2] = {0, 0};
-            if (st_begin < n_super) gemm0();
+            const int g0_items = G0_ITEMS_W + nres;
+            uint32_t p = 0, bph[2] = {0, 0};  // warp A: htfree phases, warp B: hready phases
+            if (st_begin < n_super) {
+                if (is_a) gemm0();
+                else skip(g0_items);
+            }
             for (int64_t st = st_begin; st < n_super; st += st_step) {
-                mbar_wait(xready, p);
-                tc_fence_after();
-                gemm1(0);
-                if (nchunk > 1) gemm1(1);
-                for (int c = 0; c < nchunk; ++c) {
-                    const int b = c & 1;
-                    // chunk c's accumulator is in the epilogue's registers: GEMM1 of chunk c + 2 may overwrite it and keeps
-                    // the tensor pipe busy while chunk c is still being converted
-                    mbar_wait(&htfree[b], htph[b]);
-                    htph[b] ^= 1;
+                const bool has_next = st + st_step < n_super;
+                if (is_a) {
+                    mbar_wait(xready, p);
                     tc_fence_after();
-                    if (c + 2 < nchunk) gemm1(c + 2);
-                    mbar_wait(&hready[b], hrph[b]);
-                    hrph[b] ^= 1;
-                    tc_fence_after();
-                    gemm2(c);
-                    if (c + 2 < nchunk) commit(&hsfree[b]);  // the epilogue writes chunk c + 2 into the same buffer
+                    gemm1(0);
+                    if (nchunk > 1) gemm1(1);
+                    for (int c = 0; c < nchunk; ++c) {
+                        const int b = c & 1;
+                        // chunk c's accumulator is in the epilogue's registers: GEMM1 of chunk c + 2 may overwrite it
+                        mbar_wait(&htfree[b], bph[b]);
+                        bph[b] ^= 1;
+                        tc_fence_after();
+                        if (c + 2 < nchunk) gemm1(c + 2);
+                        skip(G2_ITEMS);
+                    }
+                    if (has_next) gemm0();  // overlaps the final epilogue of this tile
+                } else {
+                    skip(G1_ITEMS);
+                    if (nchunk > 1) skip(G1_ITEMS);
+                    for (int c = 0; c < nchunk; ++c) {
+                        const int b = c & 1;
+                        if (c + 2 < nchunk) skip(G1_ITEMS);
+                        mbar_wait(&hready[b], bph[b]);  // the fp16 chunk is in shared memory (and Y holds this tile's residual)
+                        bph[b] ^= 1;
+                        tc_fence_after();
+                        gemm2(c);
+                        if (c + 2 < nchunk) commit(&hsfree[b]);  // the epilogue writes chunk c + 2 into the same buffer
+                    }
+                    commit(yfull);
+                    if (has_next) skip(g0_items);
                 }
-                commit(yfull);
-                if (st + st_step < n_super) gemm0();  // overlaps the final epilogue of this tile
                 p ^= 1;
             }
         }
-    } else {  // ------------------------------------------------------------------------------------------ epilogue warps
+    } else if (warp >= 2 && warp < 2 + ET_EPI_WARPS) {  // ------------------------------------------------ epilogue warps
         // 16 warps: four per TMEM lane quarter, each owning a quarter of the columns (64 of the 256-wide row in the
         // LayerNorm epilogues, 32 of a 128-wide hidden chunk).  These phases are dependent chains (TMEM load -> math ->
         // convert -> store) that two warps per scheduler cannot keep busy: with 8 warps ncu showed 15 500 cycles per tile
