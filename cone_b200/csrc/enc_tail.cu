@@ -39,12 +39,14 @@ using namespace ptx;
 
 namespace {
 
-constexpr int ET_THREADS = 608;           // producer warp + MMA warp A + 16 epilogue warps + MMA warp B
+constexpr int ET_THREADS = 640;           // producer A + MMA warp A + 16 epilogue warps + MMA warp B + producer B
 constexpr int ET_EPI_WARPS = 16;
 constexpr int ET_MMA_B_WARP = 18;
+constexpr int ET_PROD_B_WARP = 19;
 constexpr int ET_D = 256;               // model width (rows of 256 fp16 = 4 k-blocks of 64)
 constexpr int SLOT_BYTES = 16384;       // one [128 x 64] fp16 box, 128-byte swizzle
 constexpr int NSLOT = 5;
+constexpr int NSLOT_A = 3;             // ring slots of MMA warp A's items (GEMM0, GEMM1); the other 2 carry GEMM2's
 constexpr int XT_BYTES = 4 * SLOT_BYTES;   // X tile [128 x 256] fp16
 constexpr int HB_BYTES = 2 * SLOT_BYTES;   // one hidden chunk [128 x 128] fp16
 constexpr int I64_BYTES = 64 * 128;
@@ -165,62 +167,68 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
     constexpr uint32_t tmem_base = 0u;
     constexpr uint32_t tmemY = tmem_base, tmemH = tmem_base + 256;
 
-    if (warp == 0) {
-        if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producer
-            int slot = 0;
-            uint32_t ph = 0;
-            auto emit = [&](const CUtensorMap* map, int c0, int c1, uint32_t bytes) {
-                mbar_wait(&empty[slot], ph ^ 1);
+    if (warp == 0 || warp == ET_PROD_B_WARP) {
+        if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producers
+            // Two sub-rings with their own cursors: slots [0, NSLOT_A) carry the items of MMA warp A (GEMM0, GEMM1), slots
+            // [NSLOT_A, NSLOT) those of warp B (GEMM2).  (With ONE ring shared by two consumers a consumer that skips the
+            // other's items can get a whole lap ahead of an item that has not landed yet, and a parity wait on that slot
+            // then passes at once: the first two-issuer build failed exactly so.)
+            int slot[2] = {0, NSLOT_A};
+            uint32_t ph[2] = {0, 0};
+            auto advance = [&](int r) {
+                if (++slot[r] == (r == 0 ? NSLOT_A : NSLOT)) {
+                    slot[r] = (r == 0 ? 0 : NSLOT_A);
+                    ph[r] ^= 1;
+                }
+            };
+            auto emit = [&](int r, const CUtensorMap* map, int c0, int c1, uint32_t bytes) {
+                const int sl = slot[r];
+                mbar_wait(&empty[sl], ph[r] ^ 1);
                 if (CG == 1) {
-                    mbar_expect_tx(&full[slot], bytes);
-                    tma_load_2d(sRing + slot * SLOT_BYTES, map, &full[slot], c0, c1);
+                    mbar_expect_tx(&full[sl], bytes);
+                    tma_load_2d(sRing + sl * SLOT_BYTES, map, &full[sl], c0, c1);
                 } else {
-                    mbar_expect_tx_leader(&full[slot], bytes);
-                    tma_load_2d_pair(sRing + slot * SLOT_BYTES, map, &full[slot], c0, c1);
+                    mbar_expect_tx_leader(&full[sl], bytes);
+                    tma_load_2d_pair(sRing + sl * SLOT_BYTES, map, &full[sl], c0, c1);
                 }
-                if (++slot == NSLOT) {
-                    slot = 0;
-                    ph ^= 1;
-                }
+                advance(r);
             };
             auto emit_gemm0 = [&](int m0) {
                 for (int kb = 0; kb < 4; ++kb) {
-                    emit(&tmAtt, kb * 64, m0, SLOT_BYTES);
+                    emit(0, &tmAtt, kb * 64, m0, SLOT_BYTES);
                     if (CG == 1) {
-                        emit(&tmWo, kb * 64, 0, SLOT_BYTES);
-                        emit(&tmWo, kb * 64, 128, SLOT_BYTES);
+                        emit(0, &tmWo, kb * 64, 0, SLOT_BYTES);
+                        emit(0, &tmWo, kb * 64, 128, SLOT_BYTES);
                     } else {
-                        emit(&tmWo, kb * 64, 128 * (int)rank, SLOT_BYTES);
+                        emit(0, &tmWo, kb * 64, 128 * (int)rank, SLOT_BYTES);
                     }
                 }
-                for (int kb = 0; kb < 4; ++kb) emit(&tmRhi, kb * 64, m0, SLOT_BYTES);
+                for (int kb = 0; kb < 4; ++kb) emit(0, &tmRhi, kb * 64, m0, SLOT_BYTES);
                 if (P.has_lo_in)
-                    for (int kb = 0; kb < 4; ++kb) emit(&tmRlo, kb * 64, m0, SLOT_BYTES);
+                    for (int kb = 0; kb < 4; ++kb) emit(0, &tmRlo, kb * 64, m0, SLOT_BYTES);
             };
             auto emit_g1 = [&](int c) {  // CG = 2: this CTA's 64 rows of the chunk, TWO k-blocks per 16 KB slot
                 if (CG == 1) {
-                    for (int kb = 0; kb < 4; ++kb) emit(&tmW1, kb * 64, c * 128, SLOT_BYTES);
+                    for (int kb = 0; kb < 4; ++kb) emit(0, &tmW1, kb * 64, c * 128, SLOT_BYTES);
                 } else {
                     for (int kp = 0; kp < 2; ++kp) {
-                        mbar_wait(&empty[slot], ph ^ 1);
-                        mbar_expect_tx_leader(&full[slot], SLOT_BYTES);
-                        tma_load_2d_pair(sRing + slot * SLOT_BYTES, &tmW1, &full[slot], (2 * kp) * 64, c * 128 + 64 * (int)rank);
-                        tma_load_2d_pair(sRing + slot * SLOT_BYTES + SLOT_BYTES / 2, &tmW1, &full[slot], (2 * kp + 1) * 64,
+                        const int sl = slot[0];
+                        mbar_wait(&empty[sl], ph[0] ^ 1);
+                        mbar_expect_tx_leader(&full[sl], SLOT_BYTES);
+                        tma_load_2d_pair(sRing + sl * SLOT_BYTES, &tmW1, &full[sl], (2 * kp) * 64, c * 128 + 64 * (int)rank);
+                        tma_load_2d_pair(sRing + sl * SLOT_BYTES + SLOT_BYTES / 2, &tmW1, &full[sl], (2 * kp + 1) * 64,
                                          c * 128 + 64 * (int)rank);
-                        if (++slot == NSLOT) {
-                            slot = 0;
-                            ph ^= 1;
-                        }
+                        advance(0);
                     }
                 }
             };
             auto emit_g2 = [&](int c) {
                 for (int kb = 0; kb < 2; ++kb) {
                     if (CG == 1) {
-                        emit(&tmW2, c * 128 + kb * 64, 0, SLOT_BYTES);
-                        emit(&tmW2, c * 128 + kb * 64, 128, SLOT_BYTES);
+                        emit(1, &tmW2, c * 128 + kb * 64, 0, SLOT_BYTES);
+                        emit(1, &tmW2, c * 128 + kb * 64, 128, SLOT_BYTES);
                     } else {
-                        emit(&tmW2, c * 128 + kb * 64, 128 * (int)rank, SLOT_BYTES);
+                        emit(1, &tmW2, c * 128 + kb * 64, 128 * (int)rank, SLOT_BYTES);
                     }
                 }
             };
@@ -231,18 +239,18 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     if (P.has_lo_in) tma_prefetch_l2_2d(&tmRlo, kb * 64, m0);
                 }
             };
-            if (st_begin < n_super) emit_gemm0((int)((st_begin * CG + rank) * 128));
-            for (int64_t st = st_begin; st < n_super; st += st_step) {
-                const bool has_next = st + st_step < n_super;
-                const int m_next = (int)(((st + st_step) * CG + rank) * 128);
-                if (has_next) prefetch_rows(m_next);
-                emit_g1(0);
-                if (nchunk > 1) emit_g1(1);
-                for (int c = 0; c < nchunk; ++c) {  // the order the MMA warp consumes: GEMM1(c + 2) before GEMM2(c)
-                    if (c + 2 < nchunk) emit_g1(c + 2);
-                    emit_g2(c);
+            if (warp == 0) {  // producer of sub-ring A: GEMM0 and GEMM1 items, in MMA warp A's order
+                if (st_begin < n_super) emit_gemm0((int)((st_begin * CG + rank) * 128));
+                for (int64_t st = st_begin; st < n_super; st += st_step) {
+                    const bool has_next = st + st_step < n_super;
+                    const int m_next = (int)(((st + st_step) * CG + rank) * 128);
+                    if (has_next) prefetch_rows(m_next);
+                    for (int c = 0; c < nchunk; ++c) emit_g1(c);
+                    if (has_next) emit_gemm0(m_next);
                 }
-                if (has_next) emit_gemm0(m_next);
+            } else {  // producer of sub-ring B: GEMM2 items
+                for (int64_t st = st_begin; st < n_super; st += st_step)
+                    for (int c = 0; c < nchunk; ++c) emit_g2(c);
             }
         }
     } else if (warp == 1 || warp == ET_MMA_B_WARP) {
@@ -252,34 +260,27 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             // warp itself (barrier try_wait ~90 cycles even when complete, commit, descriptor set-up: ~190 warp-operations
             // per tile) was the critical path.  Warp A issues GEMM0 and the GEMM1 chunks, warp B the GEMM2 chunks; they
             // never touch the same accumulator and every dependency between them goes through the epilogue's barriers.
-            // Both walk the ring in the producer's order and skip the items that belong to the other warp.
+            // Each consumes its own sub-ring of TMA slots (see the producer).
             // The WHOLE warp runs the role (uniform control flow, waits included); one elected lane issues the tcgen05
             // instructions, so that descriptors stay in uniform registers.
             const bool is_a = (warp == 1);
             const uint32_t id256 = et_idesc(128 * CG, 256), id128 = et_idesc(128 * CG, 128), id64 = et_idesc(128 * CG, 64);
-            int slot = 0;
+            const int slot_lo = is_a ? 0 : NSLOT_A, slot_hi = is_a ? NSLOT_A : NSLOT;  // this warp's sub-ring
+            int slot = slot_lo;
             uint32_t ph = 0;
             // descriptor `lo` words (start address >> 4): byte offsets below are added as (bytes >> 4)
             const uint32_t ring_addr = desc_lo_sw128(smem_u32(sRing)), x_addr = desc_lo_sw128(smem_u32(sX)),
                            h_addr = desc_lo_sw128(smem_u32(sH)), i_addr = desc_lo_sw128(smem_u32(sI));
             constexpr uint32_t SLOT16 = SLOT_BYTES >> 4, HB16 = HB_BYTES >> 4;
-            constexpr int G0_ITEMS_W = (CG == 1) ? 12 : 8, G1_ITEMS = (CG == 1) ? 4 : 2, G2_ITEMS = (CG == 1) ? 4 : 2;
-            auto take = [&]() -> int {  // next ring item has landed (in both CTAs of the pair)
+            auto take = [&]() -> int {  // next item of this warp's sub-ring has landed (in both CTAs of the pair)
                 mbar_wait(&full[slot], ph);
                 tc_fence_after();
                 const int s = slot;
-                if (++slot == NSLOT) {
-                    slot = 0;
+                if (++slot == slot_hi) {
+                    slot = slot_lo;
                     ph ^= 1;
                 }
                 return s;
-            };
-            auto skip = [&](int n) {  // items consumed by the other issuing warp
-                for (int i = 0; i < n; ++i)
-                    if (++slot == NSLOT) {
-                        slot = 0;
-                        ph ^= 1;
-                    }
             };
             auto mma4 = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc_first) {
                 // the four K = 16 steps of one 64-column k-block: +32 bytes = +2 in the start-address field
@@ -353,12 +354,8 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     if (CG == 1) commit(&empty[ib1]);
                 }
             };
-            const int g0_items = G0_ITEMS_W + nres;
             uint32_t p = 0, bph[2] = {0, 0};  // warp A: htfree phases, warp B: hready phases
-            if (st_begin < n_super) {
-                if (is_a) gemm0();
-                else skip(g0_items);
-            }
+            if (st_begin < n_super && is_a) gemm0();
             for (int64_t st = st_begin; st < n_super; st += st_step) {
                 const bool has_next = st + st_step < n_super;
                 if (is_a) {
@@ -373,15 +370,11 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                         bph[b] ^= 1;
                         tc_fence_after();
                         if (c + 2 < nchunk) gemm1(c + 2);
-                        skip(G2_ITEMS);
                     }
                     if (has_next) gemm0();  // overlaps the final epilogue of this tile
                 } else {
-                    skip(G1_ITEMS);
-                    if (nchunk > 1) skip(G1_ITEMS);
                     for (int c = 0; c < nchunk; ++c) {
                         const int b = c & 1;
-                        if (c + 2 < nchunk) skip(G1_ITEMS);
                         mbar_wait(&hready[b], bph[b]);  // the fp16 chunk is in shared memory (and Y holds this tile's residual)
                         bph[b] ^= 1;
                         tc_fence_after();
@@ -389,7 +382,6 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                         if (c + 2 < nchunk) commit(&hsfree[b]);  // the epilogue writes chunk c + 2 into the same buffer
                     }
                     commit(yfull);
-                    if (has_next) skip(g0_items);
                 }
                 p ^= 1;
             }
