@@ -126,8 +126,8 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
         mbar_init(xready, ET_EPI_WARPS * CG);  // lane 0 of every epilogue warp of the pair
         for (int i = 0; i < 2; ++i) {
             mbar_init(&hfull[i], 1);
-            mbar_init(&hready[i], ET_EPI_WARPS * CG);
-            mbar_init(&htfree[i], ET_EPI_WARPS * CG);
+            mbar_init(&hready[i], (ET_EPI_WARPS / 2) * CG);  // the 8 warps of the group that owns this chunk buffer
+            mbar_init(&htfree[i], (ET_EPI_WARPS / 2) * CG);
             mbar_init(&hsfree[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -482,49 +482,57 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 __syncwarp();
                 if (lane == 0) arrive(xready);
             }
-            // ---- epi-h: hidden chunks.  Two hand-offs per chunk: `htfree` as soon as the accumulator is in registers (the
-            // MMA warp may overwrite it with chunk c + 2 while this chunk is still being converted), `hready` once the fp16
-            // chunk is in shared memory (GEMM2 of this chunk may start).
-            for (int c = 0; c < nchunk; ++c) {
-                const int b = c & 1;
-                mbar_wait(&hfull[b], hfph[b]);
-                hfph[b] ^= 1;
-                tc_fence_after();
-                float x[32];
-                tmem_ld_32x32(tmemH + lane_base + 128 * b + 32 * part, x);
-                const float4* b4 = reinterpret_cast<const float4*>(P.b1 + c * 128 + 32 * part);
-                float4 bias[8];  // issued while the TMEM load is in flight
+            // ---- epi-h: hidden chunks.  The 16 warps form two groups of 8 (two per TMEM lane quarter, 64 columns each):
+            // group g owns chunk buffer g and converts the chunks c = g, g + 2, ...; the two groups work on consecutive
+            // chunks CONCURRENTLY, so the hand-off chain of one chunk (commit -> wake-up -> TMEM load -> convert -> store ->
+            // proxy fence -> arrive -> MMA issue) may take two chunk times instead of one before the tensor pipe waits.
+            // Two hand-offs per chunk: `htfree` as soon as the accumulator is in registers (GEMM1 of chunk c + 2 may overwrite
+            // it), `hready` once the fp16 chunk is in shared memory (GEMM2 of this chunk may start).
+            {
+                const int grp = ew >> 3;        // chunk buffer / chunk parity of this warp
+                const int hp = (ew >> 2) & 1;   // which 64 of the chunk's 128 columns
+                for (int c = grp; c < nchunk; c += 2) {
+                    const int b = grp;
+                    mbar_wait(&hfull[b], hfph[b]);
+                    hfph[b] ^= 1;
+                    tc_fence_after();
+                    float x[64];
+                    tmem_ld_32x64(tmemH + lane_base + 128 * b + 64 * hp, x);
+                    const float4* b4 = reinterpret_cast<const float4*>(P.b1 + c * 128 + 64 * hp);
+                    float4 bias[8];  // first half of the bias, issued while the TMEM load is in flight
 #pragma unroll
-                for (int q = 0; q < 8; ++q) bias[q] = __ldg(b4 + q);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) arrive(&htfree[b]);
+                    for (int q = 0; q < 8; ++q) bias[q] = __ldg(b4 + q);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive(&htfree[b]);
+                    uint32_t hv[32];  // relu(x + b1) as packed fp16 pairs
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 bb = bias[q];
-                    x[4 * q] = fmaxf(x[4 * q] + bb.x, 0.f);
-                    x[4 * q + 1] = fmaxf(x[4 * q + 1] + bb.y, 0.f);
-                    x[4 * q + 2] = fmaxf(x[4 * q + 2] + bb.z, 0.f);
-                    x[4 * q + 3] = fmaxf(x[4 * q + 3] + bb.w, 0.f);
-                }
-                if (c >= 2) {  // GEMM2 of chunk c - 2 has finished reading this shared-memory buffer
-                    mbar_wait(&hsfree[b], hsph[b]);
-                    hsph[b] ^= 1;
-                }
-                uint8_t* hk = sH + b * HB_BYTES + (part >> 1) * SLOT_BYTES;
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = bias[q];
+                        hv[2 * q] = pack_h2(fmaxf(x[4 * q] + bb.x, 0.f), fmaxf(x[4 * q + 1] + bb.y, 0.f));
+                        hv[2 * q + 1] = pack_h2(fmaxf(x[4 * q + 2] + bb.z, 0.f), fmaxf(x[4 * q + 3] + bb.w, 0.f));
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 v;
-                    v.x = pack_h2(x[8 * u], x[8 * u + 1]);
-                    v.y = pack_h2(x[8 * u + 2], x[8 * u + 3]);
-                    v.z = pack_h2(x[8 * u + 4], x[8 * u + 5]);
-                    v.w = pack_h2(x[8 * u + 6], x[8 * u + 7]);
-                    *reinterpret_cast<uint4*>(hk + sw128(row, (part & 1) * 4 + u)) = v;
+                    for (int q = 0; q < 8; ++q) bias[q] = __ldg(b4 + 8 + q);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = bias[q];
+                        hv[16 + 2 * q] = pack_h2(fmaxf(x[32 + 4 * q] + bb.x, 0.f), fmaxf(x[32 + 4 * q + 1] + bb.y, 0.f));
+                        hv[16 + 2 * q + 1] = pack_h2(fmaxf(x[32 + 4 * q + 2] + bb.z, 0.f), fmaxf(x[32 + 4 * q + 3] + bb.w, 0.f));
+                    }
+                    if (c >= 2) {  // GEMM2 of chunk c - 2 has finished reading this shared-memory buffer
+                        mbar_wait(&hsfree[b], hsph[b]);
+                        hsph[b] ^= 1;
+                    }
+                    uint8_t* hk = sH + b * HB_BYTES + hp * SLOT_BYTES;  // k-block hp of chunk buffer b
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        *reinterpret_cast<uint4*>(hk + sw128(row, u)) = make_uint4(hv[4 * u], hv[4 * u + 1], hv[4 * u + 2], hv[4 * u + 3]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) arrive(&hready[b]);
                 }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) arrive(&hready[b]);
             }
             // ---- epi-f: out = LN2(Y) -> hi (+ lo) staged in X / H -> TMA stores
             mbar_wait(yfull, p);
