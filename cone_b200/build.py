@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcone_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "tc_gemm.cu", "enc_tail.cu", "rowops.cu", "attention.cu", "prefilter.cu", "pool_match.cu",
+SOURCES = ["api.cu", "gemm_simt.cu", "tc_gemm.cu", "enc_tail.cu", "enc_attn_tc.cu", "rowops.cu", "attention.cu", "prefilter.cu", "pool_match.cu",
            "fuse_nms.cu", "eval.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -115,6 +115,7 @@ struct cone_weights {
     std::vector<float*> pos_qk;
     float* pos_kdec = nullptr;
     uint16_t* pos_kdec16 = nullptr;  // fp16 copy for the mma.sync cross-attention
+    uint16_t* pos_qk16 = nullptr;    // fp16 copy of pos_qk [enc_layers][rows][2d] for the tcgen05 attention (TMA boxes)
     // memory-direct cross-attention of the tensor-core decoder (attention.cu): per decoder layer
     //   xq_w [9 d, d], xq_b [9 d]: rows [0, d) = c Wq, rows d + h d + j = c Wk_h^T Wq_h (c = softmax scale * log2 e)
     //   xo_w [d, 8 d], xo_b [d]:   columns h d + j = Wo[:, head h] Wv_h;  xo_b = Wo bv + bo
@@ -218,6 +219,7 @@ extern "C" void cone_weights_destroy(cone_weights* w) {
     if (w->tc) tc_weights_destroy(w->tc);
     if (w->pos_proj) cudaFree(w->pos_proj);
     if (w->pos_kdec16) cudaFree(w->pos_kdec16);
+    if (w->pos_qk16) cudaFree(w->pos_qk16);
     if (w->xattn) cudaFree(w->xattn);
     if (w->blob) cudaFree(w->blob);
     if (w->derived) cudaFree(w->derived);
@@ -526,7 +528,7 @@ struct CoreBuffers {
     // depend on the window it is sliced into); when set, layer 0 runs no per-window QKV GEMM
     const uint16_t* frame_qkv = nullptr;
     const uint16_t* token_qkv = nullptr;
-    int64_t n_frames = 0;
+    int64_t n_frames = 0, n_tokens = 0;
 };
 
 // The fused encoder tail (enc_tail.cu) replaces out_proj + norm1 + linear1 + linear2 + norm2 of the tensor-core mode;
@@ -648,16 +650,30 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
         for (int l = 0; l < dm.enc_layers; ++l) {
             const std::string p = "transformer.encoder.layers." + std::to_string(l);
             TcGemmArgs g;
+            // attention on tcgen05 (enc_attn_tc.cu) where the window fits its TMEM / shared-memory plan, else mma.sync
+            const bool attn_tc = enc_attn_tc_supported(b.Lv, b.Lt, d, H);
+            const size_t pos_rows = (size_t)(dm.max_v_l + 1) * dm.max_v_l;
+            const uint16_t* pos16 = c.w->pos_qk16 + (size_t)l * pos_rows * 2 * d;
             if (l == 0 && b.frame_qkv != nullptr) {
-                CONE_TRY(enc_self_attention_f16(nullptr, 3 * d, nullptr, 3 * d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H,
-                                                c.w->pos_qk[l], dm.max_v_l, c.s, b.frame_qkv, b.token_qkv, b.vid_base,
-                                                b.txt_base, b.n_frames));
+                if (attn_tc) {
+                    CONE_TRY(enc_attn_tc_run(b.frame_qkv, b.n_frames, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, pos16, dm.max_v_l,
+                                             b.token_qkv, b.n_tokens, b.vid_base, b.txt_base, tc_num_sms(t), c.s));
+                } else {
+                    CONE_TRY(enc_self_attention_f16(nullptr, 3 * d, nullptr, 3 * d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H,
+                                                    c.w->pos_qk[l], dm.max_v_l, c.s, b.frame_qkv, b.token_qkv, b.vid_base,
+                                                    b.txt_base, b.n_frames));
+                }
             } else {
                 g = G(b.src16, d, c.w->p(p + ".self_attn.in_proj_weight"), c.w->p(p + ".self_attn.in_proj_bias"), 3 * d, d);
                 g.C16 = b.qkv16; g.ldc16 = 3 * d;
                 CONE_TRY(tc_gemm_run(t, g, c.s));
-                CONE_TRY(enc_self_attention_f16(b.qkv16, 3 * d, b.qkv16 + 2 * d, 3 * d, b.att16, d, b.vlen, b.tlen, b.B,
-                                                b.Lv, b.Lt, H, c.w->pos_qk[l], dm.max_v_l, c.s));
+                if (attn_tc) {
+                    CONE_TRY(enc_attn_tc_run(b.qkv16, R, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, pos16, dm.max_v_l, nullptr, 0,
+                                             nullptr, nullptr, tc_num_sms(t), c.s));
+                } else {
+                    CONE_TRY(enc_self_attention_f16(b.qkv16, 3 * d, b.qkv16 + 2 * d, 3 * d, b.att16, d, b.vlen, b.tlen, b.B,
+                                                    b.Lv, b.Lt, H, c.w->pos_qk[l], dm.max_v_l, c.s));
+                }
             }
             const bool last_enc = (l == dm.enc_layers - 1);
             if (fused_tail_enabled(dm)) {
@@ -860,6 +876,7 @@ int fill_pos_proj(cone_weights* mw, cudaStream_t s) {
     g.C = mw->pos_kdec; g.ldc = dm.dec_layers * d; g.M = rows; g.N = dm.dec_layers * d; g.K = d;
     CONE_TRY(sgemm_nt(g, s));
     CONE_TRY(f32_to_f16_rows(mw->pos_kdec, dm.dec_layers * d, mw->pos_kdec16, rows, (int)(dm.dec_layers * d), s));
+    CONE_TRY(f32_to_f16_rows(mw->pos_proj, 2 * d, mw->pos_qk16, rows * dm.enc_layers, (int)(2 * d), s));
     (void)dec;
     return CONE_OK;
 }
@@ -873,6 +890,7 @@ int ensure_tc(const cone_weights* w, int prec, cudaStream_t s) {
         const size_t d = dm.hidden, rows = (size_t)(dm.max_v_l + 1) * dm.max_v_l;
         CONE_CUDA(cudaMalloc(&mw->pos_proj, sizeof(float) * (rows * 2 * d * dm.enc_layers + rows * dm.dec_layers * d)));
         CONE_CUDA(cudaMalloc(&mw->pos_kdec16, sizeof(uint16_t) * rows * dm.dec_layers * d));
+        CONE_CUDA(cudaMalloc(&mw->pos_qk16, sizeof(uint16_t) * rows * 2 * d * dm.enc_layers));
         CONE_TRY(fill_pos_proj(mw, s));
     }
     return CONE_OK;
@@ -1137,6 +1155,7 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
             cb.frame_qkv = frame_qkv;
             cb.token_qkv = token_qkv;
             cb.n_frames = n_frames;
+            cb.n_tokens = n * Lt;
         }
         CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
                                         topk, Lt, Lv, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));

@@ -1,0 +1,439 @@
+// Encoder self-attention on tcgen05 (CONE_PREC_TC): nn.MultiheadAttention of `TransformerEncoderLayer.forward_post`
+// (cone/transformer.py:239), 8 heads of 32 channels over one window of S = Lv + Lt <= 190 rows, key-padding mask.
+//
+// Why a second attention kernel: the mma.sync version (attention.cu, one CTA per (window, head)) spends 4 700 SM-cycles per
+// (window, head) — LSU-bound (l1tex 86 %: every q / k / v / position value goes global -> register -> shared -> ldmatrix,
+// the score block lives in mma.sync fragments that need quad shuffles for every row maximum) — against a floor of ~1 600
+// cycles set by the 22 500 exponentials per head.  Here:
+//   * q, k, v and the position-projection rows arrive by TMA (64-byte-swizzled boxes of one head: 32 channels), no register
+//     staging; two helper warps add the position rows to q and k in place (16-byte chunks, layout-agnostic);
+//   * S = Q.K^T runs on tcgen05 (M = 128 per tile, N = padded key count, K = 32) into TMEM; softmax is ONE THREAD PER ROW
+//     on `tcgen05.ld` data: no shuffles, no fragments; P goes back to shared memory as the fp16 A operand (K-major,
+//     128-byte swizzle) and O = P.V is a second tcgen05 product with V used as it lands (MN-major B operand, no transpose);
+//   * the heads of a window are pipelined: TMA of head h+1, QK^T of head h+1 and P.V of head h overlap the softmax of head h.
+// One persistent CTA per SM, 9 warps: 0 TMA producer, 1 MMA issuer (whole warp, elect.sync), 2-3 position add,
+// 4-8 softmax / output (4-7: rows 0-127 of the window, one per TMEM lane quarter; 8: rows 128-159).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+#include <stdlib.h>
+
+#include "kernels.h"
+#include "tc_gemm.h"
+#include "tc_ptx.cuh"
+
+namespace cone {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int AT_THREADS = 288;
+constexpr int AT_HD = 32;       // head dim
+constexpr int AT_ROWB = 64;     // bytes per operand row of one head (32 fp16): the 64-byte swizzle span
+constexpr int AT_MAX_NKP = 192; // padded key count supported (TMEM: 2 x NKP + 128 <= 512)
+
+// descriptor hi word for 64-byte-swizzled operands: SBO = 8 rows x 64 B = 512 B, version 1, layout SWIZZLE_64B (= 4)
+constexpr uint32_t kDescHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+
+__device__ __forceinline__ void umma_f16_desc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct AtParams {
+    __half* out;             // [B S, ldo]
+    int64_t ldo;
+    const int32_t* vlen;
+    const int32_t* tlen;
+    const int64_t* vid_base; // layer 0: first frame row of each window (null = dense rows)
+    const int64_t* txt_base;
+    int64_t B;
+    int Lv, Lt, table_lv;
+    int nkp;                 // padded key count (multiple of 16)
+    int ntile;               // 1 or 2 query tiles of 128 rows
+    int indirect;
+    int tpad;                // layer 0 with an odd Lv: the token rows start one row later (TMA destinations are 128-byte aligned)
+};
+
+// shared-memory plan (bytes), all multiples of 1 KB
+struct AtPlan {
+    int buf;     // one operand buffer: nkp x 64
+    int stage;   // Q | K | V | PQ | PK
+    int ptile;   // one P tile: ceil(nkp / 64) k-blocks of [128 x 128 B]
+    int off_p, off_bar, total;
+};
+__host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
+    AtPlan p;
+    p.buf = ((nkp * AT_ROWB + 1023) / 1024) * 1024;
+    p.stage = 5 * p.buf;
+    p.ptile = ((nkp + 63) / 64) * 16384;
+    p.off_p = 2 * p.stage + 8192;  // slack: the second query tile's A operand reads 8 KB past rows 128.. of Q
+    p.off_bar = p.off_p + ntile * p.ptile;
+    p.total = p.off_bar + 256;
+    return p;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B S, 768] (layer 1) or frames [n_frames, 768]
+                   const __grid_constant__ CUtensorMap tmTok,   // tokens [n_tok, 768] (layer 0 only)
+                   const __grid_constant__ CUtensorMap tmPos,   // position projection [(Lv+1) Lv, 512] fp16: pos.Wq^T | pos.Wk^T
+                   AtParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    const AtPlan pl = at_plan(P.nkp, P.ntile);
+    uint8_t* sP = smem + pl.off_p;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bar);
+    uint64_t* tma_full = bars;        // [2] operands of a head have landed
+    uint64_t* qk_ready = bars + 2;    // [2] position rows added to q and k
+    uint64_t* st_free = bars + 4;     // [2] P.V of the head has finished reading the stage (and q, k were consumed before)
+    uint64_t* s_full = bars + 6;      // S = Q.K^T complete
+    uint64_t* p_ready = bars + 7;     // P in shared memory, S read out of TMEM
+    uint64_t* p_free = bars + 8;      // P.V has finished reading P
+    uint64_t* o_full = bars + 9;      // [2]
+    uint64_t* o_free = bars + 11;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = P.Lv + P.Lt, nkp = P.nkp, NT = P.ntile;
+    const int n_soft = (NT == 2) ? 5 : 4;  // softmax warps in use
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQkv)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmPos)) : "memory");
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tma_full[i], 1);
+            mbar_init(&qk_ready[i], 2);
+            mbar_init(&st_free[i], 1);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_free[i], n_soft);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, n_soft);
+        mbar_init(p_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // Rows that TMA never writes must hold finite values: V rows >= S multiply P = 0 (0 x NaN would poison the output),
+    // position rows >= Lv are added to the text rows of q and k and must be zero.
+    for (int i = threadIdx.x; i < (2 * pl.stage + 8192) / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (*tmem_slot != 0u) __trap();  // the whole TMEM belongs to this CTA: addresses below are literals
+    const uint32_t tmemS = 0u;                          // [NT][nkp] fp32 scores
+    const uint32_t tmemO = (uint32_t)(NT * nkp);        // [2][NT][32] fp32 outputs, double buffered across heads
+
+    const int64_t w_begin = blockIdx.x, w_step = gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producer
+            uint32_t it = 0;
+            const uint32_t bytes_qkv = (uint32_t)(3 * S * AT_ROWB), bytes_pos = (uint32_t)(2 * P.Lv * AT_ROWB);
+            for (int64_t w = w_begin; w < P.B; w += w_step) {
+                const int vl = P.vlen[w];
+                const int64_t vb = P.indirect ? P.vid_base[w] : w * S;
+                const int64_t tb = P.indirect ? P.txt_base[w] : 0;
+                for (int h = 0; h < 8; ++h, ++it) {
+                    const int st = it & 1;
+                    mbar_wait(&st_free[st], ((it >> 1) & 1) ^ 1);
+                    uint8_t* base = smem + st * pl.stage;
+                    mbar_expect_tx(&tma_full[st], bytes_qkv + bytes_pos);
+                    for (int m = 0; m < 3; ++m) {  // q, k, v of head h: columns m * 256 + h * 32
+                        if (P.indirect) {
+                            tma_load_2d(base + m * pl.buf, &tmQkv, &tma_full[st], m * 256 + h * AT_HD, (int)vb);
+                            tma_load_2d(base + m * pl.buf + (P.Lv + P.tpad) * AT_ROWB, &tmTok, &tma_full[st], m * 256 + h * AT_HD, (int)tb);
+                        } else {
+                            tma_load_2d(base + m * pl.buf, &tmQkv, &tma_full[st], m * 256 + h * AT_HD, (int)vb);
+                        }
+                    }
+                    // position rows of (valid length, head): pos.Wq^T then pos.Wk^T
+                    tma_load_2d(base + 3 * pl.buf, &tmPos, &tma_full[st], h * AT_HD, vl * P.table_lv);
+                    tma_load_2d(base + 4 * pl.buf, &tmPos, &tma_full[st], 256 + h * AT_HD, vl * P.table_lv);
+                }
+            }
+        }
+    } else if (warp == 1) {  // --------------------------------------------------------------------------------- MMA issuer
+        const uint32_t idS = (1u << 4) | ((uint32_t)(nkp >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                 // K-major A, B
+        const uint32_t idO = (1u << 4) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // B (= V) MN-major
+        const uint32_t base_lo = desc_lo_sw128(smem_u32(smem));  // (address >> 4) | LBO = 1
+        const uint32_t p_lo = desc_lo_sw128(smem_u32(sP));
+        uint32_t it = 0;
+        auto issue_pv = [&](uint32_t itp) {  // O = P . V of the head issued at iteration itp
+            const int st = itp & 1, ob = itp & 1;
+            mbar_wait(p_ready, itp & 1);
+            mbar_wait(&o_free[ob], ((itp >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint32_t v_lo = base_lo + (uint32_t)((st * pl.stage + 2 * pl.buf) >> 4);
+                for (int t = 0; t < NT; ++t) {
+                    const uint32_t d = tmemO + (uint32_t)((ob * NT + t) * AT_HD);
+                    for (int j = 0; j < nkp / 16; ++j) {  // 16 keys per MMA: A = P[:, 16 j ..], B = V[16 j .., :]
+                        const uint32_t a = p_lo + (uint32_t)((t * pl.ptile + (j >> 2) * 16384 + (j & 3) * 32) >> 4);
+                        const uint32_t b = v_lo + (uint32_t)((j * 16 * AT_ROWB) >> 4);
+                        umma_f16_desc(d, a, kDescHiSw128, b, kDescHiSw64, idO, j > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&o_full[ob]);
+                umma_commit(p_free);
+                umma_commit(&st_free[st]);
+            }
+            __syncwarp();
+        };
+        for (int64_t w = w_begin; w < P.B; w += w_step) {
+            for (int h = 0; h < 8; ++h, ++it) {
+                const int st = it & 1;
+                mbar_wait(&qk_ready[st], (it >> 1) & 1);
+                if (it > 0) mbar_wait(p_ready, (it - 1) & 1);  // S of the previous head has been read out of TMEM
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t q_lo = base_lo + (uint32_t)((st * pl.stage) >> 4), k_lo = q_lo + (uint32_t)(pl.buf >> 4);
+                    for (int t = 0; t < NT; ++t)
+                        for (int k = 0; k < 2; ++k)
+                            umma_f16_desc(tmemS + (uint32_t)(t * nkp), q_lo + (uint32_t)((t * 128 * AT_ROWB) >> 4) + 2 * k, kDescHiSw64,
+                                          k_lo + 2 * k, kDescHiSw64, idS, k > 0 ? 1u : 0u);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+                if (it > 0) issue_pv(it - 1);  // overlaps the softmax of this head
+            }
+        }
+        if (it > 0) issue_pv(it - 1);
+    } else if (warp < 4) {  // ------------------------------------------------------------------- position add (2 warps)
+        const int t = threadIdx.x - 64;  // 0..63
+        uint32_t it = 0;
+        for (int64_t w = w_begin; w < P.B; w += w_step) {
+            for (int h = 0; h < 8; ++h, ++it) {
+                const int st = it & 1;
+                mbar_wait(&tma_full[st], (it >> 1) & 1);
+                uint8_t* base = smem + st * pl.stage;
+                // q += pos.Wq^T, k += pos.Wk^T over the first Lv rows; the operands share one swizzled layout, so the add is
+                // chunk-wise (rows >= Lv of the position buffers are zero)
+                const int nchunk = (P.Lv * AT_ROWB + 15) / 16;
+                for (int i = t; i < 2 * nchunk; i += 64) {
+                    const int m = i >= nchunk, c = m ? i - nchunk : i;
+                    uint4* dst = reinterpret_cast<uint4*>(base + m * pl.buf) + c;
+                    const uint4 a = *dst, b = reinterpret_cast<const uint4*>(base + (3 + m) * pl.buf)[c];
+                    uint4 r;
+                    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+                    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+                    __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {  // fp32 add, one rounding (as the mma.sync kernel does)
+                        const float2 x = __half22float2(ah[e]), y = __half22float2(bh[e]);
+                        rh[e] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+                    }
+                    *dst = r;
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&qk_ready[st]);
+            }
+        }
+    } else if (warp < 4 + n_soft) {  // ------------------------------------------------------------ softmax / output warps
+        const int sw = warp - 4;                // 0..4
+        const int tile = sw >> 2;               // query tile
+        const int quarter = warp & 3;           // TMEM lane quarter (warps 4-7 -> 0-3, warp 8 -> 0)
+        const int trow = tile * 128 + quarter * 32 + lane;  // row of this thread in the operand tiles
+        const int T0 = P.Lv + P.tpad;                       // first token row in the tiles
+        // window row (= output row) of the tile row: the video rows, then the token rows; -1 = no row (gap / padding)
+        const int row = trow < P.Lv ? trow : ((trow >= T0 && trow < T0 + P.Lt) ? trow - P.tpad : -1);
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+        uint32_t it = 0;
+        float inv_prev = 0.f;
+        int64_t w_prev = 0;
+        int h_prev = 0;
+        auto write_out = [&](uint32_t itp, int64_t wq, int hq, float inv) {  // O of head hq of window wq -> global memory
+            const int ob = itp & 1;
+            mbar_wait(&o_full[ob], (itp >> 1) & 1);
+            tc_fence_after();
+            float o[32];
+            tmem_ld_32x32(tmemO + lane_base + (uint32_t)((ob * NT + tile) * AT_HD), o);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[ob]);
+            if (row >= 0) {
+                uint4* dst = reinterpret_cast<uint4*>(P.out + (wq * S + row) * P.ldo + hq * AT_HD);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 v;
+                    v.x = pack_h2(o[8 * u] * inv, o[8 * u + 1] * inv);
+                    v.y = pack_h2(o[8 * u + 2] * inv, o[8 * u + 3] * inv);
+                    v.z = pack_h2(o[8 * u + 4] * inv, o[8 * u + 5] * inv);
+                    v.w = pack_h2(o[8 * u + 6] * inv, o[8 * u + 7] * inv);
+                    dst[u] = v;
+                }
+            }
+        };
+        for (int64_t w = w_begin; w < P.B; w += w_step) {
+            const int vl = P.vlen[w], tl = P.tlen[w];
+            for (int h = 0; h < 8; ++h, ++it) {
+                mbar_wait(s_full, it & 1);
+                tc_fence_after();
+                const uint32_t tS = tmemS + lane_base + (uint32_t)(tile * nkp);
+                // pass 1: row maximum over the valid keys
+                float mx = -CUDART_INF_F;
+                for (int c = 0; c < nkp; c += 32) {
+                    float s[32];
+                    tmem_ld_32x32(tS + c, s);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int key = c + j;
+                        const bool ok = key < vl || (key >= T0 && key < T0 + tl);
+                        mx = fmaxf(mx, ok ? s[j] : -CUDART_INF_F);
+                    }
+                }
+                const float off = (mx == -CUDART_INF_F) ? 0.f : -mx * sl2;
+                // pass 2: p = exp2(s * sl2 - max * sl2) as fp16 -> P tile (K-major, 128-byte swizzle); the row sum is taken over
+                // the rounded values that multiply V
+                if (it > 0) mbar_wait(p_free, (it - 1) & 1);  // P.V of the previous head has finished reading P
+                float sum = 0.f;
+                uint8_t* prow = sP + tile * pl.ptile;
+                const int r128 = quarter * 32 + lane;  // row inside the tile
+                for (int c = 0; c < nkp; c += 32) {
+                    float s[32];
+                    tmem_ld_32x32(tS + c, s);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const int key = c + j;
+                        const bool ok0 = key < vl || (key >= T0 && key < T0 + tl);
+                        const bool ok1 = (key + 1) < vl || ((key + 1) >= T0 && (key + 1) < T0 + tl);
+                        const float p0 = ok0 ? ex2_approx(fmaf(s[j], sl2, off)) : 0.f;
+                        const float p1 = ok1 ? ex2_approx(fmaf(s[j + 1], sl2, off)) : 0.f;
+                        const __half2 hh = __floats2half2_rn(p0, p1);
+                        const float2 f = __half22float2(hh);
+                        sum += f.x + f.y;
+                        pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    uint8_t* kb = prow + (c >> 6) * 16384;  // k-block of 64 keys
+                    const int u0 = (c & 63) >> 3;           // first 16-byte unit (8 keys) inside the 128-byte row
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(kb + sw128(r128, u0 + u)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                }
+                tc_fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_ready);
+                // the previous head's output, while the tensor pipe works on this head's P.V and the next head's scores
+                if (it > 0) write_out(it - 1, w_prev, h_prev, inv_prev);
+                inv_prev = 1.f / sum;
+                w_prev = w;
+                h_prev = h;
+            }
+        }
+        if (it > 0) write_out(it - 1, w_prev, h_prev, inv_prev);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "r"(512u) : "memory");
+    }
+}
+
+// 2-D map with a 64-byte inner box (one head: 32 fp16) and the 64-byte swizzle
+int make_map_sw64(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return CONE_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)AT_HD, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (64-byte swizzle) failed (%d) for [%lld x %lld] ld %lld box %d", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld, box_rows);
+        return CONE_ERR_CUDA;
+    }
+    return CONE_OK;
+}
+
+}  // namespace
+
+bool enc_attn_tc_supported(int Lv, int Lt, int d_model, int nheads) {
+    const int S = Lv + Lt + (Lv & 1), nkp = (S + 15) & ~15, nt = (S + 127) / 128;
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("CONE_ATTN_TC");
+        env = (e && e[0] == '0') ? 0 : 1;
+    }
+    return env == 1 && d_model == 256 && nheads == 8 && nkp <= AT_MAX_NKP && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
+           nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt).total <= 232448;
+}
+
+int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv,
+                    int Lt, const void* posqk16, int table_lv, const void* token_qkv, int64_t n_tok, const int64_t* vid_base,
+                    const int64_t* txt_base, int num_sms, cudaStream_t s) {
+    if (B == 0) return CONE_OK;
+    const int S = Lv + Lt;
+    const int nkp = (S + (Lv & 1) + 15) & ~15, nt = (S + (Lv & 1) + 127) / 128;  // sized for the layer-0 form (gap row)
+    CONE_REQUIRE(enc_attn_tc_supported(Lv, Lt, 256, 8), "enc_attn_tc: unsupported window %d + %d", Lv, Lt);
+    CONE_REQUIRE((ldo % 8) == 0, "enc_attn_tc: output rows must be 16-byte aligned");
+    const bool indirect = token_qkv != nullptr;
+    CONE_REQUIRE(!indirect || (vid_base && txt_base && n_tok > 0), "enc_attn_tc: incomplete row tables");
+    CUtensorMap mQ, mT, mP;
+    // dense: one box of S rows; indirect: Lv frame rows + Lt token rows
+    CONE_TRY(make_map_sw64(&mQ, qkv, rows, 768, 768, indirect ? Lv : S));
+    mT = mQ;
+    if (indirect) CONE_TRY(make_map_sw64(&mT, token_qkv, n_tok, 768, 768, Lt));
+    CONE_TRY(make_map_sw64(&mP, posqk16, (int64_t)(table_lv + 1) * table_lv, 512, 512, Lv));
+    AtParams P{};
+    P.out = static_cast<__half*>(o);
+    P.ldo = ldo;
+    P.vlen = vlen; P.tlen = tlen; P.vid_base = vid_base; P.txt_base = txt_base;
+    P.B = B; P.Lv = Lv; P.Lt = Lt; P.table_lv = table_lv; P.nkp = nkp; P.ntile = nt; P.indirect = indirect ? 1 : 0;
+    P.tpad = indirect ? (Lv & 1) : 0;
+    const AtPlan pl = at_plan(nkp, nt);
+    static int smem_set = 0;
+    if (smem_set < pl.total) {
+        CONE_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
+        smem_set = pl.total;
+    }
+    const unsigned grid = (unsigned)(B < num_sms ? B : num_sms);
+    ProfScope ps(s, P_ENC_ATTN, 4.0 * (double)B * 8 * S * S * AT_HD, 8.0 * (double)B * S * 8 * AT_HD);
+    enc_attn_tc_kernel<<<grid, AT_THREADS, pl.total, s>>>(mQ, mT, mP, P);
+    CONE_LAUNCH_CHECK("enc_attn_tc");
+    return CONE_OK;
+}
+
+}  // namespace cone

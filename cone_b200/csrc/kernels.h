@@ -76,6 +76,12 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
                            const float* posqk, int table_lv, cudaStream_t s, const void* frame_qkv = nullptr,
                            const void* token_qkv = nullptr, const int64_t* vid_base = nullptr,
                            const int64_t* txt_base = nullptr, int64_t n_frames = 0);
+// tcgen05 version (enc_attn_tc.cu): qkv = dense window rows [B S, 768] (token_qkv null) or the per-frame rows [rows, 768] with
+// token_qkv [n_tok, 768] and the window descriptors; posqk16 = fp16 copy of the position-projection table
+bool enc_attn_tc_supported(int Lv, int Lt, int d_model, int nheads);
+int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv,
+                    int Lt, const void* posqk16, int table_lv, const void* token_qkv, int64_t n_tok, const int64_t* vid_base,
+                    const int64_t* txt_base, int num_sms, cudaStream_t s);
 // frame_qkv / token_qkv (nullable): fp16 q|k|v rows [n, 3 d] of every frame / token; window row r then reads
 // frame vid_base[b] + r (r < Lv) or token txt_base[b] + r - Lv instead of qk / v
 // decoder self-attention over nq slots (no mask)
