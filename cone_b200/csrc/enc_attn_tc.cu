@@ -179,9 +179,9 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
         const uint32_t base_lo = desc_lo_sw128(smem_u32(smem));  // (address >> 4) | LBO = 1
         const uint32_t p_lo = desc_lo_sw128(smem_u32(sP));
         uint32_t it = 0;
-        auto issue_pv = [&](uint32_t itp) {  // O = P . V of the head issued at iteration itp
+        auto issue_pv = [&](uint32_t itp, bool wait_p) {  // O = P . V of the head issued at iteration itp
             const int st = itp & 1, ob = itp & 1;
-            mbar_wait(p_ready, itp & 1);
+            if (wait_p) mbar_wait(p_ready, itp & 1);  // (the main loop has already waited: never wait twice on a parity)
             mbar_wait(&o_free[ob], ((itp >> 1) & 1) ^ 1);
             tc_fence_after();
             if (elect_one_sync()) {
@@ -215,10 +215,10 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                     umma_commit(s_full);
                 }
                 __syncwarp();
-                if (it > 0) issue_pv(it - 1);  // overlaps the softmax of this head
+                if (it > 0) issue_pv(it - 1, false);  // overlaps the softmax of this head
             }
         }
-        if (it > 0) issue_pv(it - 1);
+        if (it > 0) issue_pv(it - 1, true);
     } else if (warp < 4) {  // ------------------------------------------------------------------- position add (2 warps)
         const int t = threadIdx.x - 64;  // 0..63
         uint32_t it = 0;
