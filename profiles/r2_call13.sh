@@ -3,7 +3,7 @@
 LOG=gpurun_out/r2_call13.log
 mkdir -p gpurun_out; : > $LOG
 source profiles/gpu_guard.sh
-timeout 240 python -m pytest tests/test_gpu_tc.py -k "dense_vs_oracle or other_window" -x -q -s > gpurun_out/r2_pytest13a.log 2>&1
+timeout 240 python -m pytest tests/test_gpu_tc.py -k "dense_vs_oracle or other_window or end_to_end" -x -q -s > gpurun_out/r2_pytest13a.log 2>&1
 rc=$?; echo "pytest dense rc=$rc" >> $LOG; tail -25 gpurun_out/r2_pytest13a.log >> $LOG
 if [ $rc != 0 ]; then
   echo "--- same tests with CONE_ATTN_TC=0 (mma.sync attention)" >> $LOG
@@ -11,7 +11,7 @@ if [ $rc != 0 ]; then
   echo "pytest dense (old attention) rc=$?" >> $LOG
   tail -60 $LOG; exit 1
 fi
-timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_localizer.py tests/test_localizer.py -m gpu -x -q -s > gpurun_out/r2_pytest13c.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_localizer.py tests/test_gpu_parity.py -m gpu -x -q -s > gpurun_out/r2_pytest13c.log 2>&1
 rc=$?; echo "pytest tc rc=$rc" >> $LOG
 grep -E "^\[|passed|failed|FAILED|Error" gpurun_out/r2_pytest13c.log | head -30 >> $LOG
 if [ $rc != 0 ]; then tail -60 $LOG; exit 1; fi
