@@ -31,8 +31,8 @@ namespace {
 constexpr int AT_THREADS = 288;
 constexpr int AT_HD = 32;       // head dim
 constexpr int AT_ROWB = 64;     // bytes per operand row of one head (32 fp16): the 64-byte swizzle span
-constexpr int AT_OW = 48;       // TMEM columns per (head buffer, tile): 32 outputs + 16 row-sum columns
-constexpr int AT_MAX_NKP = 160; // padded key count supported with two query tiles (TMEM: 2 x NKP + 4 x 48 <= 512)
+constexpr int AT_MAX_NKP = 192; // padded key count supported (TMEM: 2 x NKP + 128 <= 512)
+constexpr int AT_SOFT = 5;      // softmax warps: 4-7 = rows 0-127 (one per TMEM lane quarter), 8 = rows 128-159
 
 // descriptor hi word for 64-byte-swizzled operands: SBO = 8 rows x 64 B = 512 B, version 1, layout SWIZZLE_64B (= 4)
 constexpr uint32_t kDescHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
@@ -78,7 +78,7 @@ struct AtPlan {
     int buf;     // one operand buffer: nkp x 64
     int stage;   // Q | K | V | PQ | PK
     int ptile;   // one P tile: ceil(nkp / 64) k-blocks of [128 x 128 B]
-    int off_p, off_ones, off_bar, total;
+    int off_p, off_bias, off_bar, total;
 };
 __host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
     AtPlan p;
@@ -86,8 +86,8 @@ __host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
     p.stage = 5 * p.buf;
     p.ptile = ((nkp + 63) / 64) * 16384;
     p.off_p = 2 * p.stage + 8192;  // slack: the second query tile's A operand reads 8 KB past rows 128.. of Q
-    p.off_ones = p.off_p + ntile * p.ptile;  // [16 x 64] fp16 ones, K-major 128-byte swizzle: B operand of the row-sum MMA
-    p.off_bar = p.off_ones + 2048;
+    p.off_bias = p.off_p + ntile * p.ptile;  // [AT_SOFT][256] fp32 additive key mask of the current window, one copy per warp
+    p.off_bar = p.off_bias + AT_SOFT * 1024;
     p.total = p.off_bar + 256;
     return p;
 }
@@ -138,15 +138,13 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
     // Rows that TMA never writes must hold finite values: V rows >= S multiply P = 0 (0 x NaN would poison the output),
     // position rows >= Lv are added to the text rows of q and k and must be zero.
     for (int i = threadIdx.x; i < (2 * pl.stage + 8192) / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < 2048 / 16; i += AT_THREADS)  // all ones: the swizzle does not matter
-        reinterpret_cast<uint4*>(smem + pl.off_ones)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (*tmem_slot != 0u) __trap();  // the whole TMEM belongs to this CTA: addresses below are literals
     const uint32_t tmemS = 0u;                          // [NT][nkp] fp32 scores
-    const uint32_t tmemO = (uint32_t)(NT * nkp);        // [2][NT][32 + 16] fp32 outputs + row sums, double buffered across heads
+    const uint32_t tmemO = (uint32_t)(NT * nkp);        // [2][NT][32] fp32 outputs, double buffered across heads
 
     const int64_t w_begin = blockIdx.x, w_step = gridDim.x;
 
@@ -180,10 +178,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
     } else if (warp == 1) {  // --------------------------------------------------------------------------------- MMA issuer
         const uint32_t idS = (1u << 4) | ((uint32_t)(nkp >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                 // K-major A, B
         const uint32_t idO = (1u << 4) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // B (= V) MN-major
-        const uint32_t idSum = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // row sums: P . ones[16 x K]^T
         const uint32_t base_lo = desc_lo_sw128(smem_u32(smem));  // (address >> 4) | LBO = 1
         const uint32_t p_lo = desc_lo_sw128(smem_u32(sP));
-        const uint32_t ones_lo = desc_lo_sw128(smem_u32(smem + pl.off_ones));
         uint32_t it = 0;
         auto issue_pv = [&](uint32_t itp, bool wait_p) {  // O = P . V of the head issued at iteration itp
             const int st = itp & 1, ob = itp & 1;
@@ -193,13 +189,11 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
             if (elect_one_sync()) {
                 const uint32_t v_lo = base_lo + (uint32_t)((st * pl.stage + 2 * pl.buf) >> 4);
                 for (int t = 0; t < NT; ++t) {
-                    const uint32_t d = tmemO + (uint32_t)((ob * NT + t) * AT_OW);
+                    const uint32_t d = tmemO + (uint32_t)((ob * NT + t) * AT_HD);
                     for (int j = 0; j < nkp / 16; ++j) {  // 16 keys per MMA: A = P[:, 16 j ..], B = V[16 j .., :]
                         const uint32_t a = p_lo + (uint32_t)((t * pl.ptile + (j >> 2) * 16384 + (j & 3) * 32) >> 4);
                         const uint32_t b = v_lo + (uint32_t)((j * 16 * AT_ROWB) >> 4);
                         umma_f16_desc(d, a, kDescHiSw128, b, kDescHiSw64, idO, j > 0 ? 1u : 0u);
-                        // row sums of the fp16 values that multiply V, on the tensor pipe: 16 identical columns of P . 1
-                        umma_f16_desc(d + AT_HD, a, kDescHiSw128, ones_lo, kDescHiSw128, idSum, j > 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&o_full[ob]);
@@ -247,10 +241,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                     const __half2* bh = reinterpret_cast<const __half2*>(&b);
                     __half2* rh = reinterpret_cast<__half2*>(&r);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {  // fp32 add, one rounding (as the mma.sync kernel does)
-                        const float2 x = __half22float2(ah[e]), y = __half22float2(bh[e]);
-                        rh[e] = __floats2half2_rn(x.x + y.x, x.y + y.y);
-                    }
+                    for (int e = 0; e < 4; ++e) rh[e] = __hadd2(ah[e], bh[e]);  // exact sum, one rounding
                     *dst = r;
                 }
                 fence_async_smem();
@@ -267,24 +258,26 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
         // window row (= output row) of the tile row: the video rows, then the token rows; -1 = no row (gap / padding)
         const int row = trow < P.Lv ? trow : ((trow >= T0 && trow < T0 + P.Lt) ? trow - P.tpad : -1);
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+        const uint32_t tS = tmemS + lane_base + (uint32_t)(tile * nkp);
+        float* bias = reinterpret_cast<float*>(smem + pl.off_bias) + sw * 256;  // this warp's copy: no cross-warp hand-off
+        uint8_t* prow = sP + tile * pl.ptile;
+        const int r128 = quarter * 32 + lane;  // row inside the tile
         uint32_t it = 0;
         int64_t w_prev = 0;
         int h_prev = 0;
-        auto write_out = [&](uint32_t itp, int64_t wq, int hq) {  // O of head hq of window wq -> global memory
+        float sum_prev = 1.f;
+        auto write_out = [&](uint32_t itp, int64_t wq, int hq, float rsum) {  // O of head hq of window wq -> global memory
             const int ob = itp & 1;
             mbar_wait(&o_full[ob], (itp >> 1) & 1);
             tc_fence_after();
-            float o[32], sm[16];
-            const uint32_t tO = tmemO + lane_base + (uint32_t)((ob * NT + tile) * AT_OW);
-            tmem_ld_32x32(tO, o);
-            tmem_ld_32x16(tO + AT_HD, sm);
+            float o[32];
+            tmem_ld_32x32(tmemO + lane_base + (uint32_t)((ob * NT + tile) * AT_HD), o);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_free[ob]);
             if (row >= 0) {
-                const float inv = 1.f / sm[0];
+                const float inv = 1.f / rsum;
                 uint4* dst = reinterpret_cast<uint4*>(P.out + (wq * S + row) * P.ldo + hq * AT_HD);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -299,70 +292,103 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
         };
         for (int64_t w = w_begin; w < P.B; w += w_step) {
             const int vl = P.vlen[w], tl = P.tlen[w];
-            // 32-key chunks: fully valid ones take the mask-free path (warp-uniform test), the others mask branch-free
-            auto chunk_full = [&](int c) { return (c + 32 <= vl) || (c >= T0 && c + 32 <= T0 + tl); };
-            auto mask_chunk = [&](int c, float* s) {
+            const int live_end = T0 + tl;  // keys from here on are padding
+            // additive key mask of the window (0 / -inf); only chunks that hold a masked key read it
+            __syncwarp();
+            for (int k = lane; k < nkp; k += 32) bias[k] = (k < vl || (k >= T0 && k < live_end)) ? 0.f : -CUDART_INF_F;
+            __syncwarp();
+            // 32-key chunk c: n = number of leading keys worth computing (0, 16 or 32: the rest is padding whose P is 0),
+            // clean = none of those n keys is masked (warp-uniform tests)
+            auto chunk_n = [&](int c) { return c >= live_end ? 0 : (c + 16 >= live_end ? 16 : 32); };
+            auto chunk_clean = [&](int c, int n) { return (vl >= T0 || c + n <= vl || c >= T0) && c + n <= live_end; };
+            auto add_bias = [&](int c, int n, float* s) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int key = c + j;
-                    const bool ok = ((unsigned)key < (unsigned)vl) | ((unsigned)(key - T0) < (unsigned)tl);
-                    s[j] = ok ? s[j] : -CUDART_INF_F;
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < n) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + c + j);  // broadcast read
+                        s[j] += b.x; s[j + 1] += b.y; s[j + 2] += b.z; s[j + 3] += b.w;
+                    }
                 }
             };
             for (int h = 0; h < 8; ++h, ++it) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                const uint32_t tS = tmemS + lane_base + (uint32_t)(tile * nkp);
-                // pass 1: row maximum over the valid keys
+                // pass 1: row maximum over the valid keys; the TMEM load of chunk c + 1 is in flight while chunk c is reduced
                 float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
-                for (int c = 0; c < nkp; c += 32) {
-                    float s[32];
-                    tmem_ld_32x32(tS + c, s);
-                    tmem_ld_wait();
-                    if (!chunk_full(c)) mask_chunk(c, s);
+                float sa[32], sb[32];
+                auto max_chunk = [&](int c, float* s) {
+                    const int n = chunk_n(c);
+                    if (n == 0) return;
+                    if (!chunk_clean(c, n)) add_bias(c, n, s);
+                    if (n == 32) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
+                        for (int j = 0; j < 32; j += 4) {
+                            m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
+                        }
                     }
+                };
+                tmem_ld_32x32(tS, sa);
+                for (int c = 0; c < nkp; c += 64) {
+                    tmem_ld_wait();
+                    if (c + 32 < nkp) tmem_ld_32x32(tS + c + 32, sb);
+                    max_chunk(c, sa);
+                    if (c + 32 >= nkp) break;
+                    tmem_ld_wait();
+                    if (c + 64 < nkp) tmem_ld_32x32(tS + c + 64, sa);
+                    max_chunk(c + 32, sb);
                 }
                 const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
                 const float off = (mx == -CUDART_INF_F) ? 0.f : -mx * sl2;
-                // pass 2: p = exp2(s * sl2 - max * sl2) with the packed fp16 exponential (two keys per MUFU instruction; its
-                // result IS the fp16 pair the tensor core multiplies with V; the row sums come from the same values through
-                // the P . ones MMA) -> P tile (K-major, 128-byte swizzle)
-                if (it > 0) mbar_wait(p_free, (it - 1) & 1);  // P.V of the previous head has finished reading P
-                uint8_t* prow = sP + tile * pl.ptile;
-                const int r128 = quarter * 32 + lane;  // row inside the tile
-                for (int c = 0; c < nkp; c += 32) {
-                    float s[32];
-                    tmem_ld_32x32(tS + c, s);
-                    tmem_ld_wait();
-                    if (!chunk_full(c)) mask_chunk(c, s);
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const __half2 xh = __floats2half2_rn(fmaf(s[j], sl2, off), fmaf(s[j + 1], sl2, off));
-                        uint32_t r;
-                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&xh)));
-                        pk[j >> 1] = r;
-                    }
+                // pass 2: p = exp2(s * sl2 - max * sl2) -> fp16 P tile (K-major, 128-byte swizzle), fp32 row sum
+                float sum0 = 0.f, sum1 = 0.f;
+                auto exp_chunk = [&](int c, float* s) {
+                    const int n = chunk_n(c);
                     uint8_t* kb = prow + (c >> 6) * 16384;  // k-block of 64 keys
                     const int u0 = (c & 63) >> 3;           // first 16-byte unit (8 keys) inside the 128-byte row
+                    if (n > 0 && !chunk_clean(c, n)) add_bias(c, n, s);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        *reinterpret_cast<uint4*>(kb + sw128(r128, u0 + u)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (u * 8 < n) {
+                            float e[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(s[u * 8 + j], sl2, off));
+                            sum0 += (e[0] + e[1]) + (e[2] + e[3]);
+                            sum1 += (e[4] + e[5]) + (e[6] + e[7]);
+                            v = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
+                        }
+                        *reinterpret_cast<uint4*>(kb + sw128(r128, u0 + u)) = v;
+                    }
+                };
+                tmem_ld_32x32(tS, sa);
+                if (it > 0) mbar_wait(p_free, (it - 1) & 1);  // P.V of the previous head has finished reading P
+                for (int c = 0; c < nkp; c += 64) {
+                    tmem_ld_wait();
+                    if (c + 32 < nkp) tmem_ld_32x32(tS + c + 32, sb);
+                    exp_chunk(c, sa);
+                    if (c + 32 >= nkp) break;
+                    tmem_ld_wait();
+                    if (c + 64 < nkp) tmem_ld_32x32(tS + c + 64, sa);
+                    exp_chunk(c + 32, sb);
                 }
                 tc_fence_before();
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_ready);
                 // the previous head's output, while the tensor pipe works on this head's P.V and the next head's scores
-                if (it > 0) write_out(it - 1, w_prev, h_prev);
+                if (it > 0) write_out(it - 1, w_prev, h_prev, sum_prev);
                 w_prev = w;
                 h_prev = h;
+                sum_prev = sum0 + sum1;
             }
         }
-        if (it > 0) write_out(it - 1, w_prev, h_prev);
+        if (it > 0) write_out(it - 1, w_prev, h_prev, sum_prev);
     }
     tc_fence_before();
     __syncthreads();
@@ -413,7 +439,7 @@ bool enc_attn_tc_supported(int Lv, int Lt, int d_model, int nheads) {
         env = (e && e[0] == '0') ? 0 : 1;
     }
     return env == 1 && d_model == 256 && nheads == 8 && nkp <= AT_MAX_NKP && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
-           nt * nkp + 2 * nt * AT_OW <= 512 && at_plan(nkp, nt).total <= 232448;
+           nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt).total <= 232448;
 }
 
 int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv,
