@@ -11,8 +11,14 @@
 //     on `tcgen05.ld` data: no shuffles, no fragments; P goes back to shared memory as the fp16 A operand (K-major,
 //     128-byte swizzle) and O = P.V is a second tcgen05 product with V used as it lands (MN-major B operand, no transpose);
 //   * the heads of a window are pipelined: TMA of head h+1, QK^T of head h+1 and P.V of head h overlap the softmax of head h.
-// One persistent CTA per SM, 9 warps: 0 TMA producer, 1 MMA issuer (whole warp, elect.sync), 2-3 position add,
-// 4-8 softmax / output (4-7: rows 0-127 of the window, one per TMEM lane quarter; 8: rows 128-159).
+// One persistent CTA per SM, 24 warps: 0 TMA producer, 1 MMA issuer (whole warp, elect.sync), 2-3 position add, 4-23 softmax /
+// output.  The softmax is exponential- and latency-bound (22 500 ex2 per head against ~1 000 tensor-pipe cycles), so the score
+// rows are split by KEY RANGE over four warps per TMEM lane quarter (a warp reads only the lanes of its quarter = its SM
+// sub-partition): warps 4-19 take rows 0-127 (quarter = warp & 3, key range g = (warp - 4) / 4); rows 128-159 — a fifth
+// 32-row group that would otherwise double the load of one sub-partition — are computed by FOUR score MMAs, one per key
+// range, each with its A operand shifted by 32 g rows so that range g of these rows lands in lane quarter g: warps 20-23 take
+// one range each, and every sub-partition runs five warps with the same work.  Partial row maxima / sums go through shared
+// memory (named barrier per group of four warps).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -28,11 +34,11 @@ using namespace ptx;
 
 namespace {
 
-constexpr int AT_THREADS = 288;
+constexpr int AT_THREADS = 768;
+constexpr int AT_G = 4;         // key ranges = softmax warps per row group
 constexpr int AT_HD = 32;       // head dim
 constexpr int AT_ROWB = 64;     // bytes per operand row of one head (32 fp16): the 64-byte swizzle span
 constexpr int AT_MAX_NKP = 192; // padded key count supported (TMEM: 2 x NKP + 128 <= 512)
-constexpr int AT_SOFT = 5;      // softmax warps: 4-7 = rows 0-127 (one per TMEM lane quarter), 8 = rows 128-159
 
 // descriptor hi word for 64-byte-swizzled operands: SBO = 8 rows x 64 B = 512 B, version 1, layout SWIZZLE_64B (= 4)
 constexpr uint32_t kDescHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
@@ -78,16 +84,23 @@ struct AtPlan {
     int buf;     // one operand buffer: nkp x 64
     int stage;   // Q | K | V | PQ | PK
     int ptile;   // one P tile: ceil(nkp / 64) k-blocks of [128 x 128 B]
-    int off_p, off_bias, off_bar, total;
+    int off_p, off_bias, off_x, off_bar, total;
 };
+// key range g of a window with `units` 16-key units: first unit and unit count
+__host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
+    const int ub = units / AT_G, ur = units % AT_G;
+    *u0 = g * ub + (g < ur ? g : ur);
+    *un = ub + (g < ur ? 1 : 0);
+}
 __host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
     AtPlan p;
     p.buf = ((nkp * AT_ROWB + 1023) / 1024) * 1024;
     p.stage = 5 * p.buf;
     p.ptile = ((nkp + 63) / 64) * 16384;
     p.off_p = 2 * p.stage + 8192;  // slack: the second query tile's A operand reads 8 KB past rows 128.. of Q
-    p.off_bias = p.off_p + ntile * p.ptile;  // [AT_SOFT][256] fp32 additive key mask of the current window, one copy per warp
-    p.off_bar = p.off_bias + AT_SOFT * 1024;
+    p.off_bias = p.off_p + ntile * p.ptile;  // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
+    p.off_x = p.off_bias + 20 * 256;         // partial maxima [AT_G][160] and partial sums [2][AT_G][160] (row groups 0-3, 4)
+    p.off_bar = p.off_x + 3 * AT_G * 160 * 4;
     p.total = p.off_bar + 256;
     return p;
 }
@@ -114,7 +127,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.Lv + P.Lt, nkp = P.nkp, NT = P.ntile;
-    const int n_soft = (NT == 2) ? 5 : 4;  // softmax warps in use
+    const int n_soft = (NT == 2) ? 20 : 16;  // softmax warps in use
+    const int n_out = (NT == 2) ? 17 : 16;   // ... of which read O (rows 128.. are written out by one warp)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQkv)) : "memory");
@@ -124,7 +138,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
             mbar_init(&qk_ready[i], 2);
             mbar_init(&st_free[i], 1);
             mbar_init(&o_full[i], 1);
-            mbar_init(&o_free[i], n_soft);
+            mbar_init(&o_free[i], n_out);
         }
         mbar_init(s_full, 1);
         mbar_init(p_ready, n_soft);
@@ -210,10 +224,19 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint32_t q_lo = base_lo + (uint32_t)((st * pl.stage) >> 4), k_lo = q_lo + (uint32_t)(pl.buf >> 4);
-                    for (int t = 0; t < NT; ++t)
-                        for (int k = 0; k < 2; ++k)
-                            umma_f16_desc(tmemS + (uint32_t)(t * nkp), q_lo + (uint32_t)((t * 128 * AT_ROWB) >> 4) + 2 * k, kDescHiSw64,
-                                          k_lo + 2 * k, kDescHiSw64, idS, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 2; ++k) umma_f16_desc(tmemS, q_lo + 2 * k, kDescHiSw64, k_lo + 2 * k, kDescHiSw64, idS, k > 0 ? 1u : 0u);
+                    if (NT == 2) {
+                        // rows 128..: key range g against the Q rows starting at 128 - 32 g -> these rows land in lane quarter g
+                        for (int g = 0; g < AT_G; ++g) {
+                            int u0, un;
+                            at_range(nkp >> 4, g, &u0, &un);
+                            if (un == 0) continue;
+                            const uint32_t idg = (1u << 4) | ((uint32_t)((un * 16) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                            const uint32_t a = q_lo + (uint32_t)(((128 - 32 * g) * AT_ROWB) >> 4), b = k_lo + (uint32_t)((u0 * 16 * AT_ROWB) >> 4);
+                            for (int k = 0; k < 2; ++k)
+                                umma_f16_desc(tmemS + (uint32_t)(nkp + u0 * 16), a + 2 * k, kDescHiSw64, b + 2 * k, kDescHiSw64, idg, k > 0 ? 1u : 0u);
+                        }
+                    }
                     umma_commit(s_full);
                 }
                 __syncwarp();
@@ -250,145 +273,157 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
             }
         }
     } else if (warp < 4 + n_soft) {  // ------------------------------------------------------------ softmax / output warps
-        const int sw = warp - 4;                // 0..4
-        const int tile = sw >> 2;               // query tile
-        const int quarter = warp & 3;           // TMEM lane quarter (warps 4-7 -> 0-3, warp 8 -> 0)
-        const int trow = tile * 128 + quarter * 32 + lane;  // row of this thread in the operand tiles
-        const int T0 = P.Lv + P.tpad;                       // first token row in the tiles
+        const int tile = warp >= 20 ? 1 : 0;    // row group: rows 0-127 | rows 128..
+        const int quarter = warp & 3;           // TMEM lane quarter (= SM sub-partition) of this warp
+        const int g = tile ? quarter : (warp - 4) >> 2;  // key range
+        const int xrow = tile ? 128 + lane : quarter * 32 + lane;  // row of this thread in the window tiles (exchange index)
+        const int prow_i = tile ? lane : quarter * 32 + lane;      // its row inside the P / O tile of the group
+        const int T0 = P.Lv + P.tpad;                              // first token row in the tiles
         // window row (= output row) of the tile row: the video rows, then the token rows; -1 = no row (gap / padding)
-        const int row = trow < P.Lv ? trow : ((trow >= T0 && trow < T0 + P.Lt) ? trow - P.tpad : -1);
+        const int row = xrow < P.Lv ? xrow : ((xrow >= T0 && xrow < T0 + P.Lt) ? xrow - P.tpad : -1);
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        const uint32_t tS = tmemS + lane_base + (uint32_t)(tile * nkp);
-        float* bias = reinterpret_cast<float*>(smem + pl.off_bias) + sw * 256;  // this warp's copy: no cross-warp hand-off
-        uint8_t* prow = sP + tile * pl.ptile;
-        const int r128 = quarter * 32 + lane;  // row inside the tile
+        int u0, un;
+        at_range(nkp >> 4, g, &u0, &un);
+        const int k0 = u0 * 16;                                    // first key of this warp's range
+        const uint32_t tS = tmemS + lane_base + (uint32_t)(tile * nkp + k0);
+        float* bias = reinterpret_cast<float*>(smem + pl.off_bias) + (warp - 4) * 64;  // this warp's copy: no cross-warp hand-off
+        float* xmax = reinterpret_cast<float*>(smem + pl.off_x);    // [AT_G][160]
+        float* xsum = xmax + AT_G * 160;                            // [2][AT_G][160]
+        uint8_t* ptile = sP + tile * pl.ptile;
+        const int bar_id = tile ? 5 : 1 + quarter;                  // the four warps that share these rows
+        const bool writer = tile == 0 || quarter == 0;              // reads O and writes the output rows
         uint32_t it = 0;
         int64_t w_prev = 0;
         int h_prev = 0;
-        float sum_prev = 1.f;
-        auto write_out = [&](uint32_t itp, int64_t wq, int hq, float rsum) {  // O of head hq of window wq -> global memory
+        auto write_out = [&](uint32_t itp, int64_t wq, int hq) {  // O of head hq of window wq -> global memory
+            if (!writer) return;
             const int ob = itp & 1;
             mbar_wait(&o_full[ob], (itp >> 1) & 1);
             tc_fence_after();
-            float o[32];
-            tmem_ld_32x32(tmemO + lane_base + (uint32_t)((ob * NT + tile) * AT_HD), o);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[ob]);
-            if (row >= 0) {
-                const float inv = 1.f / rsum;
-                uint4* dst = reinterpret_cast<uint4*>(P.out + (wq * S + row) * P.ldo + hq * AT_HD);
+            // partial sums of the four key ranges: written before the ranges' p_ready arrivals, which the P.V commit follows
+            const float* xs = xsum + ob * AT_G * 160 + xrow;
+            const float inv = 1.f / ((xs[0] + xs[160]) + (xs[320] + xs[480]));
+            const uint32_t tO = tmemO + lane_base + (uint32_t)((ob * NT + tile) * AT_HD);
+            if (tile == 0) {  // 8 of the 32 output columns per warp: the four warps of a quarter write one 64-byte row segment
+                float o[8];
+                tmem_ld_32x8(tO + 8 * g, o);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_free[ob]);
+                if (row >= 0)
+                    *reinterpret_cast<uint4*>(P.out + (wq * S + row) * P.ldo + hq * AT_HD + 8 * g) =
+                        make_uint4(pack_h2(o[0] * inv, o[1] * inv), pack_h2(o[2] * inv, o[3] * inv), pack_h2(o[4] * inv, o[5] * inv),
+                                   pack_h2(o[6] * inv, o[7] * inv));
+            } else {
+                float o[32];
+                tmem_ld_32x32(tO, o);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_free[ob]);
+                if (row >= 0) {
+                    uint4* dst = reinterpret_cast<uint4*>(P.out + (wq * S + row) * P.ldo + hq * AT_HD);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 v;
-                    v.x = pack_h2(o[8 * u] * inv, o[8 * u + 1] * inv);
-                    v.y = pack_h2(o[8 * u + 2] * inv, o[8 * u + 3] * inv);
-                    v.z = pack_h2(o[8 * u + 4] * inv, o[8 * u + 5] * inv);
-                    v.w = pack_h2(o[8 * u + 6] * inv, o[8 * u + 7] * inv);
-                    dst[u] = v;
+                    for (int u = 0; u < 4; ++u)
+                        dst[u] = make_uint4(pack_h2(o[8 * u] * inv, o[8 * u + 1] * inv), pack_h2(o[8 * u + 2] * inv, o[8 * u + 3] * inv),
+                                            pack_h2(o[8 * u + 4] * inv, o[8 * u + 5] * inv), pack_h2(o[8 * u + 6] * inv, o[8 * u + 7] * inv));
                 }
             }
         };
         for (int64_t w = w_begin; w < P.B; w += w_step) {
             const int vl = P.vlen[w], tl = P.tlen[w];
             const int live_end = T0 + tl;  // keys from here on are padding
-            // additive key mask of the window (0 / -inf); only chunks that hold a masked key read it
+            // additive key mask of this warp's range (0 / -inf); only units that hold a masked key read it
             __syncwarp();
-            for (int k = lane; k < nkp; k += 32) bias[k] = (k < vl || (k >= T0 && k < live_end)) ? 0.f : -CUDART_INF_F;
+            for (int k = lane; k < un * 16; k += 32) {
+                const int key = k0 + k;
+                bias[k] = (key < vl || (key >= T0 && key < live_end)) ? 0.f : -CUDART_INF_F;
+            }
             __syncwarp();
-            // 32-key chunk c: n = number of leading keys worth computing (0, 16 or 32: the rest is padding whose P is 0),
-            // clean = none of those n keys is masked (warp-uniform tests)
-            auto chunk_n = [&](int c) { return c >= live_end ? 0 : (c + 16 >= live_end ? 16 : 32); };
-            auto chunk_clean = [&](int c, int n) { return (vl >= T0 || c + n <= vl || c >= T0) && c + n <= live_end; };
-            auto add_bias = [&](int c, int n, float* s) {
+            // 16-key unit at key c: dead = padding only (its P is 0), clean = no masked key (warp-uniform tests)
+            auto unit_dead = [&](int c) { return c >= live_end; };
+            auto unit_clean = [&](int c) { return (vl >= T0 || c + 16 <= vl || c >= T0) && c + 16 <= live_end; };
+            auto add_bias = [&](int u, float* s) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j < n) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias + c + j);  // broadcast read
-                        s[j] += b.x; s[j + 1] += b.y; s[j + 2] += b.z; s[j + 3] += b.w;
-                    }
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + u * 16 + j);  // broadcast read
+                    s[j] += b.x; s[j + 1] += b.y; s[j + 2] += b.z; s[j + 3] += b.w;
                 }
             };
             for (int h = 0; h < 8; ++h, ++it) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                // pass 1: row maximum over the valid keys; the TMEM load of chunk c + 1 is in flight while chunk c is reduced
+                // pass 1: maximum of the row over this warp's keys; the TMEM load of unit u + 1 is in flight while unit u is reduced
                 float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
-                float sa[32], sb[32];
-                auto max_chunk = [&](int c, float* s) {
-                    const int n = chunk_n(c);
-                    if (n == 0) return;
-                    if (!chunk_clean(c, n)) add_bias(c, n, s);
-                    if (n == 32) {
+                float sa[16], sb[16];
+                auto max_unit = [&](int u, float* s) {
+                    const int c = k0 + u * 16;
+                    if (unit_dead(c)) return;
+                    if (!unit_clean(c)) add_bias(u, s);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
-                        }
+                    for (int j = 0; j < 16; j += 4) {
+                        m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
                     }
                 };
-                tmem_ld_32x32(tS, sa);
-                for (int c = 0; c < nkp; c += 64) {
+                if (un > 0) tmem_ld_32x16(tS, sa);
+                for (int u = 0; u < un; u += 2) {
                     tmem_ld_wait();
-                    if (c + 32 < nkp) tmem_ld_32x32(tS + c + 32, sb);
-                    max_chunk(c, sa);
-                    if (c + 32 >= nkp) break;
+                    if (u + 1 < un) tmem_ld_32x16(tS + (u + 1) * 16, sb);
+                    max_unit(u, sa);
+                    if (u + 1 >= un) break;
                     tmem_ld_wait();
-                    if (c + 64 < nkp) tmem_ld_32x32(tS + c + 64, sa);
-                    max_chunk(c + 32, sb);
+                    if (u + 2 < un) tmem_ld_32x16(tS + (u + 2) * 16, sa);
+                    max_unit(u + 1, sb);
                 }
-                const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                xmax[g * 160 + xrow] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                if (un > 0) tmem_ld_32x16(tS, sa);  // first unit of pass 2: in flight across the exchange
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                const float mx = fmaxf(fmaxf(xmax[xrow], xmax[160 + xrow]), fmaxf(xmax[320 + xrow], xmax[480 + xrow]));
                 const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
                 const float off = (mx == -CUDART_INF_F) ? 0.f : -mx * sl2;
-                // pass 2: p = exp2(s * sl2 - max * sl2) -> fp16 P tile (K-major, 128-byte swizzle), fp32 row sum
+                // pass 2: p = exp2(s * sl2 - max * sl2) -> fp16 P tile (K-major, 128-byte swizzle), fp32 partial row sum
                 float sum0 = 0.f, sum1 = 0.f;
-                auto exp_chunk = [&](int c, float* s) {
-                    const int n = chunk_n(c);
-                    uint8_t* kb = prow + (c >> 6) * 16384;  // k-block of 64 keys
-                    const int u0 = (c & 63) >> 3;           // first 16-byte unit (8 keys) inside the 128-byte row
-                    if (n > 0 && !chunk_clean(c, n)) add_bias(c, n, s);
+                auto exp_unit = [&](int u, float* s) {
+                    const int c = k0 + u * 16;
+                    uint8_t* kb = ptile + (c >> 6) * 16384;  // k-block of 64 keys
+                    const int c16 = (c & 63) >> 3;           // first 16-byte chunk (8 keys) inside the 128-byte row
+                    uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+                    if (!unit_dead(c)) {
+                        if (!unit_clean(c)) add_bias(u, s);
+                        float e[16];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                        if (u * 8 < n) {
-                            float e[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(s[u * 8 + j], sl2, off));
-                            sum0 += (e[0] + e[1]) + (e[2] + e[3]);
-                            sum1 += (e[4] + e[5]) + (e[6] + e[7]);
-                            v = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
-                        }
-                        *reinterpret_cast<uint4*>(kb + sw128(r128, u0 + u)) = v;
+                        for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(s[j], sl2, off));
+                        sum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+                        sum1 += ((e[8] + e[9]) + (e[10] + e[11])) + ((e[12] + e[13]) + (e[14] + e[15]));
+                        v0 = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
+                        v1 = make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
                     }
+                    *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16)) = v0;
+                    *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16 + 1)) = v1;
                 };
-                tmem_ld_32x32(tS, sa);
                 if (it > 0) mbar_wait(p_free, (it - 1) & 1);  // P.V of the previous head has finished reading P
-                for (int c = 0; c < nkp; c += 64) {
+                for (int u = 0; u < un; u += 2) {
                     tmem_ld_wait();
-                    if (c + 32 < nkp) tmem_ld_32x32(tS + c + 32, sb);
-                    exp_chunk(c, sa);
-                    if (c + 32 >= nkp) break;
+                    if (u + 1 < un) tmem_ld_32x16(tS + (u + 1) * 16, sb);
+                    exp_unit(u, sa);
+                    if (u + 1 >= un) break;
                     tmem_ld_wait();
-                    if (c + 64 < nkp) tmem_ld_32x32(tS + c + 64, sa);
-                    exp_chunk(c + 32, sb);
+                    if (u + 2 < un) tmem_ld_32x16(tS + (u + 2) * 16, sa);
+                    exp_unit(u + 1, sb);
                 }
+                xsum[((it & 1) * AT_G + g) * 160 + xrow] = sum0 + sum1;
                 tc_fence_before();
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_ready);
                 // the previous head's output, while the tensor pipe works on this head's P.V and the next head's scores
-                if (it > 0) write_out(it - 1, w_prev, h_prev, sum_prev);
+                if (it > 0) write_out(it - 1, w_prev, h_prev);
                 w_prev = w;
                 h_prev = h;
-                sum_prev = sum0 + sum1;
             }
         }
-        if (it > 0) write_out(it - 1, w_prev, h_prev, sum_prev);
+        if (it > 0) write_out(it - 1, w_prev, h_prev);
     }
     tc_fence_before();
     __syncthreads();

@@ -111,6 +111,13 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float* v) {
           "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
         : "r"(taddr));
 }
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
 // 32 lanes x 16 columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
