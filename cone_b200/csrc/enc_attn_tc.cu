@@ -36,6 +36,7 @@ namespace {
 
 constexpr int AT_THREADS = 768;
 constexpr int AT_G = 4;         // key ranges = softmax warps per row group
+constexpr int AT_NST = 3;       // operand stages (heads in flight between TMA and the tensor pipe)
 constexpr int AT_HD = 32;       // head dim
 constexpr int AT_ROWB = 64;     // bytes per operand row of one head (32 fp16): the 64-byte swizzle span
 constexpr int AT_MAX_NKP = 192; // padded key count supported (TMEM: 2 x NKP + 128 <= 512)
@@ -82,9 +83,11 @@ struct AtParams {
 // shared-memory plan (bytes), all multiples of 1 KB
 struct AtPlan {
     int buf;     // one operand buffer: nkp x 64
-    int stage;   // Q | K | V | PQ | PK
-    int ptile;   // one P tile: ceil(nkp / 64) k-blocks of [128 x 128 B]
-    int off_p, off_bias, off_x, off_bar, total;
+    int pbuf;    // one position buffer: Lv x 64
+    int stage;   // Q | K | V | PQ | PK  (rows 128.. of Q as an M = 128 operand run on into K: finite values, unused result rows)
+    int ptile;   // P of rows 0-127: ceil(nkp / 64) k-blocks of [128 x 128 B]
+    int p1blk;   // P of rows 128..: k-blocks of [32 x 128 B]; the M = 128 operand reads on into the next blocks / into P of rows 0-127
+    int off_p1, off_p, off_bias, off_x, off_bar, total;
 };
 // key range g of a window with `units` 16-key units: first unit and unit count
 __host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
@@ -92,13 +95,17 @@ __host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
     *u0 = g * ub + (g < ur ? g : ur);
     *un = ub + (g < ur ? 1 : 0);
 }
-__host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
+__host__ __device__ inline AtPlan at_plan(int nkp, int ntile, int Lv) {
     AtPlan p;
     p.buf = ((nkp * AT_ROWB + 1023) / 1024) * 1024;
-    p.stage = 5 * p.buf;
+    p.pbuf = ((Lv * AT_ROWB + 1023) / 1024) * 1024;
+    p.stage = 3 * p.buf + 2 * p.pbuf;
     p.ptile = ((nkp + 63) / 64) * 16384;
-    p.off_p = 2 * p.stage + 8192;  // slack: the second query tile's A operand reads 8 KB past rows 128.. of Q
-    p.off_bias = p.off_p + ntile * p.ptile;  // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
+    p.p1blk = 4096;
+    p.off_p1 = AT_NST * p.stage;
+    p.off_p = p.off_p1 + (ntile == 2 ? ((nkp + 63) / 64) * p.p1blk : 0);
+    if (ntile == 2 && p.ptile < 16384) p.off_p += 16384;  // (never: two tiles mean more than 128 keys)
+    p.off_bias = p.off_p + p.ptile;  // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
     p.off_x = p.off_bias + 20 * 256;         // partial maxima [AT_G][160] and partial sums [2][AT_G][160] (row groups 0-3, 4)
     p.off_bar = p.off_x + 3 * AT_G * 160 * 4;
     p.total = p.off_bar + 256;
@@ -112,18 +119,20 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                    AtParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    const AtPlan pl = at_plan(P.nkp, P.ntile);
+    const AtPlan pl = at_plan(P.nkp, P.ntile, P.Lv);
     uint8_t* sP = smem + pl.off_p;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bar);
-    uint64_t* tma_full = bars;        // [2] operands of a head have landed
-    uint64_t* qk_ready = bars + 2;    // [2] position rows added to q and k
-    uint64_t* st_free = bars + 4;     // [2] P.V of the head has finished reading the stage (and q, k were consumed before)
-    uint64_t* s_full = bars + 6;      // S = Q.K^T complete
-    uint64_t* p_ready = bars + 7;     // P in shared memory, S read out of TMEM
-    uint64_t* p_free = bars + 8;      // P.V has finished reading P
-    uint64_t* o_full = bars + 9;      // [2]
-    uint64_t* o_free = bars + 11;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* qk_full = bars;                 // [AT_NST] q, k and the position rows of a head have landed
+    uint64_t* v_full = bars + AT_NST;         // [AT_NST] v of the head has landed
+    uint64_t* qk_ready = bars + 2 * AT_NST;   // [AT_NST] position rows added to q and k
+    uint64_t* qk_free = bars + 3 * AT_NST;    // [AT_NST] Q.K^T has finished reading q and k: refilled three heads ahead
+    uint64_t* v_free = bars + 4 * AT_NST;     // [AT_NST] P.V has finished reading v
+    uint64_t* s_full = bars + 5 * AT_NST;     // S = Q.K^T complete
+    uint64_t* p_ready = s_full + 1;           // P in shared memory, S read out of TMEM
+    uint64_t* p_free = s_full + 2;            // P.V has finished reading P
+    uint64_t* o_full = s_full + 3;            // [2]
+    uint64_t* o_free = s_full + 5;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.Lv + P.Lt, nkp = P.nkp, NT = P.ntile;
@@ -133,10 +142,14 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQkv)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmPos)) : "memory");
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tma_full[i], 1);
+        for (int i = 0; i < AT_NST; ++i) {
+            mbar_init(&qk_full[i], 1);
+            mbar_init(&v_full[i], 1);
             mbar_init(&qk_ready[i], 2);
-            mbar_init(&st_free[i], 1);
+            mbar_init(&qk_free[i], 1);
+            mbar_init(&v_free[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&o_full[i], 1);
             mbar_init(&o_free[i], n_out);
         }
@@ -151,7 +164,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
     }
     // Rows that TMA never writes must hold finite values: V rows >= S multiply P = 0 (0 x NaN would poison the output),
     // position rows >= Lv are added to the text rows of q and k and must be zero.
-    for (int i = threadIdx.x; i < (2 * pl.stage + 8192) / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (AT_NST * pl.stage) / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -164,28 +177,30 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
 
     if (warp == 0) {
         if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producer
-            uint32_t it = 0;
-            const uint32_t bytes_qkv = (uint32_t)(3 * S * AT_ROWB), bytes_pos = (uint32_t)(2 * P.Lv * AT_ROWB);
+            int st = 0;
+            uint32_t ph = 0;
+            const uint32_t bytes_m = (uint32_t)(S * AT_ROWB), bytes_pos = (uint32_t)(2 * P.Lv * AT_ROWB);
             for (int64_t w = w_begin; w < P.B; w += w_step) {
                 const int vl = P.vlen[w];
                 const int64_t vb = P.indirect ? P.vid_base[w] : w * S;
                 const int64_t tb = P.indirect ? P.txt_base[w] : 0;
-                for (int h = 0; h < 8; ++h, ++it) {
-                    const int st = it & 1;
-                    mbar_wait(&st_free[st], ((it >> 1) & 1) ^ 1);
+                for (int h = 0; h < 8; ++h) {
                     uint8_t* base = smem + st * pl.stage;
-                    mbar_expect_tx(&tma_full[st], bytes_qkv + bytes_pos);
-                    for (int m = 0; m < 3; ++m) {  // q, k, v of head h: columns m * 256 + h * 32
-                        if (P.indirect) {
-                            tma_load_2d(base + m * pl.buf, &tmQkv, &tma_full[st], m * 256 + h * AT_HD, (int)vb);
-                            tma_load_2d(base + m * pl.buf + (P.Lv + P.tpad) * AT_ROWB, &tmTok, &tma_full[st], m * 256 + h * AT_HD, (int)tb);
-                        } else {
-                            tma_load_2d(base + m * pl.buf, &tmQkv, &tma_full[st], m * 256 + h * AT_HD, (int)vb);
-                        }
-                    }
+                    auto load_m = [&](int m, uint64_t* bar) {  // q, k or v of head h: columns m * 256 + h * 32
+                        tma_load_2d(base + m * pl.buf, &tmQkv, bar, m * 256 + h * AT_HD, (int)vb);
+                        if (P.indirect) tma_load_2d(base + m * pl.buf + (P.Lv + P.tpad) * AT_ROWB, &tmTok, bar, m * 256 + h * AT_HD, (int)tb);
+                    };
+                    mbar_wait(&qk_free[st], ph ^ 1);
+                    mbar_expect_tx(&qk_full[st], 2 * bytes_m + bytes_pos);
+                    load_m(0, &qk_full[st]);
+                    load_m(1, &qk_full[st]);
                     // position rows of (valid length, head): pos.Wq^T then pos.Wk^T
-                    tma_load_2d(base + 3 * pl.buf, &tmPos, &tma_full[st], h * AT_HD, vl * P.table_lv);
-                    tma_load_2d(base + 4 * pl.buf, &tmPos, &tma_full[st], 256 + h * AT_HD, vl * P.table_lv);
+                    tma_load_2d(base + 3 * pl.buf, &tmPos, &qk_full[st], h * AT_HD, vl * P.table_lv);
+                    tma_load_2d(base + 3 * pl.buf + pl.pbuf, &tmPos, &qk_full[st], 256 + h * AT_HD, vl * P.table_lv);
+                    mbar_wait(&v_free[st], ph ^ 1);
+                    mbar_expect_tx(&v_full[st], bytes_m);
+                    load_m(2, &v_full[st]);
+                    if (++st == AT_NST) { st = 0; ph ^= 1; }
                 }
             }
         }
@@ -194,32 +209,36 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
         const uint32_t idO = (1u << 4) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // B (= V) MN-major
         const uint32_t base_lo = desc_lo_sw128(smem_u32(smem));  // (address >> 4) | LBO = 1
         const uint32_t p_lo = desc_lo_sw128(smem_u32(sP));
+        const uint32_t p1_lo = desc_lo_sw128(smem_u32(smem + pl.off_p1));
         uint32_t it = 0;
-        auto issue_pv = [&](uint32_t itp, bool wait_p) {  // O = P . V of the head issued at iteration itp
-            const int st = itp & 1, ob = itp & 1;
+        int st = 0, st_prev = 0;
+        uint32_t ph = 0, ph_prev = 0;
+        auto issue_pv = [&](uint32_t itp, int stp, uint32_t php, bool wait_p) {  // O = P . V of the head issued at iteration itp
+            const int ob = itp & 1;
             if (wait_p) mbar_wait(p_ready, itp & 1);  // (the main loop has already waited: never wait twice on a parity)
+            mbar_wait(&v_full[stp], php);
             mbar_wait(&o_free[ob], ((itp >> 1) & 1) ^ 1);
             tc_fence_after();
             if (elect_one_sync()) {
-                const uint32_t v_lo = base_lo + (uint32_t)((st * pl.stage + 2 * pl.buf) >> 4);
+                const uint32_t v_lo = base_lo + (uint32_t)((stp * pl.stage + 2 * pl.buf) >> 4);
                 for (int t = 0; t < NT; ++t) {
                     const uint32_t d = tmemO + (uint32_t)((ob * NT + t) * AT_HD);
                     for (int j = 0; j < nkp / 16; ++j) {  // 16 keys per MMA: A = P[:, 16 j ..], B = V[16 j .., :]
-                        const uint32_t a = p_lo + (uint32_t)((t * pl.ptile + (j >> 2) * 16384 + (j & 3) * 32) >> 4);
+                        const uint32_t a = t == 0 ? p_lo + (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4)
+                                                  : p1_lo + (uint32_t)(((j >> 2) * pl.p1blk + (j & 3) * 32) >> 4);
                         const uint32_t b = v_lo + (uint32_t)((j * 16 * AT_ROWB) >> 4);
                         umma_f16_desc(d, a, kDescHiSw128, b, kDescHiSw64, idO, j > 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&o_full[ob]);
                 umma_commit(p_free);
-                umma_commit(&st_free[st]);
+                umma_commit(&v_free[stp]);
             }
             __syncwarp();
         };
         for (int64_t w = w_begin; w < P.B; w += w_step) {
             for (int h = 0; h < 8; ++h, ++it) {
-                const int st = it & 1;
-                mbar_wait(&qk_ready[st], (it >> 1) & 1);
+                mbar_wait(&qk_ready[st], ph);
                 if (it > 0) mbar_wait(p_ready, (it - 1) & 1);  // S of the previous head has been read out of TMEM
                 tc_fence_after();
                 if (elect_one_sync()) {
@@ -238,19 +257,23 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                         }
                     }
                     umma_commit(s_full);
+                    umma_commit(&qk_free[st]);
                 }
                 __syncwarp();
-                if (it > 0) issue_pv(it - 1, false);  // overlaps the softmax of this head
+                if (it > 0) issue_pv(it - 1, st_prev, ph_prev, false);  // overlaps the softmax of this head
+                st_prev = st;
+                ph_prev = ph;
+                if (++st == AT_NST) { st = 0; ph ^= 1; }
             }
         }
-        if (it > 0) issue_pv(it - 1, true);
+        if (it > 0) issue_pv(it - 1, st_prev, ph_prev, true);
     } else if (warp < 4) {  // ------------------------------------------------------------------- position add (2 warps)
         const int t = threadIdx.x - 64;  // 0..63
-        uint32_t it = 0;
+        int st = 0;
+        uint32_t ph = 0;
         for (int64_t w = w_begin; w < P.B; w += w_step) {
-            for (int h = 0; h < 8; ++h, ++it) {
-                const int st = it & 1;
-                mbar_wait(&tma_full[st], (it >> 1) & 1);
+            for (int h = 0; h < 8; ++h) {
+                mbar_wait(&qk_full[st], ph);
                 uint8_t* base = smem + st * pl.stage;
                 // q += pos.Wq^T, k += pos.Wk^T over the first Lv rows; the operands share one swizzled layout, so the add is
                 // chunk-wise (rows >= Lv of the position buffers are zero)
@@ -258,7 +281,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                 for (int i = t; i < 2 * nchunk; i += 64) {
                     const int m = i >= nchunk, c = m ? i - nchunk : i;
                     uint4* dst = reinterpret_cast<uint4*>(base + m * pl.buf) + c;
-                    const uint4 a = *dst, b = reinterpret_cast<const uint4*>(base + (3 + m) * pl.buf)[c];
+                    const uint4 a = *dst, b = reinterpret_cast<const uint4*>(base + 3 * pl.buf + m * pl.pbuf)[c];
                     uint4 r;
                     const __half2* ah = reinterpret_cast<const __half2*>(&a);
                     const __half2* bh = reinterpret_cast<const __half2*>(&b);
@@ -270,6 +293,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&qk_ready[st]);
+                if (++st == AT_NST) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp < 4 + n_soft) {  // ------------------------------------------------------------ softmax / output warps
@@ -289,7 +313,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
         float* bias = reinterpret_cast<float*>(smem + pl.off_bias) + (warp - 4) * 64;  // this warp's copy: no cross-warp hand-off
         float* xmax = reinterpret_cast<float*>(smem + pl.off_x);    // [AT_G][160]
         float* xsum = xmax + AT_G * 160;                            // [2][AT_G][160]
-        uint8_t* ptile = sP + tile * pl.ptile;
+        uint8_t* ptile = tile ? smem + pl.off_p1 : sP;
+        const int pblk = tile ? pl.p1blk : 16384;                   // bytes per 64-key k-block of the P tile
         const int bar_id = tile ? 5 : 1 + quarter;                  // the four warps that share these rows
         const bool writer = tile == 0 || quarter == 0;              // reads O and writes the output rows
         uint32_t it = 0;
@@ -386,7 +411,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                 float sum0 = 0.f, sum1 = 0.f;
                 auto exp_unit = [&](int u, float* s) {
                     const int c = k0 + u * 16;
-                    uint8_t* kb = ptile + (c >> 6) * 16384;  // k-block of 64 keys
+                    uint8_t* kb = ptile + (c >> 6) * pblk;   // k-block of 64 keys
                     const int c16 = (c & 63) >> 3;           // first 16-byte chunk (8 keys) inside the 128-byte row
                     uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
                     if (!unit_dead(c)) {
@@ -474,7 +499,7 @@ bool enc_attn_tc_supported(int Lv, int Lt, int d_model, int nheads) {
         env = (e && e[0] == '0') ? 0 : 1;
     }
     return env == 1 && d_model == 256 && nheads == 8 && nkp <= AT_MAX_NKP && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
-           nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt).total <= 232448;
+           nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt, Lv).total <= 232448;
 }
 
 int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv,
@@ -499,7 +524,7 @@ int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const i
     P.vlen = vlen; P.tlen = tlen; P.vid_base = vid_base; P.txt_base = txt_base;
     P.B = B; P.Lv = Lv; P.Lt = Lt; P.table_lv = table_lv; P.nkp = nkp; P.ntile = nt; P.indirect = indirect ? 1 : 0;
     P.tpad = indirect ? (Lv & 1) : 0;
-    const AtPlan pl = at_plan(nkp, nt);
+    const AtPlan pl = at_plan(nkp, nt, Lv);
     static int smem_set = 0;
     if (smem_set < pl.total) {
         CONE_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
