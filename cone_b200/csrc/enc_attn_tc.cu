@@ -5,8 +5,10 @@
 // (window, head) — LSU-bound (l1tex 86 %: every q / k / v / position value goes global -> register -> shared -> ldmatrix,
 // the score block lives in mma.sync fragments that need quad shuffles for every row maximum) — against a floor of ~1 600
 // cycles set by the 22 500 exponentials per head.  Here:
-//   * q, k, v and the position-projection rows arrive by TMA (64-byte-swizzled boxes of one head: 32 channels), no register
-//     staging; two helper warps add the position rows to q and k in place (16-byte chunks, layout-agnostic);
+//   * q, k and v arrive by TMA, no register staging: q and k as boxes of a head PAIR (64 channels = 128-byte rows, 128-byte
+//     swizzle; the two heads are the K sub-blocks of one swizzle atom), v as 64-byte-swizzled boxes of one head; narrow rows
+//     are what limits TMA here (ncu: with five 64-byte-row boxes per head the kernel ran at the TMA unit's ~8 cycles per row);
+//     two helper warps add the position-projection rows (read from the L2-resident table) to q and k in place;
 //   * S = Q.K^T runs on tcgen05 (M = 128 per tile, N = padded key count, K = 32) into TMEM; softmax is ONE THREAD PER ROW
 //     on `tcgen05.ld` data: no shuffles, no fragments; P goes back to shared memory as the fp16 A operand (K-major,
 //     128-byte swizzle) and O = P.V is a second tcgen05 product with V used as it lands (MN-major B operand, no transpose);
@@ -36,10 +38,12 @@ namespace {
 
 constexpr int AT_THREADS = 768;
 constexpr int AT_G = 4;         // key ranges = softmax warps per row group
-constexpr int AT_NST = 3;       // operand stages (heads in flight between TMA and the tensor pipe)
 constexpr int AT_HD = 32;       // head dim
-constexpr int AT_ROWB = 64;     // bytes per operand row of one head (32 fp16): the 64-byte swizzle span
+constexpr int AT_VROWB = 64;    // bytes per v row of one head (32 fp16): the 64-byte swizzle span
+constexpr int AT_QROWB = 128;   // bytes per q / k row of a head pair: the 128-byte swizzle span
 constexpr int AT_MAX_NKP = 192; // padded key count supported (TMEM: 2 x NKP + 128 <= 512)
+constexpr int AT_NQS = 2;       // q|k stages (head pairs in flight)
+constexpr int AT_NVS = 4;       // v stages (heads in flight)
 
 // descriptor hi word for 64-byte-swizzled operands: SBO = 8 rows x 64 B = 512 B, version 1, layout SWIZZLE_64B (= 4)
 constexpr uint32_t kDescHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
@@ -72,22 +76,23 @@ struct AtParams {
     const int32_t* tlen;
     const int64_t* vid_base; // layer 0: first frame row of each window (null = dense rows)
     const int64_t* txt_base;
+    const __half* pos;       // position projection [(table_lv + 1) table_lv, 512] fp16: pos.Wq^T | pos.Wk^T
     int64_t B;
     int Lv, Lt, table_lv;
     int nkp;                 // padded key count (multiple of 16)
     int ntile;               // 1 or 2 query tiles of 128 rows
     int indirect;
-    int tpad;                // layer 0 with an odd Lv: the token rows start one row later (TMA destinations are 128-byte aligned)
+    int tpad;                // layer 0 with an odd Lv: the token rows start one row later (v rows are 64 bytes, TMA destinations 128-byte aligned)
 };
 
 // shared-memory plan (bytes), all multiples of 1 KB
 struct AtPlan {
-    int buf;     // one operand buffer: nkp x 64
-    int pbuf;    // one position buffer: Lv x 64
-    int stage;   // Q | K | V | PQ | PK  (rows 128.. of Q as an M = 128 operand run on into K: finite values, unused result rows)
+    int qbuf;    // q or k of a head pair: nkp x 128
+    int qstage;  // q | k  (rows 128.. of q as an M = 128 operand run on into k: finite values, unused result rows)
+    int vbuf;    // v of one head: nkp x 64
     int ptile;   // P of rows 0-127: ceil(nkp / 64) k-blocks of [128 x 128 B]
     int p1blk;   // P of rows 128..: k-blocks of [32 x 128 B]; the M = 128 operand reads on into the next blocks / into P of rows 0-127
-    int off_p1, off_p, off_bias, off_x, off_bar, total;
+    int off_v, off_p1, off_p, off_bias, off_x, off_bar, total;
 };
 // key range g of a window with `units` 16-key units: first unit and unit count
 __host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
@@ -95,43 +100,44 @@ __host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
     *u0 = g * ub + (g < ur ? g : ur);
     *un = ub + (g < ur ? 1 : 0);
 }
-__host__ __device__ inline AtPlan at_plan(int nkp, int ntile, int Lv) {
+__host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
     AtPlan p;
-    p.buf = ((nkp * AT_ROWB + 1023) / 1024) * 1024;
-    p.pbuf = ((Lv * AT_ROWB + 1023) / 1024) * 1024;
-    p.stage = 3 * p.buf + 2 * p.pbuf;
+    p.qbuf = ((nkp * AT_QROWB + 1023) / 1024) * 1024;
+    p.qstage = 2 * p.qbuf;
+    p.vbuf = ((nkp * AT_VROWB + 1023) / 1024) * 1024;
     p.ptile = ((nkp + 63) / 64) * 16384;
     p.p1blk = 4096;
-    p.off_p1 = AT_NST * p.stage;
+    p.off_v = AT_NQS * p.qstage;
+    p.off_p1 = p.off_v + AT_NVS * p.vbuf;
     p.off_p = p.off_p1 + (ntile == 2 ? ((nkp + 63) / 64) * p.p1blk : 0);
-    if (ntile == 2 && p.ptile < 16384) p.off_p += 16384;  // (never: two tiles mean more than 128 keys)
-    p.off_bias = p.off_p + p.ptile;  // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
-    p.off_x = p.off_bias + 20 * 256;         // partial maxima [AT_G][160] and partial sums [2][AT_G][160] (row groups 0-3, 4)
+    p.off_bias = p.off_p + p.ptile;           // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
+    p.off_x = p.off_bias + 20 * 256;          // partial maxima [AT_G][160] and partial sums [2][AT_G][160] (row groups 0-3, 4)
     p.off_bar = p.off_x + 3 * AT_G * 160 * 4;
     p.total = p.off_bar + 256;
     return p;
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B S, 768] (layer 1) or frames [n_frames, 768]
-                   const __grid_constant__ CUtensorMap tmTok,   // tokens [n_tok, 768] (layer 0 only)
-                   const __grid_constant__ CUtensorMap tmPos,   // position projection [(Lv+1) Lv, 512] fp16: pos.Wq^T | pos.Wk^T
+enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair boxes of dense rows [B S, 768] (layer 1) or frames [n_frames, 768]
+                   const __grid_constant__ CUtensorMap tmQKTok, // ... of tokens [n_tok, 768] (layer 0 only)
+                   const __grid_constant__ CUtensorMap tmV,     // one-head boxes of the same tensors
+                   const __grid_constant__ CUtensorMap tmVTok,
                    AtParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    const AtPlan pl = at_plan(P.nkp, P.ntile, P.Lv);
+    const AtPlan pl = at_plan(P.nkp, P.ntile);
     uint8_t* sP = smem + pl.off_p;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bar);
-    uint64_t* qk_full = bars;                 // [AT_NST] q, k and the position rows of a head have landed
-    uint64_t* v_full = bars + AT_NST;         // [AT_NST] v of the head has landed
-    uint64_t* qk_ready = bars + 2 * AT_NST;   // [AT_NST] position rows added to q and k
-    uint64_t* qk_free = bars + 3 * AT_NST;    // [AT_NST] Q.K^T has finished reading q and k: refilled three heads ahead
-    uint64_t* v_free = bars + 4 * AT_NST;     // [AT_NST] P.V has finished reading v
-    uint64_t* s_full = bars + 5 * AT_NST;     // S = Q.K^T complete
-    uint64_t* p_ready = s_full + 1;           // P in shared memory, S read out of TMEM
-    uint64_t* p_free = s_full + 2;            // P.V has finished reading P
-    uint64_t* o_full = s_full + 3;            // [2]
-    uint64_t* o_free = s_full + 5;            // [2]
+    uint64_t* qk_full = bars;                       // [AT_NQS] q and k of a head pair have landed
+    uint64_t* qk_ready = bars + AT_NQS;             // [AT_NQS] position rows added to q and k
+    uint64_t* qk_free = bars + 2 * AT_NQS;          // [AT_NQS] Q.K^T of the pair's second head has finished reading q and k
+    uint64_t* v_full = bars + 3 * AT_NQS;           // [AT_NVS] v of a head has landed
+    uint64_t* v_free = v_full + AT_NVS;             // [AT_NVS] P.V has finished reading v
+    uint64_t* s_full = v_free + AT_NVS;             // S = Q.K^T complete
+    uint64_t* p_ready = s_full + 1;                 // P in shared memory, S read out of TMEM
+    uint64_t* p_free = s_full + 2;                  // P.V has finished reading P
+    uint64_t* o_full = s_full + 3;                  // [2]
+    uint64_t* o_free = s_full + 5;                  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,13 +146,15 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
     const int n_out = (NT == 2) ? 17 : 16;   // ... of which read O (rows 128.. are written out by one warp)
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQkv)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmPos)) : "memory");
-        for (int i = 0; i < AT_NST; ++i) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQK)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+        for (int i = 0; i < AT_NQS; ++i) {
             mbar_init(&qk_full[i], 1);
-            mbar_init(&v_full[i], 1);
             mbar_init(&qk_ready[i], 2);
             mbar_init(&qk_free[i], 1);
+        }
+        for (int i = 0; i < AT_NVS; ++i) {
+            mbar_init(&v_full[i], 1);
             mbar_init(&v_free[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -162,9 +170,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // Rows that TMA never writes must hold finite values: V rows >= S multiply P = 0 (0 x NaN would poison the output),
-    // position rows >= Lv are added to the text rows of q and k and must be zero.
-    for (int i = threadIdx.x; i < (AT_NST * pl.stage) / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    // Rows that TMA never writes must hold finite values: v rows >= S multiply P = 0 (0 x NaN would poison the output)
+    for (int i = threadIdx.x; i < pl.off_p1 / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -177,30 +184,30 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
 
     if (warp == 0) {
         if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producer
-            int st = 0;
-            uint32_t ph = 0;
-            const uint32_t bytes_m = (uint32_t)(S * AT_ROWB), bytes_pos = (uint32_t)(2 * P.Lv * AT_ROWB);
+            int qs = 0, vs = 0;
+            uint32_t qph = 0, vph = 0;
+            const uint32_t bytes_q = (uint32_t)(S * AT_QROWB), bytes_v = (uint32_t)(S * AT_VROWB);
             for (int64_t w = w_begin; w < P.B; w += w_step) {
-                const int vl = P.vlen[w];
                 const int64_t vb = P.indirect ? P.vid_base[w] : w * S;
                 const int64_t tb = P.indirect ? P.txt_base[w] : 0;
                 for (int h = 0; h < 8; ++h) {
-                    uint8_t* base = smem + st * pl.stage;
-                    auto load_m = [&](int m, uint64_t* bar) {  // q, k or v of head h: columns m * 256 + h * 32
-                        tma_load_2d(base + m * pl.buf, &tmQkv, bar, m * 256 + h * AT_HD, (int)vb);
-                        if (P.indirect) tma_load_2d(base + m * pl.buf + (P.Lv + P.tpad) * AT_ROWB, &tmTok, bar, m * 256 + h * AT_HD, (int)tb);
-                    };
-                    mbar_wait(&qk_free[st], ph ^ 1);
-                    mbar_expect_tx(&qk_full[st], 2 * bytes_m + bytes_pos);
-                    load_m(0, &qk_full[st]);
-                    load_m(1, &qk_full[st]);
-                    // position rows of (valid length, head): pos.Wq^T then pos.Wk^T
-                    tma_load_2d(base + 3 * pl.buf, &tmPos, &qk_full[st], h * AT_HD, vl * P.table_lv);
-                    tma_load_2d(base + 3 * pl.buf + pl.pbuf, &tmPos, &qk_full[st], 256 + h * AT_HD, vl * P.table_lv);
-                    mbar_wait(&v_free[st], ph ^ 1);
-                    mbar_expect_tx(&v_full[st], bytes_m);
-                    load_m(2, &v_full[st]);
-                    if (++st == AT_NST) { st = 0; ph ^= 1; }
+                    if ((h & 1) == 0) {  // q and k of heads h, h + 1: columns m * 256 + h * 32 .. + 64
+                        uint8_t* base = smem + qs * pl.qstage;
+                        mbar_wait(&qk_free[qs], qph ^ 1);
+                        mbar_expect_tx(&qk_full[qs], 2 * bytes_q);
+                        for (int m = 0; m < 2; ++m) {
+                            tma_load_2d(base + m * pl.qbuf, &tmQK, &qk_full[qs], m * 256 + h * AT_HD, (int)vb);
+                            if (P.indirect)
+                                tma_load_2d(base + m * pl.qbuf + (P.Lv + P.tpad) * AT_QROWB, &tmQKTok, &qk_full[qs], m * 256 + h * AT_HD, (int)tb);
+                        }
+                        if (++qs == AT_NQS) { qs = 0; qph ^= 1; }
+                    }
+                    uint8_t* vbase = smem + pl.off_v + vs * pl.vbuf;
+                    mbar_wait(&v_free[vs], vph ^ 1);
+                    mbar_expect_tx(&v_full[vs], bytes_v);
+                    tma_load_2d(vbase, &tmV, &v_full[vs], 512 + h * AT_HD, (int)vb);
+                    if (P.indirect) tma_load_2d(vbase + (P.Lv + P.tpad) * AT_VROWB, &tmVTok, &v_full[vs], 512 + h * AT_HD, (int)tb);
+                    if (++vs == AT_NVS) { vs = 0; vph ^= 1; }
                 }
             }
         }
@@ -211,39 +218,40 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
         const uint32_t p_lo = desc_lo_sw128(smem_u32(sP));
         const uint32_t p1_lo = desc_lo_sw128(smem_u32(smem + pl.off_p1));
         uint32_t it = 0;
-        int st = 0, st_prev = 0;
-        uint32_t ph = 0, ph_prev = 0;
-        auto issue_pv = [&](uint32_t itp, int stp, uint32_t php, bool wait_p) {  // O = P . V of the head issued at iteration itp
+        int qs = 0, vs = 0, vs_prev = 0;
+        uint32_t qph = 0, vph = 0, vph_prev = 0;
+        auto issue_pv = [&](uint32_t itp, int vsp, uint32_t vphp, bool wait_p) {  // O = P . V of the head issued at iteration itp
             const int ob = itp & 1;
             if (wait_p) mbar_wait(p_ready, itp & 1);  // (the main loop has already waited: never wait twice on a parity)
-            mbar_wait(&v_full[stp], php);
+            mbar_wait(&v_full[vsp], vphp);
             mbar_wait(&o_free[ob], ((itp >> 1) & 1) ^ 1);
             tc_fence_after();
             if (elect_one_sync()) {
-                const uint32_t v_lo = base_lo + (uint32_t)((stp * pl.stage + 2 * pl.buf) >> 4);
+                const uint32_t v_lo = base_lo + (uint32_t)((pl.off_v + vsp * pl.vbuf) >> 4);
                 for (int t = 0; t < NT; ++t) {
                     const uint32_t d = tmemO + (uint32_t)((ob * NT + t) * AT_HD);
                     for (int j = 0; j < nkp / 16; ++j) {  // 16 keys per MMA: A = P[:, 16 j ..], B = V[16 j .., :]
                         const uint32_t a = t == 0 ? p_lo + (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4)
                                                   : p1_lo + (uint32_t)(((j >> 2) * pl.p1blk + (j & 3) * 32) >> 4);
-                        const uint32_t b = v_lo + (uint32_t)((j * 16 * AT_ROWB) >> 4);
+                        const uint32_t b = v_lo + (uint32_t)((j * 16 * AT_VROWB) >> 4);
                         umma_f16_desc(d, a, kDescHiSw128, b, kDescHiSw64, idO, j > 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&o_full[ob]);
                 umma_commit(p_free);
-                umma_commit(&v_free[stp]);
+                umma_commit(&v_free[vsp]);
             }
             __syncwarp();
         };
         for (int64_t w = w_begin; w < P.B; w += w_step) {
             for (int h = 0; h < 8; ++h, ++it) {
-                mbar_wait(&qk_ready[st], ph);
+                if ((h & 1) == 0) mbar_wait(&qk_ready[qs], qph);
                 if (it > 0) mbar_wait(p_ready, (it - 1) & 1);  // S of the previous head has been read out of TMEM
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const uint32_t q_lo = base_lo + (uint32_t)((st * pl.stage) >> 4), k_lo = q_lo + (uint32_t)(pl.buf >> 4);
-                    for (int k = 0; k < 2; ++k) umma_f16_desc(tmemS, q_lo + 2 * k, kDescHiSw64, k_lo + 2 * k, kDescHiSw64, idS, k > 0 ? 1u : 0u);
+                    // the head is the (h & 1)-th 64-byte half of the pair's 128-byte rows: K sub-blocks 2 (h & 1), 2 (h & 1) + 1
+                    const uint32_t q_lo = base_lo + (uint32_t)((qs * pl.qstage) >> 4) + 4 * (h & 1), k_lo = q_lo + (uint32_t)(pl.qbuf >> 4);
+                    for (int k = 0; k < 2; ++k) umma_f16_desc(tmemS, q_lo + 2 * k, kDescHiSw128, k_lo + 2 * k, kDescHiSw128, idS, k > 0 ? 1u : 0u);
                     if (NT == 2) {
                         // rows 128..: key range g against the Q rows starting at 128 - 32 g -> these rows land in lane quarter g
                         for (int g = 0; g < AT_G; ++g) {
@@ -251,49 +259,73 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
                             at_range(nkp >> 4, g, &u0, &un);
                             if (un == 0) continue;
                             const uint32_t idg = (1u << 4) | ((uint32_t)((un * 16) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                            const uint32_t a = q_lo + (uint32_t)(((128 - 32 * g) * AT_ROWB) >> 4), b = k_lo + (uint32_t)((u0 * 16 * AT_ROWB) >> 4);
+                            const uint32_t a = q_lo + (uint32_t)(((128 - 32 * g) * AT_QROWB) >> 4), b = k_lo + (uint32_t)((u0 * 16 * AT_QROWB) >> 4);
                             for (int k = 0; k < 2; ++k)
-                                umma_f16_desc(tmemS + (uint32_t)(nkp + u0 * 16), a + 2 * k, kDescHiSw64, b + 2 * k, kDescHiSw64, idg, k > 0 ? 1u : 0u);
+                                umma_f16_desc(tmemS + (uint32_t)(nkp + u0 * 16), a + 2 * k, kDescHiSw128, b + 2 * k, kDescHiSw128, idg, k > 0 ? 1u : 0u);
                         }
                     }
                     umma_commit(s_full);
-                    umma_commit(&qk_free[st]);
+                    if (h & 1) umma_commit(&qk_free[qs]);
                 }
                 __syncwarp();
-                if (it > 0) issue_pv(it - 1, st_prev, ph_prev, false);  // overlaps the softmax of this head
-                st_prev = st;
-                ph_prev = ph;
-                if (++st == AT_NST) { st = 0; ph ^= 1; }
+                if (h & 1) {
+                    if (++qs == AT_NQS) { qs = 0; qph ^= 1; }
+                }
+                if (it > 0) issue_pv(it - 1, vs_prev, vph_prev, false);  // overlaps the softmax of this head
+                vs_prev = vs;
+                vph_prev = vph;
+                if (++vs == AT_NVS) { vs = 0; vph ^= 1; }
             }
         }
-        if (it > 0) issue_pv(it - 1, st_prev, ph_prev, true);
+        if (it > 0) issue_pv(it - 1, vs_prev, vph_prev, true);
     } else if (warp < 4) {  // ------------------------------------------------------------------- position add (2 warps)
+        // q += pos.Wq^T, k += pos.Wk^T over the first Lv rows of both heads of the pair: 16-byte chunks (8 channels), the
+        // position rows come from the table (L2-resident: 2 x 64 channels x Lv rows per pair), 8 loads in flight per thread
         const int t = threadIdx.x - 64;  // 0..63
-        int st = 0;
-        uint32_t ph = 0;
+        int qs = 0;
+        uint32_t qph = 0;
+        const int nchunk = P.Lv * 8;     // per matrix
         for (int64_t w = w_begin; w < P.B; w += w_step) {
-            for (int h = 0; h < 8; ++h) {
-                mbar_wait(&qk_full[st], ph);
-                uint8_t* base = smem + st * pl.stage;
-                // q += pos.Wq^T, k += pos.Wk^T over the first Lv rows; the operands share one swizzled layout, so the add is
-                // chunk-wise (rows >= Lv of the position buffers are zero)
-                const int nchunk = (P.Lv * AT_ROWB + 15) / 16;
-                for (int i = t; i < 2 * nchunk; i += 64) {
-                    const int m = i >= nchunk, c = m ? i - nchunk : i;
-                    uint4* dst = reinterpret_cast<uint4*>(base + m * pl.buf) + c;
-                    const uint4 a = *dst, b = reinterpret_cast<const uint4*>(base + 3 * pl.buf + m * pl.pbuf)[c];
-                    uint4 r;
-                    const __half2* ah = reinterpret_cast<const __half2*>(&a);
-                    const __half2* bh = reinterpret_cast<const __half2*>(&b);
-                    __half2* rh = reinterpret_cast<__half2*>(&r);
+            const __half* ptab = P.pos + (int64_t)P.vlen[w] * P.table_lv * 512;
+            for (int hp = 0; hp < 4; ++hp) {
+                uint8_t* base = smem + qs * pl.qstage;
+                bool waited = false;
+                for (int i0 = t; i0 < 2 * nchunk; i0 += 64 * 8) {
+                    uint4 pv[8];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) rh[e] = __hadd2(ah[e], bh[e]);  // exact sum, one rounding
-                    *dst = r;
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * 64;
+                        if (i < 2 * nchunk) {
+                            const int m = i >= nchunk, c = m ? i - nchunk : i;
+                            pv[u] = __ldg(reinterpret_cast<const uint4*>(ptab + (int64_t)(c >> 3) * 512 + m * 256 + hp * 64 + (c & 7) * 8));
+                        }
+                    }
+                    if (!waited) {
+                        mbar_wait(&qk_full[qs], qph);
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * 64;
+                        if (i < 2 * nchunk) {
+                            const int m = i >= nchunk, c = m ? i - nchunk : i;
+                            uint4* dst = reinterpret_cast<uint4*>(base + m * pl.qbuf + sw128(c >> 3, c & 7));
+                            const uint4 a = *dst;
+                            uint4 r;
+                            const __half2* ah = reinterpret_cast<const __half2*>(&a);
+                            const __half2* bh = reinterpret_cast<const __half2*>(&pv[u]);
+                            __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) rh[e] = __hadd2(ah[e], bh[e]);  // exact sum, one rounding
+                            *dst = r;
+                        }
+                    }
                 }
+                if (!waited) mbar_wait(&qk_full[qs], qph);
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&qk_ready[st]);
-                if (++st == AT_NST) { st = 0; ph ^= 1; }
+                if (lane == 0) mbar_arrive(&qk_ready[qs]);
+                if (++qs == AT_NQS) { qs = 0; qph ^= 1; }
             }
         }
     } else if (warp < 4 + n_soft) {  // ------------------------------------------------------------ softmax / output warps
@@ -458,8 +490,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQkv,   // dense rows [B
     }
 }
 
-// 2-D map with a 64-byte inner box (one head: 32 fp16) and the 64-byte swizzle
-int make_map_sw64(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D fp16 map with an inner box of `box_cols` channels: 32 -> 64-byte rows and swizzle, 64 -> 128-byte rows and swizzle
+int make_map_box(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -476,14 +508,14 @@ int make_map_sw64(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
     }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)AT_HD, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled (64-byte swizzle) failed (%d) for [%lld x %lld] ld %lld box %d", (int)r, (long long)rows,
-                  (long long)cols, (long long)ld, box_rows);
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld box %d x %d", (int)r, (long long)rows, (long long)cols,
+                  (long long)ld, box_rows, box_cols);
         return CONE_ERR_CUDA;
     }
     return CONE_OK;
@@ -498,8 +530,8 @@ bool enc_attn_tc_supported(int Lv, int Lt, int d_model, int nheads) {
         const char* e = getenv("CONE_ATTN_TC");
         env = (e && e[0] == '0') ? 0 : 1;
     }
-    return env == 1 && d_model == 256 && nheads == 8 && nkp <= AT_MAX_NKP && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
-           nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt, Lv).total <= 232448;
+    return env == 1 && d_model == 256 && nheads == 8 && nkp <= AT_MAX_NKP && nkp <= 160 && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
+           nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt).total <= 232448;
 }
 
 int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv,
@@ -512,19 +544,24 @@ int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const i
     CONE_REQUIRE((ldo % 8) == 0, "enc_attn_tc: output rows must be 16-byte aligned");
     const bool indirect = token_qkv != nullptr;
     CONE_REQUIRE(!indirect || (vid_base && txt_base && n_tok > 0), "enc_attn_tc: incomplete row tables");
-    CUtensorMap mQ, mT, mP;
+    CUtensorMap mQ, mQT, mV, mVT;
     // dense: one box of S rows; indirect: Lv frame rows + Lt token rows
-    CONE_TRY(make_map_sw64(&mQ, qkv, rows, 768, 768, indirect ? Lv : S));
-    mT = mQ;
-    if (indirect) CONE_TRY(make_map_sw64(&mT, token_qkv, n_tok, 768, 768, Lt));
-    CONE_TRY(make_map_sw64(&mP, posqk16, (int64_t)(table_lv + 1) * table_lv, 512, 512, Lv));
+    CONE_TRY(make_map_box(&mQ, qkv, rows, 768, 768, indirect ? Lv : S, 64));
+    CONE_TRY(make_map_box(&mV, qkv, rows, 768, 768, indirect ? Lv : S, 32));
+    mQT = mQ;
+    mVT = mV;
+    if (indirect) {
+        CONE_TRY(make_map_box(&mQT, token_qkv, n_tok, 768, 768, Lt, 64));
+        CONE_TRY(make_map_box(&mVT, token_qkv, n_tok, 768, 768, Lt, 32));
+    }
     AtParams P{};
     P.out = static_cast<__half*>(o);
     P.ldo = ldo;
     P.vlen = vlen; P.tlen = tlen; P.vid_base = vid_base; P.txt_base = txt_base;
+    P.pos = static_cast<const __half*>(posqk16);
     P.B = B; P.Lv = Lv; P.Lt = Lt; P.table_lv = table_lv; P.nkp = nkp; P.ntile = nt; P.indirect = indirect ? 1 : 0;
     P.tpad = indirect ? (Lv & 1) : 0;
-    const AtPlan pl = at_plan(nkp, nt, Lv);
+    const AtPlan pl = at_plan(nkp, nt);
     static int smem_set = 0;
     if (smem_set < pl.total) {
         CONE_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
@@ -532,7 +569,7 @@ int enc_attn_tc_run(const void* qkv, int64_t rows, void* o, int64_t ldo, const i
     }
     const unsigned grid = (unsigned)(B < num_sms ? B : num_sms);
     ProfScope ps(s, P_ENC_ATTN, 4.0 * (double)B * 8 * S * S * AT_HD, 8.0 * (double)B * S * 8 * AT_HD);
-    enc_attn_tc_kernel<<<grid, AT_THREADS, pl.total, s>>>(mQ, mT, mP, P);
+    enc_attn_tc_kernel<<<grid, AT_THREADS, pl.total, s>>>(mQ, mQT, mV, mVT, P);
     CONE_LAUNCH_CHECK("enc_attn_tc");
     return CONE_OK;
 }
