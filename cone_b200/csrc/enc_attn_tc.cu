@@ -138,7 +138,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
     uint64_t* p_free = s_full + 2;                  // P.V has finished reading P
     uint64_t* o_full = s_full + 3;                  // [2]
     uint64_t* o_free = s_full + 5;                  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
+    uint64_t* s_free = s_full + 7;                  // S copied to registers: the next head's Q.K^T may overwrite it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.Lv + P.Lt, nkp = P.nkp, NT = P.ntile;
@@ -163,6 +164,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         }
         mbar_init(s_full, 1);
         mbar_init(p_ready, n_soft);
+        mbar_init(s_free, n_soft);
         mbar_init(p_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -182,6 +184,11 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
 
     const int64_t w_begin = blockIdx.x, w_step = gridDim.x;
 
+    // 768 threads leave 80 registers each; the softmax warps hold their 48 scores in registers across the exchange of the row
+    // maxima, the four service warps (one warpgroup) need few: 128 x 40 registers move to the five softmax warpgroups
+    // (each setmaxnreg sits inside its role's branch: code reachable from both would be compiled for the smaller budget)
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producer
             int qs = 0, vs = 0;
@@ -246,7 +253,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         for (int64_t w = w_begin; w < P.B; w += w_step) {
             for (int h = 0; h < 8; ++h, ++it) {
                 if ((h & 1) == 0) mbar_wait(&qk_ready[qs], qph);
-                if (it > 0) mbar_wait(p_ready, (it - 1) & 1);  // S of the previous head has been read out of TMEM
+                if (it > 0) mbar_wait(s_free, (it - 1) & 1);  // S of the previous head is in the softmax warps' registers
                 tc_fence_after();
                 if (elect_one_sync()) {
                     // the head is the (h & 1)-th 64-byte half of the pair's 128-byte rows: K sub-blocks 2 (h & 1), 2 (h & 1) + 1
@@ -271,16 +278,16 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                 if (h & 1) {
                     if (++qs == AT_NQS) { qs = 0; qph ^= 1; }
                 }
-                if (it > 0) issue_pv(it - 1, vs_prev, vph_prev, false);  // overlaps the softmax of this head
+                if (it > 0) issue_pv(it - 1, vs_prev, vph_prev, true);  // while the softmax warps reduce this head's scores
                 vs_prev = vs;
                 vph_prev = vph;
                 if (++vs == AT_NVS) { vs = 0; vph ^= 1; }
             }
         }
         if (it > 0) issue_pv(it - 1, vs_prev, vph_prev, true);
-    } else if (warp < 4) {  // ------------------------------------------------------------------- position add (2 warps)
+    } else {  // ---------------------------------------------------------------------------------- position add (2 warps)
         // q += pos.Wq^T, k += pos.Wk^T over the first Lv rows of both heads of the pair: 16-byte chunks (8 channels), the
-        // position rows come from the table (L2-resident: 2 x 64 channels x Lv rows per pair), 8 loads in flight per thread
+        // position rows come from the table (L2-resident: 2 x 64 channels x Lv rows per pair), 4 loads in flight per thread
         const int t = threadIdx.x - 64;  // 0..63
         int qs = 0;
         uint32_t qph = 0;
@@ -290,10 +297,10 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
             for (int hp = 0; hp < 4; ++hp) {
                 uint8_t* base = smem + qs * pl.qstage;
                 bool waited = false;
-                for (int i0 = t; i0 < 2 * nchunk; i0 += 64 * 8) {
-                    uint4 pv[8];
+                for (int i0 = t; i0 < 2 * nchunk; i0 += 64 * 4) {
+                    uint4 pv[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < 4; ++u) {
                         const int i = i0 + u * 64;
                         if (i < 2 * nchunk) {
                             const int m = i >= nchunk, c = m ? i - nchunk : i;
@@ -305,7 +312,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                         waited = true;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < 4; ++u) {
                         const int i = i0 + u * 64;
                         if (i < 2 * nchunk) {
                             const int m = i >= nchunk, c = m ? i - nchunk : i;
@@ -328,7 +335,9 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                 if (++qs == AT_NQS) { qs = 0; qph ^= 1; }
             }
         }
+    }
     } else if (warp < 4 + n_soft) {  // ------------------------------------------------------------ softmax / output warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         const int tile = warp >= 20 ? 1 : 0;    // row group: rows 0-127 | rows 128..
         const int quarter = warp & 3;           // TMEM lane quarter (= SM sub-partition) of this warp
         const int g = tile ? quarter : (warp - 4) >> 2;  // key range
@@ -411,63 +420,58 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
             for (int h = 0; h < 8; ++h, ++it) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                // pass 1: maximum of the row over this warp's keys; the TMEM load of unit u + 1 is in flight while unit u is reduced
-                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
-                float sa[16], sb[16];
-                auto max_unit = [&](int u, float* s) {
-                    const int c = k0 + u * 16;
-                    if (unit_dead(c)) return;
-                    if (!unit_clean(c)) add_bias(u, s);
+                // this warp's scores (<= 48 keys) move to registers and S is released at once: the next head's Q.K^T runs
+                // under this head's softmax
+                float sv[3][16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); m2 = fmaxf(m2, s[j + 2]); m3 = fmaxf(m3, s[j + 3]);
+                for (int u = 0; u < 3; ++u)
+                    if (u < un) tmem_ld_32x16(tS + u * 16, sv[u]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free);
+                // pass 1: maximum of the row over this warp's keys
+                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int c = k0 + u * 16;
+                    if (u < un && !unit_dead(c)) {
+                        if (!unit_clean(c)) add_bias(u, sv[u]);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            m0 = fmaxf(m0, sv[u][j]); m1 = fmaxf(m1, sv[u][j + 1]); m2 = fmaxf(m2, sv[u][j + 2]); m3 = fmaxf(m3, sv[u][j + 3]);
+                        }
                     }
-                };
-                if (un > 0) tmem_ld_32x16(tS, sa);
-                for (int u = 0; u < un; u += 2) {
-                    tmem_ld_wait();
-                    if (u + 1 < un) tmem_ld_32x16(tS + (u + 1) * 16, sb);
-                    max_unit(u, sa);
-                    if (u + 1 >= un) break;
-                    tmem_ld_wait();
-                    if (u + 2 < un) tmem_ld_32x16(tS + (u + 2) * 16, sa);
-                    max_unit(u + 1, sb);
                 }
                 xmax[g * 160 + xrow] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                if (un > 0) tmem_ld_32x16(tS, sa);  // first unit of pass 2: in flight across the exchange
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 const float mx = fmaxf(fmaxf(xmax[xrow], xmax[160 + xrow]), fmaxf(xmax[320 + xrow], xmax[480 + xrow]));
                 const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
                 const float off = (mx == -CUDART_INF_F) ? 0.f : -mx * sl2;
                 // pass 2: p = exp2(s * sl2 - max * sl2) -> fp16 P tile (K-major, 128-byte swizzle), fp32 partial row sum
                 float sum0 = 0.f, sum1 = 0.f;
-                auto exp_unit = [&](int u, float* s) {
-                    const int c = k0 + u * 16;
-                    uint8_t* kb = ptile + (c >> 6) * pblk;   // k-block of 64 keys
-                    const int c16 = (c & 63) >> 3;           // first 16-byte chunk (8 keys) inside the 128-byte row
-                    uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-                    if (!unit_dead(c)) {
-                        if (!unit_clean(c)) add_bias(u, s);
-                        float e[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(s[j], sl2, off));
-                        sum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-                        sum1 += ((e[8] + e[9]) + (e[10] + e[11])) + ((e[12] + e[13]) + (e[14] + e[15]));
-                        v0 = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
-                        v1 = make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
-                    }
-                    *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16)) = v0;
-                    *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16 + 1)) = v1;
-                };
                 if (it > 0) mbar_wait(p_free, (it - 1) & 1);  // P.V of the previous head has finished reading P
-                for (int u = 0; u < un; u += 2) {
-                    tmem_ld_wait();
-                    if (u + 1 < un) tmem_ld_32x16(tS + (u + 1) * 16, sb);
-                    exp_unit(u, sa);
-                    if (u + 1 >= un) break;
-                    tmem_ld_wait();
-                    if (u + 2 < un) tmem_ld_32x16(tS + (u + 2) * 16, sa);
-                    exp_unit(u + 1, sb);
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    if (u < un) {
+                        const int c = k0 + u * 16;
+                        uint8_t* kb = ptile + (c >> 6) * pblk;   // k-block of 64 keys
+                        const int c16 = (c & 63) >> 3;           // first 16-byte chunk (8 keys) inside the 128-byte row
+                        const bool dead = unit_dead(c);
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {  // 8 keys = one 16-byte chunk of the P row
+                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                            if (!dead) {
+                                float* e = &sv[u][hf * 8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(e[j], sl2, off));
+                                if (hf == 0) sum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+                                else sum1 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+                                v = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
+                            }
+                            *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16 + hf)) = v;
+                        }
+                    }
                 }
                 xsum[((it & 1) * AT_G + g) * 160 + xrow] = sum0 + sum1;
                 tc_fence_before();
