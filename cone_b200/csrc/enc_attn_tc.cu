@@ -92,7 +92,7 @@ struct AtPlan {
     int vbuf;    // v of one head: nkp x 64
     int ptile;   // P of rows 0-127: ceil(nkp / 64) k-blocks of [128 x 128 B]
     int p1blk;   // P of rows 128..: k-blocks of [32 x 128 B]; the M = 128 operand reads on into the next blocks / into P of rows 0-127
-    int off_v, off_p1, off_p, off_bias, off_x, off_bar, total;
+    int off_v, off_p1, off_p, off_bias, off_x, off_park, off_bar, total;
 };
 // key range g of a window with `units` 16-key units: first unit and unit count
 __host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
@@ -112,7 +112,8 @@ __host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
     p.off_p = p.off_p1 + (ntile == 2 ? ((nkp + 63) / 64) * p.p1blk : 0);
     p.off_bias = p.off_p + p.ptile;           // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
     p.off_x = p.off_bias + 20 * 256;          // partial maxima [AT_G][160] and partial sums [2][AT_G][160] (row groups 0-3, 4)
-    p.off_bar = p.off_x + 3 * AT_G * 160 * 4;
+    p.off_park = p.off_x + 3 * AT_G * 160 * 4;  // [10][16][32] fp32: the third 16-key unit of key ranges 0 and 1 between the passes
+    p.off_bar = p.off_park + 10 * 2048;
     p.total = p.off_bar + 256;
     return p;
 }
@@ -352,6 +353,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         const int k0 = u0 * 16;                                    // first key of this warp's range
         const uint32_t tS = tmemS + lane_base + (uint32_t)(tile * nkp + k0);
         float* bias = reinterpret_cast<float*>(smem + pl.off_bias) + (warp - 4) * 64;  // this warp's copy: no cross-warp hand-off
+        float* park = reinterpret_cast<float*>(smem + pl.off_park) + (tile ? 8 + (g & 1) : quarter * 2 + (g & 1)) * 512;  // [16][32]
         float* xmax = reinterpret_cast<float*>(smem + pl.off_x);    // [AT_G][160]
         float* xsum = xmax + AT_G * 160;                            // [2][AT_G][160]
         uint8_t* ptile = tile ? smem + pl.off_p1 : sP;
@@ -422,27 +424,35 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                 tc_fence_after();
                 // this warp's scores (<= 48 keys) move to registers and S is released at once: the next head's Q.K^T runs
                 // under this head's softmax
-                float sv[3][16];
+                float sv[2][16];
+                // pass 1: maximum of the row over this warp's keys
+                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+                auto max_unit = [&](int u, float* sx) {
+                    const int c = k0 + u * 16;
+                    if (unit_dead(c)) return;
+                    if (!unit_clean(c)) add_bias(u, sx);
 #pragma unroll
-                for (int u = 0; u < 3; ++u)
+                    for (int j = 0; j < 16; j += 4) {
+                        m0 = fmaxf(m0, sx[j]); m1 = fmaxf(m1, sx[j + 1]); m2 = fmaxf(m2, sx[j + 2]); m3 = fmaxf(m3, sx[j + 3]);
+                    }
+                };
+                if (un > 2) {  // a third unit exists only in key ranges 0 and 1: it waits in shared memory between the passes
+                    tmem_ld_32x16(tS + 32, sv[0]);
+                    tmem_ld_wait();
+                    max_unit(2, sv[0]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) park[j * 32 + lane] = sv[0][j];
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
                     if (u < un) tmem_ld_32x16(tS + u * 16, sv[u]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_free);
-                // pass 1: maximum of the row over this warp's keys
-                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int c = k0 + u * 16;
-                    if (u < un && !unit_dead(c)) {
-                        if (!unit_clean(c)) add_bias(u, sv[u]);
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            m0 = fmaxf(m0, sv[u][j]); m1 = fmaxf(m1, sv[u][j + 1]); m2 = fmaxf(m2, sv[u][j + 2]); m3 = fmaxf(m3, sv[u][j + 3]);
-                        }
-                    }
-                }
+                for (int u = 0; u < 2; ++u)
+                    if (u < un) max_unit(u, sv[u]);
                 xmax[g * 160 + xrow] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 const float mx = fmaxf(fmaxf(xmax[xrow], xmax[160 + xrow]), fmaxf(xmax[320 + xrow], xmax[480 + xrow]));
@@ -450,29 +460,34 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                 const float off = (mx == -CUDART_INF_F) ? 0.f : -mx * sl2;
                 // pass 2: p = exp2(s * sl2 - max * sl2) -> fp16 P tile (K-major, 128-byte swizzle), fp32 partial row sum
                 float sum0 = 0.f, sum1 = 0.f;
+                auto exp_unit = [&](int u, float* sx, bool parked) {
+                    const int c = k0 + u * 16;
+                    uint8_t* kb = ptile + (c >> 6) * pblk;   // k-block of 64 keys
+                    const int c16 = (c & 63) >> 3;           // first 16-byte chunk (8 keys) inside the 128-byte row
+                    const bool dead = unit_dead(c);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {  // 8 keys = one 16-byte chunk of the P row
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (!dead) {
+                            float* e = sx + hf * 8;
+                            if (parked) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) e[j] = park[(hf * 8 + j) * 32 + lane];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(e[j], sl2, off));
+                            if (hf == 0) sum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+                            else sum1 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+                            v = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
+                        }
+                        *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16 + hf)) = v;
+                    }
+                };
                 if (it > 0) mbar_wait(p_free, (it - 1) & 1);  // P.V of the previous head has finished reading P
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    if (u < un) {
-                        const int c = k0 + u * 16;
-                        uint8_t* kb = ptile + (c >> 6) * pblk;   // k-block of 64 keys
-                        const int c16 = (c & 63) >> 3;           // first 16-byte chunk (8 keys) inside the 128-byte row
-                        const bool dead = unit_dead(c);
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {  // 8 keys = one 16-byte chunk of the P row
-                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                            if (!dead) {
-                                float* e = &sv[u][hf * 8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(e[j], sl2, off));
-                                if (hf == 0) sum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-                                else sum1 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-                                v = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
-                            }
-                            *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16 + hf)) = v;
-                        }
-                    }
-                }
+                for (int u = 0; u < 2; ++u)
+                    if (u < un) exp_unit(u, sv[u], false);
+                if (un > 2) exp_unit(2, sv[0], true);
                 xsum[((it & 1) * AT_G + g) * 160 + xrow] = sum0 + sum1;
                 tc_fence_before();
                 fence_async_smem();
