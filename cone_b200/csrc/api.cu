@@ -660,7 +660,7 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
                                              b.token_qkv, b.n_tokens, b.vid_base, b.txt_base, tc_num_sms(t), c.s));
                 } else {
                     CONE_TRY(enc_self_attention_f16(nullptr, 3 * d, nullptr, 3 * d, b.att16, d, b.vlen, b.tlen, b.B, b.Lv, b.Lt, H,
-                                                    c.w->pos_qk[l], dm.max_v_l, c.s, b.frame_qkv, b.token_qkv, b.vid_base,
+                                                    pos16, dm.max_v_l, c.s, b.frame_qkv, b.token_qkv, b.vid_base,
                                                     b.txt_base, b.n_frames));
                 }
             } else {
@@ -672,7 +672,7 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
                                              nullptr, nullptr, tc_num_sms(t), c.s));
                 } else {
                     CONE_TRY(enc_self_attention_f16(b.qkv16, 3 * d, b.qkv16 + 2 * d, 3 * d, b.att16, d, b.vlen, b.tlen, b.B,
-                                                    b.Lv, b.Lt, H, c.w->pos_qk[l], dm.max_v_l, c.s));
+                                                    b.Lv, b.Lt, H, pos16, dm.max_v_l, c.s));
                 }
             }
             const bool last_enc = (l == dm.enc_layers - 1);

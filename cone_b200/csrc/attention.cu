@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, NB <= 20 ? 4 : 2)
 enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __half* __restrict__ v, int64_t ldv,
                          __half* __restrict__ o, int64_t ldo, const int32_t* __restrict__ vlen,
                          const int32_t* __restrict__ tlen, int Lv, int Lt, int d_model,
-                         const float* __restrict__ posqk, int table_lv, EncRowSource src) {
+                         const __half* __restrict__ posqk, int table_lv, EncRowSource src) {
     extern __shared__ __align__(16) unsigned char att_smem[];
     const int S = Lv + Lt;
     const int Sp = (S + 15) & ~15;
@@ -459,7 +459,7 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
         }
     }
     const int vl = vlen[b], tl = tlen[b];
-    const float* pp = posqk + ((int64_t)vl * table_lv + r0) * (2 * d_model) + c8;
+    const __half* pp = posqk + ((int64_t)vl * table_lv + r0) * (2 * d_model) + c8;
     unsigned char* sbase = att_smem + (r0 * QK_PAD + (threadIdx.x & 3) * 8) * 2;  // this thread's chunk of row r0 in Qs
     const int mat_bytes = Sp * QK_PAD * 2;
 #pragma unroll
@@ -469,22 +469,18 @@ enc_attention_f16_kernel(const __half* __restrict__ qk, int64_t ldqk, const __ha
             if (posqk != nullptr && r < Lv) {
                 // q = (src + pos) Wq^T + bq = (src Wq^T + bq) + pos Wq^T: the position term comes from a per-layer
                 // table indexed by (valid length, row), so no position-added copy of the activations exists
-                const float* pr = pp + it * ROWS_PER_IT * 2 * d_model;
-                const float4 pq0 = __ldg(reinterpret_cast<const float4*>(pr));
-                const float4 pq1 = __ldg(reinterpret_cast<const float4*>(pr) + 1);
-                const float4 pk0 = __ldg(reinterpret_cast<const float4*>(pr + d_model));
-                const float4 pk1 = __ldg(reinterpret_cast<const float4*>(pr + d_model) + 1);
+                const __half* pr = pp + it * ROWS_PER_IT * 2 * d_model;
+                const uint4 pq = __ldg(reinterpret_cast<const uint4*>(pr));
+                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(pr + d_model));
                 __half2* qh = reinterpret_cast<__half2*>(&q4[it]);
                 __half2* kh = reinterpret_cast<__half2*>(&k4[it]);
-                float2 f;
-                f = __half22float2(qh[0]); qh[0] = __floats2half2_rn(f.x + pq0.x, f.y + pq0.y);
-                f = __half22float2(qh[1]); qh[1] = __floats2half2_rn(f.x + pq0.z, f.y + pq0.w);
-                f = __half22float2(qh[2]); qh[2] = __floats2half2_rn(f.x + pq1.x, f.y + pq1.y);
-                f = __half22float2(qh[3]); qh[3] = __floats2half2_rn(f.x + pq1.z, f.y + pq1.w);
-                f = __half22float2(kh[0]); kh[0] = __floats2half2_rn(f.x + pk0.x, f.y + pk0.y);
-                f = __half22float2(kh[1]); kh[1] = __floats2half2_rn(f.x + pk0.z, f.y + pk0.w);
-                f = __half22float2(kh[2]); kh[2] = __floats2half2_rn(f.x + pk1.x, f.y + pk1.y);
-                f = __half22float2(kh[3]); kh[3] = __floats2half2_rn(f.x + pk1.z, f.y + pk1.w);
+                const __half2* pqh = reinterpret_cast<const __half2*>(&pq);
+                const __half2* pkh = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {  // exact sum of two fp16 values, one rounding
+                    qh[e] = __hadd2(qh[e], pqh[e]);
+                    kh[e] = __hadd2(kh[e], pkh[e]);
+                }
             }
             unsigned char* sp = sbase + it * ROWS_PER_IT * QK_PAD * 2;
             *reinterpret_cast<uint4*>(sp) = q4[it];
@@ -935,7 +931,7 @@ int dec_cross_attention(const void* q_any, int64_t ldq, const void* k, int64_t l
 
 int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
                            const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
-                           const float* posqk, int table_lv, cudaStream_t s, const void* frame_qkv,
+                           const void* posqk16, int table_lv, cudaStream_t s, const void* frame_qkv,
                            const void* token_qkv, const int64_t* vid_base, const int64_t* txt_base, int64_t n_frames) {
     if (B == 0) return CONE_OK;
     const int S = Lv + Lt;
@@ -950,7 +946,7 @@ int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t 
     __half* o16 = static_cast<__half*>(o);
 #define CONE_ENC_ATT(NBV, EX)                                                                                      \
     enc_attention_f16_kernel<NBV, EX><<<grid, ATT_WARPS * 32, smem, s>>>(qk16, ldqk, v16, ldv, o16, ldo, vlen, tlen, Lv, Lt, \
-                                                                       nheads * HD, posqk, table_lv, rs)
+                                                                       nheads * HD, static_cast<const __half*>(posqk16), table_lv, rs)
     EncRowSource rs{static_cast<const __half*>(frame_qkv), static_cast<const __half*>(token_qkv), vid_base, txt_base, n_frames};
     CONE_REQUIRE(frame_qkv == nullptr || (token_qkv && vid_base && txt_base && n_frames > 0),
                  "enc_self_attention_f16: incomplete row tables");

@@ -546,8 +546,10 @@ bool enc_attn_tc_supported(int Lv, int Lt, int d_model, int nheads) {
     const int S = Lv + Lt + (Lv & 1), nkp = (S + 15) & ~15, nt = (S + 127) / 128;
     static int env = -1;
     if (env < 0) {
+        // opt-in: on the benchmark windows (150 rows, 8 heads of 32) this kernel runs at 3.1 ms per launch against 2.75 ms of
+        // the mma.sync kernel (profiles/r02_notes.md §5: the exponentials, not the products, bound both)
         const char* e = getenv("CONE_ATTN_TC");
-        env = (e && e[0] == '0') ? 0 : 1;
+        env = (e && e[0] == '1') ? 1 : 0;
     }
     return env == 1 && d_model == 256 && nheads == 8 && nkp <= AT_MAX_NKP && nkp <= 160 && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
            nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt).total <= 232448;

@@ -73,7 +73,7 @@ int enc_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
 // posqk (nullable): per-layer table [(table_lv+1)*table_lv, 2*d] = pos . [Wq; Wk]^T added to q | k of video rows
 int enc_self_attention_f16(const void* qk, int64_t ldqk, const void* v, int64_t ldv, void* o, int64_t ldo,
                            const int32_t* vlen, const int32_t* tlen, int64_t B, int Lv, int Lt, int nheads,
-                           const float* posqk, int table_lv, cudaStream_t s, const void* frame_qkv = nullptr,
+                           const void* posqk16, int table_lv, cudaStream_t s, const void* frame_qkv = nullptr,
                            const void* token_qkv = nullptr, const int64_t* vid_base = nullptr,
                            const int64_t* txt_base = nullptr, int64_t n_frames = 0);
 // tcgen05 version (enc_attn_tc.cu): qkv = dense window rows [B S, 768] (token_qkv null) or the per-frame rows [rows, 768] with
