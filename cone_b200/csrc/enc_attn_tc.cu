@@ -43,7 +43,7 @@ constexpr int AT_VROWB = 64;    // bytes per v row of one head (32 fp16): the 64
 constexpr int AT_QROWB = 128;   // bytes per q / k row of a head pair: the 128-byte swizzle span
 constexpr int AT_MAX_NKP = 192; // padded key count supported (TMEM: 2 x NKP + 128 <= 512)
 constexpr int AT_NQS = 2;       // q|k stages (head pairs in flight)
-constexpr int AT_NVS = 4;       // v stages (heads in flight)
+constexpr int AT_NVS = 3;       // v stages (heads in flight)
 
 // descriptor hi word for 64-byte-swizzled operands: SBO = 8 rows x 64 B = 512 B, version 1, layout SWIZZLE_64B (= 4)
 constexpr uint32_t kDescHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
@@ -90,9 +90,11 @@ struct AtPlan {
     int qbuf;    // q or k of a head pair: nkp x 128
     int qstage;  // q | k  (rows 128.. of q as an M = 128 operand run on into k: finite values, unused result rows)
     int vbuf;    // v of one head: nkp x 64
-    int ptile;   // P of rows 0-127: ceil(nkp / 64) k-blocks of [128 x 128 B]
-    int p1blk;   // P of rows 128..: k-blocks of [32 x 128 B]; the M = 128 operand reads on into the next blocks / into P of rows 0-127
-    int off_v, off_p1, off_p, off_bias, off_x, off_park, off_bar, total;
+    // One P set = [P of rows 128..: two k-blocks of [32 x 128 B] + a 64-byte-swizzled tail block [32 x 64 B] for keys 128-159]
+    //             [P of rows 0-127: two k-blocks of [128 x 128 B] + tail block [128 x 64 B]].
+    // The M = 128 operand of rows 128.. reads on into the blocks behind it (finite values, unused result rows).
+    int p1_tail, p0, p0_tail, pset;
+    int off_v, off_p, off_bias, off_x, off_bar, total;
 };
 // key range g of a window with `units` 16-key units: first unit and unit count
 __host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
@@ -105,15 +107,16 @@ __host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
     p.qbuf = ((nkp * AT_QROWB + 1023) / 1024) * 1024;
     p.qstage = 2 * p.qbuf;
     p.vbuf = ((nkp * AT_VROWB + 1023) / 1024) * 1024;
-    p.ptile = ((nkp + 63) / 64) * 16384;
-    p.p1blk = 4096;
+    const int nblk = nkp > 64 ? 2 : 1;       // 128-byte-swizzled k-blocks of 64 keys (keys 128.. go to the tail block)
+    p.p1_tail = ntile == 2 ? nblk * 4096 : 0;
+    p.p0 = ntile == 2 ? p.p1_tail + 2048 : 0;
+    p.p0_tail = p.p0 + nblk * 16384;
+    p.pset = p.p0_tail + (nkp > 128 ? 8192 : 0);
     p.off_v = AT_NQS * p.qstage;
-    p.off_p1 = p.off_v + AT_NVS * p.vbuf;
-    p.off_p = p.off_p1 + (ntile == 2 ? ((nkp + 63) / 64) * p.p1blk : 0);
-    p.off_bias = p.off_p + p.ptile;           // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
+    p.off_p = p.off_v + AT_NVS * p.vbuf;      // two P sets: the softmax of head h + 1 writes while P.V of head h reads
+    p.off_bias = p.off_p + 2 * p.pset;        // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
     p.off_x = p.off_bias + 20 * 256;          // partial maxima [AT_G][160] and partial sums [2][AT_G][160] (row groups 0-3, 4)
-    p.off_park = p.off_x + 3 * AT_G * 160 * 4;  // [10][16][32] fp32: the third 16-key unit of key ranges 0 and 1 between the passes
-    p.off_bar = p.off_park + 10 * 2048;
+    p.off_bar = p.off_x + 3 * AT_G * 160 * 4;
     p.total = p.off_bar + 256;
     return p;
 }
@@ -127,7 +130,6 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     const AtPlan pl = at_plan(P.nkp, P.ntile);
-    uint8_t* sP = smem + pl.off_p;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bar);
     uint64_t* qk_full = bars;                       // [AT_NQS] q and k of a head pair have landed
     uint64_t* qk_ready = bars + AT_NQS;             // [AT_NQS] position rows added to q and k
@@ -136,11 +138,11 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
     uint64_t* v_free = v_full + AT_NVS;             // [AT_NVS] P.V has finished reading v
     uint64_t* s_full = v_free + AT_NVS;             // S = Q.K^T complete
     uint64_t* p_ready = s_full + 1;                 // P in shared memory, S read out of TMEM
-    uint64_t* p_free = s_full + 2;                  // P.V has finished reading P
-    uint64_t* o_full = s_full + 3;                  // [2]
-    uint64_t* o_free = s_full + 5;                  // [2]
-    uint64_t* s_free = s_full + 7;                  // S copied to registers: the next head's Q.K^T may overwrite it
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+    uint64_t* p_free = s_full + 2;                  // [2] P.V has finished reading the P set
+    uint64_t* o_full = s_full + 4;                  // [2]
+    uint64_t* o_free = s_full + 6;                  // [2]
+    uint64_t* s_free = s_full + 8;                  // S copied to registers: the next head's Q.K^T may overwrite it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = P.Lv + P.Lt, nkp = P.nkp, NT = P.ntile;
@@ -162,11 +164,11 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         for (int i = 0; i < 2; ++i) {
             mbar_init(&o_full[i], 1);
             mbar_init(&o_free[i], n_out);
+            mbar_init(&p_free[i], 1);
         }
         mbar_init(s_full, 1);
         mbar_init(p_ready, n_soft);
         mbar_init(s_free, n_soft);
-        mbar_init(p_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -174,7 +176,7 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // Rows that TMA never writes must hold finite values: v rows >= S multiply P = 0 (0 x NaN would poison the output)
-    for (int i = threadIdx.x; i < pl.off_p1 / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < pl.off_p / 16; i += AT_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -223,8 +225,6 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         const uint32_t idS = (1u << 4) | ((uint32_t)(nkp >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                 // K-major A, B
         const uint32_t idO = (1u << 4) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // B (= V) MN-major
         const uint32_t base_lo = desc_lo_sw128(smem_u32(smem));  // (address >> 4) | LBO = 1
-        const uint32_t p_lo = desc_lo_sw128(smem_u32(sP));
-        const uint32_t p1_lo = desc_lo_sw128(smem_u32(smem + pl.off_p1));
         uint32_t it = 0;
         int qs = 0, vs = 0, vs_prev = 0;
         uint32_t qph = 0, vph = 0, vph_prev = 0;
@@ -236,17 +236,20 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint32_t v_lo = base_lo + (uint32_t)((pl.off_v + vsp * pl.vbuf) >> 4);
+                const uint32_t set_lo = base_lo + (uint32_t)((pl.off_p + ob * pl.pset) >> 4);  // P set of this head
                 for (int t = 0; t < NT; ++t) {
                     const uint32_t d = tmemO + (uint32_t)((ob * NT + t) * AT_HD);
+                    const bool t1 = NT == 2 && t == 1;  // rows 128..
+                    const uint32_t blk_lo = set_lo + (uint32_t)((t1 ? 0 : pl.p0) >> 4), blk_sz = t1 ? 4096u : 16384u;
+                    const uint32_t tail_lo = set_lo + (uint32_t)((t1 ? pl.p1_tail : pl.p0_tail) >> 4);
                     for (int j = 0; j < nkp / 16; ++j) {  // 16 keys per MMA: A = P[:, 16 j ..], B = V[16 j .., :]
-                        const uint32_t a = t == 0 ? p_lo + (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4)
-                                                  : p1_lo + (uint32_t)(((j >> 2) * pl.p1blk + (j & 3) * 32) >> 4);
                         const uint32_t b = v_lo + (uint32_t)((j * 16 * AT_VROWB) >> 4);
-                        umma_f16_desc(d, a, kDescHiSw128, b, kDescHiSw64, idO, j > 0 ? 1u : 0u);
+                        if (j < 8) umma_f16_desc(d, blk_lo + (((uint32_t)(j >> 2) * blk_sz + (uint32_t)(j & 3) * 32u) >> 4), kDescHiSw128, b, kDescHiSw64, idO, j > 0 ? 1u : 0u);
+                        else umma_f16_desc(d, tail_lo + (uint32_t)(((j - 8) * 32) >> 4), kDescHiSw64, b, kDescHiSw64, idO, 1u);
                     }
                 }
                 umma_commit(&o_full[ob]);
-                umma_commit(p_free);
+                umma_commit(&p_free[ob]);
                 umma_commit(&v_free[vsp]);
             }
             __syncwarp();
@@ -353,11 +356,10 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         const int k0 = u0 * 16;                                    // first key of this warp's range
         const uint32_t tS = tmemS + lane_base + (uint32_t)(tile * nkp + k0);
         float* bias = reinterpret_cast<float*>(smem + pl.off_bias) + (warp - 4) * 64;  // this warp's copy: no cross-warp hand-off
-        float* park = reinterpret_cast<float*>(smem + pl.off_park) + (tile ? 8 + (g & 1) : quarter * 2 + (g & 1)) * 512;  // [16][32]
         float* xmax = reinterpret_cast<float*>(smem + pl.off_x);    // [AT_G][160]
         float* xsum = xmax + AT_G * 160;                            // [2][AT_G][160]
-        uint8_t* ptile = tile ? smem + pl.off_p1 : sP;
-        const int pblk = tile ? pl.p1blk : 16384;                   // bytes per 64-key k-block of the P tile
+        const int p_blk0 = pl.off_p + (tile ? 0 : pl.p0), p_tail = pl.off_p + (tile ? pl.p1_tail : pl.p0_tail);  // in P set 0
+        const int pblk = tile ? 4096 : 16384;                       // bytes per 64-key k-block of the P tile
         const int bar_id = tile ? 5 : 1 + quarter;                  // the four warps that share these rows
         const bool writer = tile == 0 || quarter == 0;              // reads O and writes the output rows
         uint32_t it = 0;
@@ -425,7 +427,9 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                 // this warp's scores (<= 48 keys) move to registers and S is released at once: the next head's Q.K^T runs
                 // under this head's softmax
                 float sv[2][16];
-                // pass 1: maximum of the row over this warp's keys
+                // pass 1: maximum of the row over this warp's keys.  Two 16-key units stay in registers; a third unit exists
+                // only in key ranges 0 and 1: it is reduced first and read from TMEM again in pass 2, which delays those
+                // warps' release of S to the first third of pass 2 (still long before the next head's scores are needed)
                 float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
                 auto max_unit = [&](int u, float* sx) {
                     const int c = k0 + u * 16;
@@ -436,20 +440,21 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                         m0 = fmaxf(m0, sx[j]); m1 = fmaxf(m1, sx[j + 1]); m2 = fmaxf(m2, sx[j + 2]); m3 = fmaxf(m3, sx[j + 3]);
                     }
                 };
-                if (un > 2) {  // a third unit exists only in key ranges 0 and 1: it waits in shared memory between the passes
+                const bool third = un > 2 && !unit_dead(k0 + 32);
+                if (third) {
                     tmem_ld_32x16(tS + 32, sv[0]);
                     tmem_ld_wait();
                     max_unit(2, sv[0]);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) park[j * 32 + lane] = sv[0][j];
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
                     if (u < un) tmem_ld_32x16(tS + u * 16, sv[u]);
                 tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_free);
+                if (!third) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free);
+                }
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
                     if (u < un) max_unit(u, sv[u]);
@@ -458,36 +463,46 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
                 const float mx = fmaxf(fmaxf(xmax[xrow], xmax[160 + xrow]), fmaxf(xmax[320 + xrow], xmax[480 + xrow]));
                 const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
                 const float off = (mx == -CUDART_INF_F) ? 0.f : -mx * sl2;
-                // pass 2: p = exp2(s * sl2 - max * sl2) -> fp16 P tile (K-major, 128-byte swizzle), fp32 partial row sum
+                // pass 2: p = exp2(s * sl2 - max * sl2) -> fp16 P set it & 1 (K-major; 128-byte swizzle, keys 128.. in the
+                // 64-byte-swizzled tail block), fp32 partial row sum
                 float sum0 = 0.f, sum1 = 0.f;
-                auto exp_unit = [&](int u, float* sx, bool parked) {
+                uint8_t* pset = smem + (it & 1) * pl.pset;
+                auto exp_unit = [&](int u, float* sx) {
                     const int c = k0 + u * 16;
-                    uint8_t* kb = ptile + (c >> 6) * pblk;   // k-block of 64 keys
-                    const int c16 = (c & 63) >> 3;           // first 16-byte chunk (8 keys) inside the 128-byte row
                     const bool dead = unit_dead(c);
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {  // 8 keys = one 16-byte chunk of the P row
                         uint4 v = make_uint4(0u, 0u, 0u, 0u);
                         if (!dead) {
                             float* e = sx + hf * 8;
-                            if (parked) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) e[j] = park[(hf * 8 + j) * 32 + lane];
-                            }
 #pragma unroll
                             for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(e[j], sl2, off));
                             if (hf == 0) sum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
                             else sum1 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
                             v = make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
                         }
-                        *reinterpret_cast<uint4*>(kb + sw128(prow_i, c16 + hf)) = v;
+                        uint8_t* dst;
+                        if (c < 128) {
+                            dst = pset + p_blk0 + (c >> 6) * pblk + sw128(prow_i, ((c & 63) >> 3) + hf);
+                        } else {  // 64-byte rows: 16-byte chunk index XOR (row / 2) % 4
+                            const int ch = ((c - 128) >> 3) + hf;
+                            dst = pset + p_tail + prow_i * 64 + ((ch ^ ((prow_i >> 1) & 3)) << 4);
+                        }
+                        *reinterpret_cast<uint4*>(dst) = v;
                     }
                 };
-                if (it > 0) mbar_wait(p_free, (it - 1) & 1);  // P.V of the previous head has finished reading P
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (u < un) exp_unit(u, sv[u], false);
-                if (un > 2) exp_unit(2, sv[0], true);
+                if (it > 1) mbar_wait(&p_free[it & 1], ((it >> 1) & 1) ^ 1);  // P.V of head it - 2 has finished reading this set
+                if (un > 0) exp_unit(0, sv[0]);
+                if (third) {
+                    tmem_ld_32x16(tS + 32, sv[0]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free);
+                    if (!unit_clean(k0 + 32)) add_bias(2, sv[0]);
+                }
+                if (un > 1) exp_unit(1, sv[1]);
+                if (un > 2) exp_unit(2, sv[0]);  // (a dead third unit only writes its zeros)
                 xsum[((it & 1) * AT_G + g) * 160 + xrow] = sum0 + sum1;
                 tc_fence_before();
                 fence_async_smem();
@@ -551,7 +566,7 @@ bool enc_attn_tc_supported(int Lv, int Lt, int d_model, int nheads) {
         const char* e = getenv("CONE_ATTN_TC");
         env = (e && e[0] == '1') ? 1 : 0;
     }
-    return env == 1 && d_model == 256 && nheads == 8 && nkp <= AT_MAX_NKP && nkp <= 160 && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
+    return env == 1 && d_model == 256 && nheads == 8 && (nkp <= 128 || nkp == 160) && nt <= 2 && Lv <= 256 && Lt >= 1 && Lt <= 256 &&
            nt * nkp + 2 * nt * AT_HD <= 512 && at_plan(nkp, nt).total <= 232448;
 }
 
