@@ -41,9 +41,9 @@ constexpr int AT_G = 4;         // key ranges = softmax warps per row group
 constexpr int AT_HD = 32;       // head dim
 constexpr int AT_VROWB = 64;    // bytes per v row of one head (32 fp16): the 64-byte swizzle span
 constexpr int AT_QROWB = 128;   // bytes per q / k row of a head pair: the 128-byte swizzle span
+constexpr int AT_MAX_NKP = 192; // padded key count supported (TMEM: 2 x NKP + 128 <= 512)
 constexpr int AT_NQS = 2;       // q|k stages (head pairs in flight)
-constexpr int AT_NVS = 2;       // v stages (heads in flight)
-constexpr int AT_RING = 12;     // position-row loads in flight per position-add thread (1 KB of shared memory each)
+constexpr int AT_NVS = 3;       // v stages (heads in flight)
 
 // descriptor hi word for 64-byte-swizzled operands: SBO = 8 rows x 64 B = 512 B, version 1, layout SWIZZLE_64B (= 4)
 constexpr uint32_t kDescHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
@@ -94,7 +94,7 @@ struct AtPlan {
     //             [P of rows 0-127: two k-blocks of [128 x 128 B] + tail block [128 x 64 B]].
     // The M = 128 operand of rows 128.. reads on into the blocks behind it (finite values, unused result rows).
     int p1_tail, p0, p0_tail, pset;
-    int off_v, off_p, off_bias, off_x, off_stage, off_bar, total;
+    int off_v, off_p, off_bias, off_x, off_bar, total;
 };
 // key range g of a window with `units` 16-key units: first unit and unit count
 __host__ __device__ inline void at_range(int units, int g, int* u0, int* un) {
@@ -116,8 +116,7 @@ __host__ __device__ inline AtPlan at_plan(int nkp, int ntile) {
     p.off_p = p.off_v + AT_NVS * p.vbuf;      // two P sets: the softmax of head h + 1 writes while P.V of head h reads
     p.off_bias = p.off_p + 2 * p.pset;        // [20][64] fp32 additive key mask of the warp's key range (one copy per warp)
     p.off_x = p.off_bias + 20 * 256;          // partial maxima [AT_G][160] and partial sums [2][AT_G][160] (row groups 0-3, 4)
-    p.off_stage = p.off_x + 3 * AT_G * 160 * 4;  // [AT_RING][64 threads][16 B] position rows on their way in
-    p.off_bar = p.off_stage + AT_RING * 1024;
+    p.off_bar = p.off_x + 3 * AT_G * 160 * 4;
     p.total = p.off_bar + 256;
     return p;
 }
@@ -291,66 +290,55 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK,    // head-pair box
         }
         if (it > 0) issue_pv(it - 1, vs_prev, vph_prev, true);
     } else {  // ---------------------------------------------------------------------------------- position add (2 warps)
-        // q += pos.Wq^T, k += pos.Wk^T over the first Lv rows of both heads of the pair, in 16-byte chunks (8 channels).  The
-        // position rows come from the L2-resident fp16 table; a load costs ~700 cycles and these warps have 40 registers, so
-        // the rows travel by cp.async through a per-thread ring of AT_RING slots in shared memory: 12 loads per thread stay
-        // in flight, across pair and window boundaries (the sequence of chunks is known in advance).
+        // q += pos.Wq^T, k += pos.Wk^T over the first Lv rows of both heads of the pair: 16-byte chunks (8 channels), the
+        // position rows come from the table (L2-resident: 2 x 64 channels x Lv rows per pair), 4 loads in flight per thread
         const int t = threadIdx.x - 64;  // 0..63
-        uint8_t* stg = smem + pl.off_stage + t * 16;  // slot s of this thread: stg + s * 1024
-        const int nchunk = P.Lv * 8;     // per matrix
-        const int per_pair = (2 * nchunk - t + 63) / 64;  // this thread's chunks of a pair: i = t + 64 n
-        int64_t wi = w_begin;
-        int hpi = 0, ni = 0, slot_i = 0;
-        const __half* ptabi = wi < P.B ? P.pos + (int64_t)P.vlen[wi] * P.table_lv * 512 : nullptr;
-        auto issue_one = [&]() {
-            if (wi < P.B) {
-                const int i = t + 64 * ni;
-                const int m = i >= nchunk, c = m ? i - nchunk : i;
-                const __half* src = ptabi + (int64_t)(c >> 3) * 512 + m * 256 + hpi * 64 + (c & 7) * 8;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg + slot_i * 1024)), "l"(src) : "memory");
-                if (++ni == per_pair) {
-                    ni = 0;
-                    if (++hpi == 4) {
-                        hpi = 0;
-                        wi += w_step;
-                        if (wi < P.B) ptabi = P.pos + (int64_t)P.vlen[wi] * P.table_lv * 512;
-                    }
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group past the end keeps the count in step)
-            slot_i = slot_i + 1 == AT_RING ? 0 : slot_i + 1;
-        };
-        for (int r = 0; r < AT_RING; ++r) issue_one();
-        int qs = 0, slot_c = 0;
+        int qs = 0;
         uint32_t qph = 0;
+        const int nchunk = P.Lv * 8;     // per matrix
         for (int64_t w = w_begin; w < P.B; w += w_step) {
+            const __half* ptab = P.pos + (int64_t)P.vlen[w] * P.table_lv * 512;
             for (int hp = 0; hp < 4; ++hp) {
                 uint8_t* base = smem + qs * pl.qstage;
-                mbar_wait(&qk_full[qs], qph);
-                for (int n = 0; n < per_pair; ++n) {
-                    asm volatile("cp.async.wait_group %0;" ::"n"(AT_RING - 1) : "memory");  // the oldest load has landed
-                    const uint4 pv = *reinterpret_cast<const uint4*>(stg + slot_c * 1024);
-                    const int i = t + 64 * n;
-                    const int m = i >= nchunk, c = m ? i - nchunk : i;
-                    uint4* dst = reinterpret_cast<uint4*>(base + m * pl.qbuf + sw128(c >> 3, c & 7));
-                    const uint4 a = *dst;
-                    uint4 r;
-                    const __half2* ah = reinterpret_cast<const __half2*>(&a);
-                    const __half2* bh = reinterpret_cast<const __half2*>(&pv);
-                    __half2* rh = reinterpret_cast<__half2*>(&r);
+                bool waited = false;
+                for (int i0 = t; i0 < 2 * nchunk; i0 += 64 * 4) {
+                    uint4 pv[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) rh[e] = __hadd2(ah[e], bh[e]);  // exact sum, one rounding
-                    *dst = r;
-                    issue_one();  // refills the slot just consumed (its value has been used above)
-                    slot_c = slot_c + 1 == AT_RING ? 0 : slot_c + 1;
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * 64;
+                        if (i < 2 * nchunk) {
+                            const int m = i >= nchunk, c = m ? i - nchunk : i;
+                            pv[u] = __ldg(reinterpret_cast<const uint4*>(ptab + (int64_t)(c >> 3) * 512 + m * 256 + hp * 64 + (c & 7) * 8));
+                        }
+                    }
+                    if (!waited) {
+                        mbar_wait(&qk_full[qs], qph);
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * 64;
+                        if (i < 2 * nchunk) {
+                            const int m = i >= nchunk, c = m ? i - nchunk : i;
+                            uint4* dst = reinterpret_cast<uint4*>(base + m * pl.qbuf + sw128(c >> 3, c & 7));
+                            const uint4 a = *dst;
+                            uint4 r;
+                            const __half2* ah = reinterpret_cast<const __half2*>(&a);
+                            const __half2* bh = reinterpret_cast<const __half2*>(&pv[u]);
+                            __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) rh[e] = __hadd2(ah[e], bh[e]);  // exact sum, one rounding
+                            *dst = r;
+                        }
+                    }
                 }
+                if (!waited) mbar_wait(&qk_full[qs], qph);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&qk_ready[qs]);
                 if (++qs == AT_NQS) { qs = 0; qph ^= 1; }
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     } else if (warp < 4 + n_soft) {  // ------------------------------------------------------------ softmax / output warps
         asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
