@@ -221,163 +221,6 @@ def test_video_context_and_frame_scores_vs_oracle():
 
 
 # --------------------------------------------------------------------------------------- end to end
-@pytest.mark.parametrize("name", list(E2E_CASES))
-def test_fuse_nms_operator_boundary_exact(name):
-    """Fed the reference's own raw model outputs, rows / fusion / proposal / matching lists are identical."""
-    cfg, sd, ds, arrays, lists = load_e2e(name)
-    eng = engine_for(cfg, E2E_CASES[name][2], E2E_CASES[name][3])
-    ora = {q.query_id: O.slice_query_windows(torch.from_numpy(ds.videos[q.video_idx]), lists[q.query_id]["ranklist"],
-                                             cfg.topk_window, cfg.max_v_l) for q in ds.queries}
-    k, ns, nq = cfg.topk_window, cfg.num_queries, len(ds.queries)
-    spans = torch.zeros((nq, k, ns, 2)); prob = torch.zeros((nq, k, ns)); match = torch.zeros((nq, k, ns))
-    wstart = torch.zeros((nq, k), dtype=torch.int32); wlen = torch.zeros((nq, k), dtype=torch.int32)
-    for j, q in enumerate(ds.queries):
-        n = len(ora[q.query_id])
-        spans[j, :n] = torch.from_numpy(arrays[f"{q.query_id}/pred_spans"])
-        prob[j, :n] = torch.from_numpy(arrays[f"{q.query_id}/prob_fg"])
-        match[j, :n] = torch.from_numpy(arrays[f"{q.query_id}/match"])
-        for t, (s, ln, _) in enumerate(ora[q.query_id]):
-            wstart[j, t], wlen[j, t] = s, ln
-    out, cnt, rows, rcnt = eng.fuse_nms(spans.to(DEV), prob.to(DEV), match.to(DEV), wstart.to(DEV), wlen.to(DEV),
-                                        want_rows=True)
-    out, cnt, rows, rcnt = out.cpu().numpy(), cnt.cpu().numpy(), rows.cpu().numpy(), rcnt.cpu().numpy()
-    for j, q in enumerate(ds.queries):
-        g = lists[q.query_id]
-        assert rows[j, : rcnt[j]].tolist() == g["rows"], q.query_id
-        for m, key in enumerate(("fusion", "proposal", "matching")):
-            assert out[j, m, : cnt[j, m]].tolist() == g[key], (q.query_id, key)
-
-
-def test_fuse_nms_without_nms_and_large_candidate_sets():
-    """nms_thd = -1 (inference.py:125-127) and the stress shape: k = 200 windows -> 1000 candidates."""
-    cfg = EGO4D.replace(topk_window=200, nms_thd=-1, max_after_nms=10)
-    eng = engine_for(EGO4D, 0)
-    rng = np.random.default_rng(5)
-    nq, k, ns = 3, 200, 5
-    spans = torch.from_numpy(rng.uniform(0.05, 0.95, (nq, k, ns, 2)).astype(np.float32))
-    prob = torch.from_numpy(np.round(rng.uniform(0, 1, (nq, k, ns)), 2).astype(np.float32))  # many ties
-    match = torch.from_numpy(rng.uniform(-1, 1, (nq, k, ns)).astype(np.float32))
-    wstart = torch.from_numpy((np.arange(k, dtype=np.int32) * 45)[None].repeat(nq, 0))
-    wlen = torch.full((nq, k), 90, dtype=torch.int32)
-    wlen[1, 150:] = 0  # a video with fewer windows than k
-    for thd in (-1, 0.5):
-        c2 = cfg.replace(nms_thd=thd)
-        out, cnt, _, _ = eng.fuse_nms(spans.to(DEV), prob.to(DEV), match.to(DEV), wstart.to(DEV), wlen.to(DEV), cfg=c2)
-        out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
-        for j in range(nq):
-            n = int((wlen[j] > 0).sum())
-            wins = [(int(wstart[j, t]), int(wlen[j, t])) for t in range(n)]
-            pp = O.postprocess_query(c2, wins, spans[j, :n], prob[j, :n], match[j, :n])
-            for m, key in enumerate(("fusion", "proposal", "matching")):
-                assert out[j, m, : cnt[j, m]].tolist() == pp[key], (thd, j, key)
-
-
-# ---------------------------------------------------------------------------------------------- K2
-@pytest.mark.parametrize("name", list(E2E_CASES))
-def test_window_ranklist_operator_boundary_exact(name):
-    cfg, sd, ds, arrays, lists = load_e2e(name)
-    n = 0
-    for q in ds.queries:
-        key = f"{q.query_id}/frame_score"
-        if key in arrays:
-            got = ops.compute_window_ranklist(torch.from_numpy(arrays[key]).to(DEV), cfg.max_v_l)
-            assert got == lists[q.query_id]["ranklist"]
-            n += 1
-    assert n >= 2
-
-
-def test_window_ranklist_ties_and_long_videos():
-    """Heavy exact ties (scores quantised to one decimal) and the 10-hour stress length; ties -> lower index."""
-    rng = np.random.default_rng(1)
-    for L, mvl in ((1, 90), (44, 90), (45, 90), (46, 90), (900, 90), (2000, 125), (45017, 125), (180000, 90), (180000, 125)):
-        fs = np.round(rng.standard_normal(L), 1).astype(np.float32)
-        got = ops.compute_window_ranklist(torch.from_numpy(fs).to(DEV), mvl)
-        want = O.window_ranklist(torch.from_numpy(fs), mvl)
-        assert got == want, (L, mvl)
-        assert sorted(got) == list(range(len(got)))  # a permutation of all windows
-
-
-# ---------------------------------------------------------------------------------------- K3/K4/K5
-@pytest.mark.parametrize("name,cfg,wseed", [("dense_ego4d", EGO4D, 3), ("dense_mad512", MAD512, 4)])
-def test_forward_and_matching_dense_vs_reference(name, cfg, wseed):
-    """`model(**inputs)` and `forward_clip_matching` of the drop-in module vs the reference's outputs."""
-    g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    model = CONE(cfg, init_state_dict(cfg, wseed), aux_loss=True).to(DEV).eval()
-    vid, vm, txt, tm, cls = [t.to(DEV) for t in dense_case(cfg, 100 + wseed)]
-    out = model(src_txt=txt, src_txt_mask=tm, src_vid_motion=vid, src_vid_motion_mask=vm)
-    assert_close(out["pred_logits"].cpu(), g["pred_logits"], FP32_TOL, "pred_logits")
-    assert_close(out["pred_spans"].cpu(), g["pred_spans"], FP32_TOL, "pred_spans")
-    assert_close(out["saliency_scores"].cpu(), g["saliency"], FP32_TOL, "saliency")
-    assert_close(out["aux_outputs"][0]["pred_spans"].cpu(), g["aux_spans"], FP32_TOL, "aux_spans")
-    assert_close(out["aux_outputs"][0]["pred_logits"].cpu(), g["aux_logits"], FP32_TOL, "aux_logits")
-    # operator boundary: matching is fed the reference's spans, so the floor/ceil bounds are identical
-    match = model.forward_clip_matching(src_cls_txt=cls, src_vid_appear=vid, src_vid_appear_mask=vm,
-                                        proposal=torch.from_numpy(g["pred_spans"]).to(DEV))
-    assert_close(match.cpu(), g["match"], FP32_TOL, "match")
-    adapted = model.adapter_layer(vid[0]) + vid[0]
-    assert_close(adapted.cpu(), g["adapted0"], FP32_TOL, "adapter")
-
-
-def test_forward_dense_vs_oracle_mad768_ragged():
-    cfg = MAD768
-    sd = init_state_dict(cfg, 11)
-    model = CONE(cfg, sd).to(DEV).eval()
-    vid, vm, txt, tm, cls = dense_case(cfg, 77)
-    with torch.no_grad():
-        want = O.cone_forward(sd, txt, tm, vid, vm)
-        wmatch = O.clip_matching(sd, cls, vid, vm, want["pred_spans"])
-    out = model(src_txt=txt.to(DEV), src_txt_mask=tm.to(DEV), src_vid_motion=vid.to(DEV), src_vid_motion_mask=vm.to(DEV))
-    assert_close(out["pred_logits"].cpu(), want["pred_logits"], FP32_TOL, "pred_logits")
-    assert_close(out["pred_spans"].cpu(), want["pred_spans"], FP32_TOL, "pred_spans")
-    match = model.forward_clip_matching(cls.to(DEV), vid.to(DEV), vm.to(DEV), proposal=want["pred_spans"].to(DEV))
-    assert_close(match.cpu(), wmatch, FP32_TOL, "match")
-
-
-def test_padded_row_pooling_and_empty_slice():
-    """`end` clips to the PADDED length, pad rows are averaged in, empty slice -> NaN."""
-    cfg = EGO4D
-    sd = init_state_dict(cfg, 2)
-    eng = engine_for(cfg, 2)
-    g = torch.Generator().manual_seed(3)
-    vid = torch.randn(3, 90, cfg.v_feat_dim, generator=g)
-    vlen = torch.tensor([45, 90, 10], dtype=torch.int32)
-    vm = (torch.arange(90)[None] < vlen[:, None]).float()
-    vid = vid * vm[..., None]
-    cls = torch.randn(3, cfg.v_feat_dim, generator=g)
-    spans = torch.tensor([[[0.9, 0.8], [0.5, 0.2], [0.95, 0.1], [0.3, 1.0], [0.6, 0.6]]] * 3)  # ends past the valid rows
-    spans[2, 0] = torch.tensor([1.0, 0.0])  # start = end = dur at an integer boundary -> empty slice -> NaN
-    with torch.no_grad():
-        want = O.clip_matching(sd, cls, vid, vm, spans)
-    got = eng.clip_matching(cls.to(DEV), vid.to(DEV), vlen.to(DEV), spans.to(DEV)).cpu()
-    assert torch.isnan(want[2, 0]) and torch.isnan(got[2, 0])
-    ok = ~torch.isnan(want)
-    assert_close(got[ok], want[ok], FP32_TOL, "padded pooling")
-
-
-# ------------------------------------------------------------------------------------- stage 0 / 1
-def test_video_context_and_frame_scores_vs_oracle():
-    cfg = MAD512
-    sd = init_state_dict(cfg, 5)
-    eng = engine_for(cfg, 5)
-    ds = make_dataset(cfg, 2, [1500, 333], [4, 3], seed=9)
-    with torch.no_grad():
-        want_ctx = [O.stage0_video_context(sd, torch.from_numpy(O.l2_normalize_np(v))) for v in ds.videos]
-        want_vp = [O.input_proj(sd, "input_vid_proj", torch.from_numpy(v)) for v in ds.videos]
-    frames = torch.from_numpy(np.concatenate(ds.videos)).to(DEV)
-    ctx, vp = eng.video_prepare(frames)
-    assert_close(ctx.cpu(), torch.cat(want_ctx), FP32_TOL, "ctx")
-    assert_close(vp.cpu(), torch.cat(want_vp), FP32_TOL, "vidproj")
-    qb = pack_queries(cfg, [len(v) for v in ds.videos], ds.queries).to(DEV)
-    cls_n = eng.l2_normalize(qb.cls, 1e-5)
-    scores, offs = eng.frame_scores(ctx, qb, cls_n)
-    scores, offs = scores.cpu(), offs.cpu().tolist()
-    for j, i in enumerate(qb.order):
-        q = ds.queries[i]
-        want = torch.einsum("db,b->d", want_ctx[q.video_idx], torch.from_numpy(O.l2_normalize_np(q.cls)))
-        assert_close(scores[offs[j]: offs[j] + len(want)], want, FP32_TOL, "frame scores")
-
-
-# --------------------------------------------------------------------------------------- end to end
 def _tie_audit(win_scores, k, rel=1e-5):
     """near-ties between DIFFERENT frames at the top-k boundary may legitimately flip between
     CPU and GPU fp32; exact ties (shared frame) may not."""
