@@ -46,6 +46,8 @@ SIGNATURES = {
     "cone_encoder_tail": (C.c_int, [_p, _i32, _p, _p, _i64, _p, _i32, _p, _sz, _p]),
     "cone_frame_scores": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _p, _p, C.c_int, _p]),
     "cone_window_ranklist": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _i32, _p]),
+    "cone_prefilter_workspace_bytes": (_sz, [_p, _i64, _i32]),
+    "cone_prefilter": (C.c_int, [_p, _p, _i64, _p, _i32, _i32, _p, _p, _p, _sz, _p]),
     "cone_ground_windows": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _i32,
                                       _p, _p, _p, _p, _p, _p, _sz, C.c_int, _p]),
     "cone_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, C.c_int, _p]),

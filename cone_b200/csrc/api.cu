@@ -1047,6 +1047,58 @@ extern "C" int cone_window_ranklist(const float* frame_score, const int64_t* sco
                            ranklist_stride, (cudaStream_t)stream);
 }
 
+// ---- A1-A3 for one video in one call (SURVEY.md §8b `cone_prefilter`)
+static int prefilter_windows(const cone_dims& dm, int64_t L) { return (int)((L + dm.max_v_l / 2 - 1) / (dm.max_v_l / 2)) + 1; }
+
+extern "C" size_t cone_prefilter_workspace_bytes(const cone_dims* dims, int64_t L, int32_t n_queries) {
+    if (check_dims(dims) != CONE_OK || L <= 0 || n_queries < 0) return 0;
+    Arena a(nullptr, 0);
+    const int nw = prefilter_windows(*dims, L);
+    a.get<float>(L * dims->v_dim);                    // ctx
+    a.get<float>((int64_t)n_queries * dims->v_dim);   // normalised CLS
+    a.get<float>((int64_t)n_queries * L);             // frame scores
+    a.get<int64_t>(2); a.get<int32_t>(2); a.get<int64_t>(n_queries); a.get<int32_t>(n_queries);
+    a.get<int32_t>((int64_t)n_queries * nw);          // rank-lists
+    a.get<float>((int64_t)n_queries * nw);            // window scores
+    // the frame stage works in slabs sized to what is left: ask for enough to take a 4096-frame slab in one piece
+    return a.used + cone_prepare_workspace_bytes(dims, L < 4096 ? L : 4096);
+}
+
+extern "C" int cone_prefilter(const cone_weights* w, const float* frames_raw, int64_t L, const float* cls_raw,
+                              int32_t n_queries, int32_t topk, int32_t* win_idx, float* win_score, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    CONE_REQUIRE(w && frames_raw && win_idx && (cls_raw || n_queries == 0), "null argument");
+    CONE_REQUIRE(L > 0 && n_queries >= 0 && topk > 0, "cone_prefilter: L=%lld n_queries=%d topk=%d", (long long)L, n_queries, topk);
+    if (n_queries == 0) return CONE_OK;
+    const cone_dims& dm = w->dims;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nw = prefilter_windows(dm, L);
+    Arena a(workspace, workspace_bytes);
+    float* ctx = a.get<float>(L * dm.v_dim);
+    float* cls_n = a.get<float>((int64_t)n_queries * dm.v_dim);
+    float* scores = a.get<float>((int64_t)n_queries * L);
+    int64_t* video_offsets = a.get<int64_t>(2);
+    int32_t* q_first = a.get<int32_t>(2);
+    int64_t* score_offsets = a.get<int64_t>(n_queries);
+    int32_t* frame_count = a.get<int32_t>(n_queries);
+    int32_t* ranklist = a.get<int32_t>((int64_t)n_queries * nw);
+    float* winscore = a.get<float>((int64_t)n_queries * nw);
+    if (!workspace || a.used >= workspace_bytes || cone_prepare_workspace_bytes(&dm, 1) > workspace_bytes - a.used) {
+        set_error("cone_prefilter: workspace of %zu bytes, cone_prefilter_workspace_bytes() asks for %zu", workspace_bytes,
+                  cone_prefilter_workspace_bytes(&dm, L, n_queries));
+        return CONE_ERR_WORKSPACE;
+    }
+    // A1 + A2: normalised, adapted context features of every frame (always fp32: the ranking must be bit-stable)
+    CONE_TRY(cone_video_prepare(w, frames_raw, L, ctx, nullptr, a.base + a.used, workspace_bytes - a.used, CONE_PREC_FP32, stream));
+    CONE_TRY(l2norm_rows(cls_raw, cls_n, n_queries, dm.v_dim, 1e-5f, s));  // dataloader:472
+    // A3: frame scores, window maxima, full rank-list; the first topk entries leave
+    CONE_TRY(prefilter_desc(video_offsets, q_first, score_offsets, frame_count, L, n_queries, s));
+    CONE_REQUIRE(L <= INT32_MAX, "cone_prefilter: video too long");
+    CONE_TRY(sgemm_frame_scores(ctx, cls_n, dm.v_dim, video_offsets, q_first, 1, (int)L, n_queries, scores, score_offsets, s));
+    CONE_TRY(window_ranklist(scores, score_offsets, frame_count, n_queries, dm.max_v_l, ranklist, winscore, nw, s));
+    return take_topk(ranklist, winscore, nw, n_queries, topk, win_idx, win_score, s);
+}
+
 namespace {
 size_t ground_chunk_bytes(const cone_dims& dm, int64_t nqc, int topk, int Lv, int Lt, int prec) {
     Arena a(nullptr, 0);

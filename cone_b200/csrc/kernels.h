@@ -107,6 +107,10 @@ int dec_cross_attention_mem(const void* mem, int64_t ldm, const void* qqt, int64
 int window_ranklist(const float* frame_score, const int64_t* score_offsets, const int32_t* frame_count, int n_queries,
                     int max_v_l, int32_t* ranklist, float* winscore, int ranklist_stride, cudaStream_t s);
 // window descriptors of the first `topk` ranked windows of each query
+int prefilter_desc(int64_t* video_offsets, int32_t* q_first, int64_t* score_offsets, int32_t* frame_count, int64_t L,
+                   int n_queries, cudaStream_t s);
+int take_topk(const int32_t* ranklist, const float* winscore, int ranklist_stride, int n_queries, int topk, int32_t* win_idx,
+              float* win_score, cudaStream_t s);
 int build_windows(const int32_t* ranklist, int ranklist_stride, const int32_t* q_video_len, int n_queries, int topk,
                   int max_v_l, int32_t* win_start, int32_t* win_len, cudaStream_t s);
 int batch_max_len(const int32_t* win_len, const int32_t* q_batch, int n_queries, int topk, int32_t* batch_max,

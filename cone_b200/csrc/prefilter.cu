@@ -136,6 +136,49 @@ int window_ranklist(const float* frame_score, const int64_t* score_offsets, cons
     return CONE_OK;
 }
 
+namespace {
+// descriptors of the single-video form: every query sees the same L frames
+__global__ void prefilter_desc_kernel(int64_t* video_offsets, int32_t* q_first, int64_t* score_offsets, int32_t* frame_count,
+                                      int64_t L, int n_queries) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) {
+        video_offsets[0] = 0; video_offsets[1] = L;
+        q_first[0] = 0; q_first[1] = n_queries;
+    }
+    if (q < n_queries) {
+        score_offsets[q] = (int64_t)q * L;
+        frame_count[q] = (int32_t)L;
+    }
+}
+// first `topk` entries of each rank-list and the scores of those windows; -1 / NaN past the video's window count
+__global__ void take_topk_kernel(const int32_t* __restrict__ ranklist, const float* __restrict__ winscore, int ranklist_stride,
+                                 int n_queries, int topk, int32_t* __restrict__ win_idx, float* __restrict__ win_score) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_queries * topk) return;
+    const int q = i / topk, j = i - q * topk;
+    const int32_t w = j < ranklist_stride ? ranklist[(int64_t)q * ranklist_stride + j] : -1;
+    win_idx[i] = w;
+    if (win_score) win_score[i] = w >= 0 ? winscore[(int64_t)q * ranklist_stride + w] : __int_as_float(0x7fc00000);
+}
+}  // namespace
+
+int prefilter_desc(int64_t* video_offsets, int32_t* q_first, int64_t* score_offsets, int32_t* frame_count, int64_t L,
+                   int n_queries, cudaStream_t s) {
+    prefilter_desc_kernel<<<cdiv(n_queries > 0 ? n_queries : 1, 256), 256, 0, s>>>(video_offsets, q_first, score_offsets, frame_count, L,
+                                                                                  n_queries);
+    CONE_LAUNCH_CHECK("prefilter_desc");
+    return CONE_OK;
+}
+
+int take_topk(const int32_t* ranklist, const float* winscore, int ranklist_stride, int n_queries, int topk, int32_t* win_idx,
+              float* win_score, cudaStream_t s) {
+    if (n_queries == 0 || topk == 0) return CONE_OK;
+    take_topk_kernel<<<cdiv(n_queries * topk, 256), 256, 0, s>>>(ranklist, winscore, ranklist_stride, n_queries, topk, win_idx,
+                                                                win_score);
+    CONE_LAUNCH_CHECK("take_topk");
+    return CONE_OK;
+}
+
 int build_windows(const int32_t* ranklist, int ranklist_stride, const int32_t* q_video_len, int n_queries, int topk,
                   int max_v_l, int32_t* win_start, int32_t* win_len, cudaStream_t s) {
     if (n_queries == 0) return CONE_OK;

@@ -278,6 +278,23 @@ class ConeEngine:
                                                  _ptr(rl), _ptr(ws), ranklist_stride, _stream()), "cone_window_ranklist")
         return (rl, ws) if want_scores else rl
 
+    def prefilter(self, frames_raw: torch.Tensor, cls_raw: torch.Tensor, topk: Optional[int] = None, want_scores: bool = False):
+        """Stages 0 + 1 for ONE video in one call (`cone_prefilter`): raw frames [L, Dv] and raw CLS [Nq, Dv] -> the first
+        `topk` window ids of every query's rank-list (-1 where the video has fewer windows) and their window scores.
+        The same pre-filter `compute_window_ranklist` runs (run_on_video/cone_localizator.py:83-100) and the 2D-TAN
+        variant reuses (cone_2dtan/moment_localization/test.py:173-239)."""
+        frames_raw = _need(frames_raw, torch.float32, "frames_raw")
+        cls_raw = _need(cls_raw, torch.float32, "cls_raw")
+        L, nq = frames_raw.shape[0], cls_raw.shape[0]
+        topk = topk or self.cfg.topk_window
+        idx = torch.empty((nq, topk), dtype=torch.int32, device=frames_raw.device)
+        sc = torch.empty((nq, topk), dtype=torch.float32, device=frames_raw.device) if want_scores else None
+        need = self.lib.cone_prefilter_workspace_bytes(C.byref(self.dims), L, nq)
+        ws, nb = self._wsargs(need)
+        _lib.check(self.lib.cone_prefilter(self._handle, _ptr(frames_raw), L, _ptr(cls_raw), nq, topk, _ptr(idx), _ptr(sc), ws, nb,
+                                           _stream()), "cone_prefilter")
+        return (idx, sc) if want_scores else idx
+
     def forward(self, src_txt, txt_len, src_vid, vid_len, want_saliency=False, want_aux=False):
         """`CONE.forward` on a dense padded batch (cone/model.py:82-128); lengths instead of masks."""
         src_txt = _need(src_txt, torch.float32, "src_txt")

@@ -139,6 +139,18 @@ int cone_window_ranklist(const float* frame_score, const int64_t* score_offsets,
                          int32_t n_queries, int32_t max_v_l, int32_t* ranklist_out, float* winscore_out,
                          int32_t ranklist_stride, void* stream);
 
+/* ---- A1-A3 for ONE video in one call: the `cone_prefilter` of SURVEY.md §8(b) — host L2 normalisation of the raw frames and
+ * CLS vectors (cone/ego4d_mad_dataloader.py:459, 472), stage 0 (cone/inference.py:250-260) and stage 1
+ * (cone/inference.py:276-299; the same pre-filter runs in cone_2dtan/moment_localization/test.py:173-239).
+ *   frames_raw [L, Dv] raw features of the video, cls_raw [n_queries, Dv] raw CLS features (device)
+ *   win_idx   [n_queries, topk] int32: the first topk window ids of each query's rank-list, -1 where the video has fewer
+ *   win_score [n_queries, topk] fp32 (nullable): the window scores (max frame score) of those windows
+ * Always fp32 (the ranking must be bit-stable).  The window length is the handle's max_v_l.
+ * Composition of cone_l2_normalize, cone_video_prepare, cone_frame_scores, cone_window_ranklist: bit-identical to them. */
+size_t cone_prefilter_workspace_bytes(const cone_dims* dims, int64_t n_frames, int32_t n_queries);
+int cone_prefilter(const cone_weights* w, const float* frames_raw, int64_t n_frames, const float* cls_raw, int32_t n_queries,
+                   int32_t topk, int32_t* win_idx, float* win_score, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- A4-A9  stage 2: slice the top-k windows of every query straight out of the frame tensors,
  * run Moment-DETR on them and score the proposals (cone/ego4d_mad_dataloader.py:144-159, 305-358;
  * cone/model.py:82-152; cone/inference.py:46-52).

@@ -220,6 +220,43 @@ def test_video_context_and_frame_scores_vs_oracle():
         assert_close(scores[offs[j]: offs[j] + len(want)], want, FP32_TOL, "frame scores")
 
 
+def test_prefilter_single_call_vs_oracle_and_staged_calls():
+    """`cone_prefilter`: stages 0 + 1 of one video in one call = the oracle's rank-list prefix and window
+    scores, and bit-identical to the staged entry points it is composed of; a video with fewer windows than topk pads with -1."""
+    cfg = MAD512
+    sd = init_state_dict(cfg, 5)
+    eng = engine_for(cfg, 5)
+    for n_frames, nq, seed in ((1500, 5, 3), (130, 3, 4), (7, 2, 5)):
+        ds = make_dataset(cfg, 1, [n_frames], [nq], seed=seed)
+        ora = O.eval_pipeline(sd, cfg, ds.videos, ds.queries)
+        frames = torch.from_numpy(ds.videos[0]).to(DEV)
+        cls = torch.from_numpy(np.stack([q.cls for q in ds.queries])).to(DEV)
+        idx, sc = eng.prefilter(frames, cls, want_scores=True)
+        idx, sc = idx.cpu().numpy(), sc.cpu().numpy()
+        nw = cfg.num_window(n_frames)
+        k = min(nw, cfg.topk_window)
+        hatch = Hatch(f"prefilter[{n_frames}]", "top-k window list differs from the oracle (near-tie audited)", 0)
+        for j, q in enumerate(ds.queries):
+            want = ora[q.query_id]["ranklist"][:k]
+            wscore = oracle_window_scores(sd, cfg, ds, q)
+            assert (idx[j, k:] == -1).all() and np.isnan(sc[j, k:]).all()
+            if list(idx[j, :k]) != want:
+                assert ranklist_near_tie(wscore, list(idx[j, :k]), want, k), q.query_id
+                hatch.use(q.query_id)
+                continue
+            assert_close(sc[j, :k], np.asarray(wscore)[want], FP32_TOL, "window scores")
+        hatch.close(len(ds.queries))
+        # the staged entry points on the same video: identical bits
+        ctx, _ = eng.video_prepare(frames)
+        qb = pack_queries(cfg, [n_frames], ds.queries).to(DEV)
+        scores, offs = eng.frame_scores(ctx, qb, eng.l2_normalize(qb.cls, 1e-5))
+        rl, ws = eng.window_ranklist(scores, offs, qb.q_video_len, want_scores=True)
+        rl, ws = rl.cpu().numpy(), ws.cpu().numpy()
+        for j, i in enumerate(qb.order):
+            assert list(rl[j, :k]) == list(idx[i, :k])
+            assert np.array_equal(ws[j][rl[j, :k]], sc[i, :k])
+
+
 # --------------------------------------------------------------------------------------- end to end
 def _tie_audit(win_scores, k, rel=1e-5):
     """near-ties between DIFFERENT frames at the top-k boundary may legitimately flip between
