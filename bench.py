@@ -176,9 +176,11 @@ def reference_sample(cfg, sd, ds, n_queries, threads, model=None):
     torch.set_num_threads(threads)
     qs = [q for q in ds.queries if q.video_idx == 0][:n_queries]
     sub = dataclasses.replace(ds, videos=ds.videos[:1], queries=qs)
-    if model is None:
-        model = RH.build_reference_model(cfg, sd)
-    res = RH.run_eval_epoch_files(cfg, sub, model, device="cpu")
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the reference prints its metric tables: stdout carries only the JSON line
+        if model is None:
+            model = RH.build_reference_model(cfg, sd)
+        res = RH.run_eval_epoch_files(cfg, sub, model, device="cpu")
     return len(qs) / res["seconds"], res["seconds"], len(qs), model
 
 
