@@ -529,10 +529,24 @@ struct CoreBuffers {
     const uint16_t* frame_qkv = nullptr;
     const uint16_t* token_qkv = nullptr;
     int64_t n_frames = 0, n_tokens = 0;
+    // ... and the hi / lo fp16 tables [n_frames + n_tokens, d] of the projected frame and token rows: when set, the fused tail
+    // of layer 0 fetches its residual rows from them by TMA gather4 and no per-window copy of the inputs is made
+    const uint16_t* g_src_hi = nullptr;
+    const uint16_t* g_src_lo = nullptr;
 };
 
 // The fused encoder tail (enc_tail.cu) replaces out_proj + norm1 + linear1 + linear2 + norm2 of the tensor-core mode;
 // CONE_FUSED_TAIL=0 in the environment selects the unfused three-GEMM chain (A/B measurements, fall-back).
+// CONE_TAIL_GATHER=0: materialise the window rows with the gather kernel instead (A/B measurements, fall-back)
+bool tail_gather_enabled() {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("CONE_TAIL_GATHER");
+        env = (e && e[0] == '0') ? 0 : 1;
+    }
+    return env == 1;
+}
+
 bool fused_tail_enabled(const cone_dims& c) {
     static int env = -1;
     if (env < 0) {
@@ -682,6 +696,12 @@ int transformer_core(const Ctx& c, CoreBuffers& b, float* logits, float* prob_fg
                 EncTailArgs e;
                 e.att16 = b.att16; e.lda = d;
                 e.res_hi = b.src16; e.res_lo = b.src16lo; e.ldr = d;
+                if (l == 0 && b.g_src_hi != nullptr) {  // window slicing fused into the tail: residual rows by TMA gather4
+                    e.res_hi = b.g_src_hi; e.res_lo = b.g_src_lo;
+                    e.g_vid_base = b.vid_base; e.g_txt_base = b.txt_base;
+                    e.g_S = b.Lv + b.Lt; e.g_Lv = b.Lv;
+                    e.g_nvid = b.n_frames; e.g_nsrc = b.n_frames + b.n_tokens;
+                }
                 e.out_hi = b.src16; e.out_lo = last_enc ? nullptr : b.src16lo; e.ldo = d;  // the memory is read as fp16
                 if (saliency && last_enc) { e.C32 = b.src; e.ldc32 = d; }
                 e.M = R; e.d = d; e.ffn = ff;
@@ -1159,16 +1179,23 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
     // same row once for every window that contains the frame: k * Nq * Lv rows against n_frames)
     uint16_t* frame_qkv = nullptr;
     uint16_t* vidproj16 = nullptr;
+    uint16_t* vidproj16lo = nullptr;
     const int d = dm.hidden;
     const std::string l0 = "transformer.encoder.layers.0.self_attn";
+    // window slicing fused into the encoder tail (TMA gather4 from the per-frame / per-token tables) instead of a gathered copy
+    const bool tail_gather = precision == CONE_PREC_TC && fused_tail_enabled(dm) && tail_gather_enabled() &&
+                             n_frames + (int64_t)n_queries * Lt < ((int64_t)1 << 31);
     if (precision == CONE_PREC_TC) {
-        vidproj16 = head.get<uint16_t>(n_frames * d);
+        // [frames | tokens of the current chunk]: the fp16 (= hi) rows, and with tail_gather their lo parts
+        vidproj16 = head.get<uint16_t>((n_frames + (tail_gather ? (int64_t)n_queries * Lt : 0)) * d);
+        if (tail_gather) vidproj16lo = head.get<uint16_t>((n_frames + (int64_t)n_queries * Lt) * d);
         frame_qkv = head.get<uint16_t>(n_frames * 3 * d);
         if (!head.fits()) {
             set_error("cone_ground_windows: workspace too small for the per-frame projections");
             return CONE_ERR_WORKSPACE;
         }
-        CONE_TRY(f32_to_f16_rows(vidproj, d, vidproj16, n_frames, d, c.s));
+        if (tail_gather) CONE_TRY(split_hilo_rows(vidproj, vidproj16, vidproj16lo, n_frames * d, c.s));
+        else CONE_TRY(f32_to_f16_rows(vidproj, d, vidproj16, n_frames, d, c.s));
         TcGemmArgs g;
         g.A16 = vidproj16; g.lda = d; g.M = n_frames; g.W = w->p(l0 + ".in_proj_weight"); g.bias = w->p(l0 + ".in_proj_bias");
         g.N = 3 * d; g.K = d; g.C16 = frame_qkv; g.ldc16 = 3 * d;
@@ -1196,10 +1223,11 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
         CONE_TRY(input_proj(c, "input_txt_proj", tok + q0 * Lt * dm.t_dim, n * Lt, dm.t_dim, txtproj, pb));
         uint16_t* txtproj16 = nullptr;
         if (precision == CONE_PREC_TC) {  // token q|k|v of encoder layer 0, once per query token
-            txtproj16 = a.get<uint16_t>(n * Lt * d);
+            txtproj16 = tail_gather ? vidproj16 + n_frames * d : a.get<uint16_t>(n * Lt * d);
             uint16_t* token_qkv = a.get<uint16_t>(n * Lt * 3 * d);
             tc_set_scratch(w->tc, a.base + a.used, avail > a.used ? avail - a.used : 0);
-            CONE_TRY(f32_to_f16_rows(txtproj, d, txtproj16, n * Lt, d, c.s));
+            if (tail_gather) CONE_TRY(split_hilo_rows(txtproj, txtproj16, vidproj16lo + n_frames * d, n * Lt * d, c.s));
+            else CONE_TRY(f32_to_f16_rows(txtproj, d, txtproj16, n * Lt, d, c.s));
             TcGemmArgs g;
             g.A16 = txtproj16; g.lda = d; g.M = n * Lt; g.W = w->p(l0 + ".in_proj_weight"); g.bias = w->p(l0 + ".in_proj_bias");
             g.N = 3 * d; g.K = d; g.C16 = token_qkv; g.ldc16 = 3 * d;
@@ -1208,10 +1236,16 @@ extern "C" int cone_ground_windows(const cone_weights* w, const float* frames_ra
             cb.token_qkv = token_qkv;
             cb.n_frames = n_frames;
             cb.n_tokens = n * Lt;
+            if (tail_gather) {
+                cb.g_src_hi = vidproj16;
+                cb.g_src_lo = vidproj16lo;
+            }
         }
         CONE_TRY(fill_window_desc_chunk(q_video_start, win_start, win_len, tok_len, q_batch, batch_max, (int)q0, (int)n,
                                         topk, Lt, Lv, cb.vid_base, cb.vlen, cb.txt_base, cb.tlen, cb.pad_len, cb.qidx, c.s));
-        if (precision == CONE_PREC_TC && fused_tail_enabled(dm)) {  // hi + lo of the projected rows (fp32-accurate residual)
+        if (tail_gather) {
+            // nothing to copy: layer 0 reads q|k|v and its residual rows through the window descriptors
+        } else if (precision == CONE_PREC_TC && fused_tail_enabled(dm)) {  // hi + lo of the projected rows (fp32-accurate residual)
             CONE_TRY(gather_window_rows_f16(vidproj, n_frames, cb.vid_base, txtproj, cb.txt_base, cb.src16, B, Lv, Lt, dm.hidden,
                                             c.s, cb.src16lo));
         } else if (precision == CONE_PREC_TC) {

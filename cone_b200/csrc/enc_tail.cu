@@ -71,6 +71,14 @@ struct EtParams {
     int64_t M;
     int nchunk;      // ffn / 128
     int has_lo_in, has_lo_out;
+    // gather mode (encoder layer 0): the residual rows are the window slices of the per-frame / per-token projections
+    // (cone/ego4d_mad_dataloader.py:144-159 + start_end_collate): tile row m = window b = m / S, row r = m % S comes from source
+    // row min(vid_base[b] + r, n_vid - 1) for r < Lv, n_vid + txt_base[b] + (r - Lv) otherwise; tmRhi / tmRlo are maps of the
+    // source table [n_vid + n_txt, 256] with one-row boxes and the rows arrive by TMA gather4 — no gathered copy in HBM
+    int gather, g_S, g_Lv;
+    int64_t g_nvid;
+    const int64_t* g_vid_base;
+    const int64_t* g_txt_base;
 };
 
 __device__ __forceinline__ uint32_t et_idesc(int M, int N) {  // D fp32, A / B fp16 K-major
@@ -167,7 +175,97 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
     constexpr uint32_t tmem_base = 0u;
     constexpr uint32_t tmemY = tmem_base, tmemH = tmem_base + 256;
 
-    if (warp == 0 || warp == ET_PROD_B_WARP) {
+    if (warp == 0 && P.gather) {  // ---------------------------------------- producer A with gathered residual rows (whole warp)
+        int slot = 0;
+        uint32_t ph = 0;
+        auto advance = [&]() {
+            if (++slot == NSLOT_A) {
+                slot = 0;
+                ph ^= 1;
+            }
+        };
+        auto emit = [&](const CUtensorMap* map, int c0, int c1) {  // one [128 x 64] box, issued by lane 0
+            mbar_wait(&empty[slot], ph ^ 1);
+            if (lane == 0) {
+                if (CG == 1) {
+                    mbar_expect_tx(&full[slot], SLOT_BYTES);
+                    tma_load_2d(sRing + slot * SLOT_BYTES, map, &full[slot], c0, c1);
+                } else {
+                    mbar_expect_tx_leader(&full[slot], SLOT_BYTES);
+                    tma_load_2d_pair(sRing + slot * SLOT_BYTES, map, &full[slot], c0, c1);
+                }
+            }
+            __syncwarp();
+            advance();
+        };
+        auto emit_rows = [&](const CUtensorMap* map, int kb, const int* idx) {  // lane l: tile rows 4 l .. 4 l + 3 of the box
+            mbar_wait(&empty[slot], ph ^ 1);
+            if (lane == 0) {
+                if (CG == 1) mbar_expect_tx(&full[slot], SLOT_BYTES);
+                else mbar_expect_tx_leader(&full[slot], SLOT_BYTES);
+            }
+            __syncwarp();
+            tma_gather4<CG>(sRing + slot * SLOT_BYTES + lane * 512, map, &full[slot], kb * 64, idx[0], idx[1], idx[2], idx[3]);
+            __syncwarp();
+            advance();
+        };
+        auto emit_gemm0 = [&](int m0) {
+            for (int kb = 0; kb < 4; ++kb) {
+                emit(&tmAtt, kb * 64, m0);
+                if (CG == 1) {
+                    emit(&tmWo, kb * 64, 0);
+                    emit(&tmWo, kb * 64, 128);
+                } else {
+                    emit(&tmWo, kb * 64, 128 * (int)rank);
+                }
+            }
+            int idx[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int64_t m = (int64_t)m0 + 4 * lane + j;
+                if (m >= P.M) m = P.M - 1;  // rows past the end are clipped by the output stores
+                const int64_t b = m / P.g_S;
+                const int r = (int)(m - b * P.g_S);
+                int64_t src;
+                if (r < P.g_Lv) {
+                    src = P.g_vid_base[b] + r;
+                    src = src < P.g_nvid ? src : P.g_nvid - 1;
+                } else {
+                    src = P.g_nvid + P.g_txt_base[b] + (r - P.g_Lv);
+                }
+                idx[j] = (int)src;
+            }
+            for (int kb = 0; kb < 4; ++kb) emit_rows(&tmRhi, kb, idx);
+            if (P.has_lo_in)
+                for (int kb = 0; kb < 4; ++kb) emit_rows(&tmRlo, kb, idx);
+        };
+        auto emit_g1 = [&](int c) {
+            if (CG == 1) {
+                for (int kb = 0; kb < 4; ++kb) emit(&tmW1, kb * 64, c * 128);
+            } else {
+                for (int kp = 0; kp < 2; ++kp) {
+                    mbar_wait(&empty[slot], ph ^ 1);
+                    if (lane == 0) {
+                        mbar_expect_tx_leader(&full[slot], SLOT_BYTES);
+                        tma_load_2d_pair(sRing + slot * SLOT_BYTES, &tmW1, &full[slot], (2 * kp) * 64, c * 128 + 64 * (int)rank);
+                        tma_load_2d_pair(sRing + slot * SLOT_BYTES + SLOT_BYTES / 2, &tmW1, &full[slot], (2 * kp + 1) * 64,
+                                         c * 128 + 64 * (int)rank);
+                    }
+                    __syncwarp();
+                    advance();
+                }
+            }
+        };
+        if (st_begin < n_super) emit_gemm0((int)((st_begin * CG + rank) * 128));
+        for (int64_t st = st_begin; st < n_super; st += st_step) {
+            const bool has_next = st + st_step < n_super;
+            const int m_next = (int)(((st + st_step) * CG + rank) * 128);
+            if (has_next && lane == 0)
+                for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmAtt, kb * 64, m_next);
+            for (int c = 0; c < nchunk; ++c) emit_g1(c);
+            if (has_next) emit_gemm0(m_next);
+        }
+    } else if (warp == 0 || warp == ET_PROD_B_WARP) {
         if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producers
             // Two sub-rings with their own cursors: slots [0, NSLOT_A) carry the items of MMA warp A (GEMM0, GEMM1), slots
             // [NSLOT_A, NSLOT) those of warp B (GEMM2).  (With ONE ring shared by two consumers a consumer that skips the
@@ -617,6 +715,10 @@ int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
     CONE_REQUIRE(enc_tail_supported(a.d, a.ffn), "enc_tail: unsupported width d=%d ffn=%d", a.d, a.ffn);
     CONE_REQUIRE(a.M >= 1 && a.M < ((int64_t)1 << 31) - 512, "enc_tail: bad row count %lld", (long long)a.M);
     CONE_REQUIRE(a.att16 && a.res_hi && a.out_hi, "enc_tail: null argument");
+    const bool gather = a.g_vid_base != nullptr;
+    CONE_REQUIRE(!gather || (a.g_txt_base && a.g_S > 0 && a.g_Lv > 0 && a.g_Lv <= a.g_S && a.g_nvid > 0 && a.g_nsrc > a.g_nvid &&
+                             a.g_nsrc < ((int64_t)1 << 31) && a.ldr == a.d),
+                 "enc_tail: incomplete gather description");
     CONE_REQUIRE((a.lda % 8) == 0 && (a.ldr % 8) == 0 && (a.ldo % 8) == 0, "enc_tail: row pitches must be multiples of 8");
     int cg = a.cta_group;
     if (cg == 0) {
@@ -634,9 +736,10 @@ int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
     CONE_TRY(tc_weight_f16(t, a.W2, a.d, a.ffn, s, &w2));
     CUtensorMap mAtt, mRhi, mRlo, mWo, mW1, mW2, mOhi, mOlo;
     CONE_TRY(tc_make_map(&mAtt, a.att16, false, a.M, a.d, a.lda, 64, 128));
-    CONE_TRY(tc_make_map(&mRhi, a.res_hi, false, a.M, a.d, a.ldr, 64, 128));
+    // residual rows: dense [M, d] tiles, or (gather mode) one-row boxes of the source table [g_nsrc, d] for TMA gather4
+    CONE_TRY(tc_make_map(&mRhi, a.res_hi, false, gather ? a.g_nsrc : a.M, a.d, a.ldr, 64, gather ? 1 : 128));
     mRlo = mRhi;
-    if (a.res_lo) CONE_TRY(tc_make_map(&mRlo, a.res_lo, false, a.M, a.d, a.ldr, 64, 128));
+    if (a.res_lo) CONE_TRY(tc_make_map(&mRlo, a.res_lo, false, gather ? a.g_nsrc : a.M, a.d, a.ldr, 64, gather ? 1 : 128));
     CONE_TRY(tc_make_map(&mWo, wo, false, a.d, a.d, a.d, 64, 128));
     CONE_TRY(tc_make_map(&mW1, w1, false, a.ffn, a.d, a.d, 64, 128 / cg));
     CONE_TRY(tc_make_map(&mW2, w2, false, a.d, a.ffn, a.ffn, 64, 128));
@@ -651,6 +754,8 @@ int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
     P.nchunk = a.ffn / 128;
     P.has_lo_in = a.res_lo != nullptr;
     P.has_lo_out = a.out_lo != nullptr;
+    P.gather = gather ? 1 : 0;
+    P.g_S = a.g_S; P.g_Lv = a.g_Lv; P.g_nvid = a.g_nvid; P.g_vid_base = a.g_vid_base; P.g_txt_base = a.g_txt_base;
     const int num_sms = tc_num_sms(t);
     const int64_t n_super = cdiv64(a.M, 128 * cg);
     int64_t clusters = num_sms / cg;

@@ -75,6 +75,13 @@ struct EncTailArgs {
     const float *Wo = nullptr, *bo = nullptr, *ln1_g = nullptr, *ln1_b = nullptr;
     const float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
     int cta_group = 0;                 // 1 or 2; 0 = default (2, or env CONE_ENC_TAIL_CG)
+    // gather mode (g_vid_base != nullptr): res_hi / res_lo are the SOURCE tables [g_nsrc, d] = per-frame rows [g_nvid] followed by
+    // the per-token rows, and residual row m = window b = m / g_S, row r = m % g_S is fetched from source row
+    // min(g_vid_base[b] + r, g_nvid - 1) (r < g_Lv) or g_nvid + g_txt_base[b] + r - g_Lv by TMA gather4 (ldr == d)
+    const int64_t* g_vid_base = nullptr;
+    const int64_t* g_txt_base = nullptr;
+    int g_S = 0, g_Lv = 0;
+    int64_t g_nvid = 0, g_nsrc = 0;
 };
 int enc_tail_supported(int d, int ffn);
 int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s);
