@@ -209,17 +209,7 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             __syncwarp();
             advance();
         };
-        auto emit_gemm0 = [&](int m0) {
-            for (int kb = 0; kb < 4; ++kb) {
-                emit(&tmAtt, kb * 64, m0);
-                if (CG == 1) {
-                    emit(&tmWo, kb * 64, 0);
-                    emit(&tmWo, kb * 64, 128);
-                } else {
-                    emit(&tmWo, kb * 64, 128 * (int)rank);
-                }
-            }
-            int idx[4];
+        auto source_rows = [&](int m0, int* idx) {  // lane l: source rows of tile rows 4 l .. 4 l + 3
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 int64_t m = (int64_t)m0 + 4 * lane + j;
@@ -234,6 +224,17 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     src = P.g_nvid + P.g_txt_base[b] + (r - P.g_Lv);
                 }
                 idx[j] = (int)src;
+            }
+        };
+        auto emit_gemm0 = [&](int m0, const int* idx) {
+            for (int kb = 0; kb < 4; ++kb) {
+                emit(&tmAtt, kb * 64, m0);
+                if (CG == 1) {
+                    emit(&tmWo, kb * 64, 0);
+                    emit(&tmWo, kb * 64, 128);
+                } else {
+                    emit(&tmWo, kb * 64, 128 * (int)rank);
+                }
             }
             for (int kb = 0; kb < 4; ++kb) emit_rows(&tmRhi, kb, idx);
             if (P.has_lo_in)
@@ -256,14 +257,28 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 }
             }
         };
-        if (st_begin < n_super) emit_gemm0((int)((st_begin * CG + rank) * 128));
+        int idx[4];
+        if (st_begin < n_super) {
+            const int m_first = (int)((st_begin * CG + rank) * 128);
+            source_rows(m_first, idx);
+            emit_gemm0(m_first, idx);
+        }
         for (int64_t st = st_begin; st < n_super; st += st_step) {
             const bool has_next = st + st_step < n_super;
             const int m_next = (int)(((st + st_step) * CG + rank) * 128);
-            if (has_next && lane == 0)
-                for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmAtt, kb * 64, m_next);
+            if (has_next) {  // next tile's rows -> L2 a whole tile ahead of their loads (the tables compete with 7 GB of streams)
+                source_rows(m_next, idx);
+                if (P.gather > 1) {
+                    for (int kb = 0; kb < 4; ++kb) {
+                        tma_prefetch_l2_gather4(&tmRhi, kb * 64, idx[0], idx[1], idx[2], idx[3]);
+                        if (P.has_lo_in) tma_prefetch_l2_gather4(&tmRlo, kb * 64, idx[0], idx[1], idx[2], idx[3]);
+                    }
+                }
+                if (lane == 0)
+                    for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmAtt, kb * 64, m_next);
+            }
             for (int c = 0; c < nchunk; ++c) emit_g1(c);
-            if (has_next) emit_gemm0(m_next);
+            if (has_next) emit_gemm0(m_next, idx);
         }
     } else if (warp == 0 || warp == ET_PROD_B_WARP) {
         if (lane == 0) {  // ------------------------------------------------------------------------------ TMA producers
@@ -754,7 +769,14 @@ int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
     P.nchunk = a.ffn / 128;
     P.has_lo_in = a.res_lo != nullptr;
     P.has_lo_out = a.out_lo != nullptr;
-    P.gather = gather ? 1 : 0;
+    {
+        static int pf = -1;  // CONE_TAIL_GATHER_PF=1: L2 prefetch of the gathered rows one tile ahead
+        if (pf < 0) {
+            const char* e = getenv("CONE_TAIL_GATHER_PF");
+            pf = (e && e[0] == '1') ? 1 : 0;
+        }
+        P.gather = gather ? 1 + pf : 0;
+    }
     P.g_S = a.g_S; P.g_Lv = a.g_Lv; P.g_nvid = a.g_nvid; P.g_vid_base = a.g_vid_base; P.g_txt_base = a.g_txt_base;
     const int num_sms = tc_num_sms(t);
     const int64_t n_super = cdiv64(a.M, 128 * cg);
