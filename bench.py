@@ -685,6 +685,20 @@ def roofline_entry(prof, peaks, flops_per_query, alg_bytes_step, args, cfg, ms_s
             "frac_of_hbm_peak": alg_bytes_step / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
             "traffic_bytes_per_step": tr.get("step_dram_bytes"),
             "traffic_ratio": (tr["step_dram_bytes"] / alg_bytes_step) if tr.get("step_dram_bytes") else None}
+    detail = None
+    if prof and prof.get("enc_tail_gather", {}).get("launches"):
+        # the fused encoder tail runs twice per step: on layer 0 it also does the window slicing (its residual rows arrive by
+        # TMA gather4 from the per-frame / per-token tables), on layer 1 its residual rows are dense.  One kernel: the roofline
+        # entry is the sum of both; the two forms are listed under `detail`
+        a, b = prof.get("enc_tail", {"ms": 0, "launches": 0, "flops": 0, "bytes": 0}), prof["enc_tail_gather"]
+        detail = {}
+        for name, v in (("layer 1: dense residual rows", a), ("layer 0: + window slicing by TMA gather4", b)):
+            if v["launches"]:
+                tfl = v["flops"] / (v["ms"] * 1e-3) / 1e12
+                detail[name] = {"avg_launch_ms": v["ms"] / v["launches"], "TFLOPs": tfl, "frac": tfl / peaks["tflops"]}
+        prof = dict(prof)
+        prof["enc_tail"] = {k: a[k] + b[k] for k in ("ms", "launches", "flops", "bytes")}
+        del prof["enc_tail_gather"]
     cands = [k for k in ("enc_tail", "gemm_tc", "gemm_fp32", "enc_attention") if prof and k in prof and prof[k]["launches"]]
     if not cands:
         return {"bound": "tensor", "achieved": None, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": None,
@@ -700,6 +714,8 @@ def roofline_entry(prof, peaks, flops_per_query, alg_bytes_step, args, cfg, ms_s
            "declared_hbm_gbs": p["bytes"] / sec / 1e9,
            "traffic": (tr.get("kernels", {}).get(key, {}) or {}).get("dram_bytes_per_launch"),
            "step": step}
+    if detail and key == "enc_tail":
+        ent["detail"] = detail
     if key == "gemm_fp32":
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         ent.update(bound="fp32", peak=fp32_peak, frac=tf / fp32_peak,

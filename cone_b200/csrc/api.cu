@@ -62,7 +62,7 @@ ProfScope::~ProfScope() {
 
 static const char* kProfNames[cone::P_COUNT] = {"gemm_fp32", "gemm_tc", "enc_attention", "dec_attention", "layernorm",
                                                 "rowops", "frame_scores", "window_ranklist", "span_pool", "fuse_nms",
-                                                "convert", "enc_tail"};
+                                                "convert", "enc_tail", "enc_tail_gather"};
 extern "C" void cone_profile_enable(int on) {
     cone::g_prof_on = on != 0;
     // events are created here, not at the first profiled launches: event creation inside a timed region showed up as

@@ -62,7 +62,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // Optional per-kernel timing (cone_profile_enable): CUDA events around each launch on the launching stream,
 // aggregated per category.  Off by default: a scope is then a no-op.
 enum ProfCat { P_GEMM_FP32 = 0, P_GEMM_TC, P_ENC_ATTN, P_DEC_ATTN, P_LAYERNORM, P_ROWOPS, P_SCORES, P_RANKLIST, P_POOL,
-               P_NMS, P_CONVERT, P_ENC_TAIL, P_COUNT };
+               P_NMS, P_CONVERT, P_ENC_TAIL, P_ENC_TAIL_G, P_COUNT };
 struct ProfScope {
     ProfScope(cudaStream_t s, ProfCat cat, double flops = 0.0, double bytes = 0.0);
     ~ProfScope();

@@ -266,14 +266,10 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
         for (int64_t st = st_begin; st < n_super; st += st_step) {
             const bool has_next = st + st_step < n_super;
             const int m_next = (int)(((st + st_step) * CG + rank) * 128);
-            if (has_next) {  // next tile's rows -> L2 a whole tile ahead of their loads (the tables compete with 7 GB of streams)
+            if (has_next) {
+                // (an L2 prefetch of the next tile's gathered rows was measured: +0.7 ms per launch — the TMA unit's rate of
+                // ~10 cycles per 128-byte row segment is what the gather costs, not L2 misses)
                 source_rows(m_next, idx);
-                if (P.gather > 1) {
-                    for (int kb = 0; kb < 4; ++kb) {
-                        tma_prefetch_l2_gather4(&tmRhi, kb * 64, idx[0], idx[1], idx[2], idx[3]);
-                        if (P.has_lo_in) tma_prefetch_l2_gather4(&tmRlo, kb * 64, idx[0], idx[1], idx[2], idx[3]);
-                    }
-                }
                 if (lane == 0)
                     for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmAtt, kb * 64, m_next);
             }
@@ -769,14 +765,7 @@ int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
     P.nchunk = a.ffn / 128;
     P.has_lo_in = a.res_lo != nullptr;
     P.has_lo_out = a.out_lo != nullptr;
-    {
-        static int pf = -1;  // CONE_TAIL_GATHER_PF=1: L2 prefetch of the gathered rows one tile ahead
-        if (pf < 0) {
-            const char* e = getenv("CONE_TAIL_GATHER_PF");
-            pf = (e && e[0] == '1') ? 1 : 0;
-        }
-        P.gather = gather ? 1 + pf : 0;
-    }
+    P.gather = gather ? 1 : 0;
     P.g_S = a.g_S; P.g_Lv = a.g_Lv; P.g_nvid = a.g_nvid; P.g_vid_base = a.g_vid_base; P.g_txt_base = a.g_txt_base;
     const int num_sms = tc_num_sms(t);
     const int64_t n_super = cdiv64(a.M, 128 * cg);
@@ -784,7 +773,7 @@ int enc_tail_run(TcWeights* t, const EncTailArgs& a, cudaStream_t s) {
     if (clusters > n_super) clusters = n_super;
     const unsigned grid = (unsigned)(clusters * cg);
     const double m = (double)a.M;
-    ProfScope ps(s, P_ENC_TAIL, 2.0 * m * ((double)a.d * a.d + 2.0 * a.d * a.ffn),
+    ProfScope ps(s, gather ? P_ENC_TAIL_G : P_ENC_TAIL, 2.0 * m * ((double)a.d * a.d + 2.0 * a.d * a.ffn),
                  2.0 * m * a.d * (2.0 + (a.res_lo ? 1.0 : 0.0) + 1.0 + (a.out_lo ? 1.0 : 0.0)) + (a.C32 ? 4.0 * m * a.d : 0.0));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

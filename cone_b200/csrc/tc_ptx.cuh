@@ -267,12 +267,6 @@ __device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, u
             : "memory");
     }
 }
-__device__ __forceinline__ void tma_prefetch_l2_gather4(const CUtensorMap* map, int c0, int r0, int r1, int r2, int r3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile::gather4 [%0, {%1, %2, %3, %4, %5}];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
                  "r"(c1)
