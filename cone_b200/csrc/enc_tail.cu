@@ -25,6 +25,12 @@
 //   epi-f   out = LN2(Y) -> fp16 hi (+ fp16 lo = out - hi: the residual stream crosses HBM as hi + lo, the operands of
 //           the next GEMMs read hi only) staged in the X / H regions -> TMA stores
 // The MMA warp issues GEMM0 of the NEXT tile right after the last GEMM2, so it overlaps the final epilogue.
+//
+// Gather mode (encoder layer 0, EtParams::gather): the residual rows are the window slices of the per-frame / per-token
+// projections (cone/ego4d_mad_dataloader.py:144-159, start_end_collate).  Producer warp A derives the source row of every
+// tile row from the window descriptors and fetches each [128 x 64] residual panel with 32 TMA gather4 instructions (four
+// arbitrary rows each, one-row boxes, 128-byte swizzle): the panel lands exactly as a tiled box would, nothing else
+// changes, and no gathered copy of the window inputs is ever written to HBM.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
