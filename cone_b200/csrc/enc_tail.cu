@@ -13,7 +13,7 @@
 // would exceed what L2 delivers.
 //
 // Data flow of one tile (TMEM: Y = columns [0,256), Hreg = columns [256,512)):
-//   GEMM0   Hreg  = att . Wo^T   (K = 256)  + res_hi . I + res_lo . I     -- the residual rows ride the same TMA ring as
+//   GEMM0   Hreg  = res_hi . I + res_lo . I + att . Wo^T   (K = 256)     -- the residual rows ride the same TMA ring as
 //           the operands and are added by N = 64 MMAs against a 64 x 64 identity tile (exact: products with 1.0, fp32
 //           accumulation), so the epilogue never touches global memory for them
 //   epi-0   x = LN1(Hreg + bo): fp16 copy -> X tile in shared memory (A operand of GEMM1, UMMA K-major 128B-swizzle
@@ -233,6 +233,11 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
             }
         };
         auto emit_gemm0 = [&](int m0, const int* idx) {
+            // the residual panels go FIRST: they are the slow loads (128 row segments each), and the first ring slots of a
+            // tile are filled while the previous tile's last GEMM1 chunks are still being multiplied
+            for (int kb = 0; kb < 4; ++kb) emit_rows(&tmRhi, kb, idx);
+            if (P.has_lo_in)
+                for (int kb = 0; kb < 4; ++kb) emit_rows(&tmRlo, kb, idx);
             for (int kb = 0; kb < 4; ++kb) {
                 emit(&tmAtt, kb * 64, m0);
                 if (CG == 1) {
@@ -242,9 +247,6 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                     emit(&tmWo, kb * 64, 128 * (int)rank);
                 }
             }
-            for (int kb = 0; kb < 4; ++kb) emit_rows(&tmRhi, kb, idx);
-            if (P.has_lo_in)
-                for (int kb = 0; kb < 4; ++kb) emit_rows(&tmRlo, kb, idx);
         };
         auto emit_g1 = [&](int c) {
             if (CG == 1) {
@@ -308,7 +310,10 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 }
                 advance(r);
             };
-            auto emit_gemm0 = [&](int m0) {
+            auto emit_gemm0 = [&](int m0) {  // (same item order as the gather-mode producer: residual panels first)
+                for (int kb = 0; kb < 4; ++kb) emit(0, &tmRhi, kb * 64, m0, SLOT_BYTES);
+                if (P.has_lo_in)
+                    for (int kb = 0; kb < 4; ++kb) emit(0, &tmRlo, kb * 64, m0, SLOT_BYTES);
                 for (int kb = 0; kb < 4; ++kb) {
                     emit(0, &tmAtt, kb * 64, m0, SLOT_BYTES);
                     if (CG == 1) {
@@ -318,9 +323,6 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                         emit(0, &tmWo, kb * 64, 128 * (int)rank, SLOT_BYTES);
                     }
                 }
-                for (int kb = 0; kb < 4; ++kb) emit(0, &tmRhi, kb * 64, m0, SLOT_BYTES);
-                if (P.has_lo_in)
-                    for (int kb = 0; kb < 4; ++kb) emit(0, &tmRlo, kb * 64, m0, SLOT_BYTES);
             };
             auto emit_g1 = [&](int c) {  // CG = 2: this CTA's 64 rows of the chunk, TWO k-blocks per 16 KB slot
                 if (CG == 1) {
@@ -417,23 +419,23 @@ enc_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant
                 __syncwarp();
             };
             auto gemm0 = [&]() {
-                for (int kb = 0; kb < 4; ++kb) {
+                for (int j = 0; j < nres; ++j) {  // res_hi (+ res_lo): 64 columns at a time against the identity tile; they
+                    const int ia = take();        // open the accumulation (the first product of each block overwrites)
+                    mma4(tmemH + 64 * (j & 3), ring_addr + ia * SLOT16, i_addr, id64, j >= 4);
+                    commit(&empty[ia]);
+                }
+                for (int kb = 0; kb < 4; ++kb) {  // + att . Wo^T
                     const int ia = take(), ib0 = take(), ib1 = (CG == 1) ? take() : 0;
                     const uint32_t a = ring_addr + ia * SLOT16, b0 = ring_addr + ib0 * SLOT16, b1 = ring_addr + ib1 * SLOT16;
                     if (CG == 1) {
-                        mma4(tmemH, a, b0, id128, kb > 0);
-                        mma4(tmemH + 128, a, b1, id128, kb > 0);
+                        mma4(tmemH, a, b0, id128, true);
+                        mma4(tmemH + 128, a, b1, id128, true);
                     } else {
-                        mma4(tmemH, a, b0, id256, kb > 0);
+                        mma4(tmemH, a, b0, id256, true);
                     }
                     commit(&empty[ia]);
                     commit(&empty[ib0]);
                     if (CG == 1) commit(&empty[ib1]);
-                }
-                for (int j = 0; j < nres; ++j) {  // + res_hi (+ res_lo): 64 columns at a time against the identity tile
-                    const int ia = take();
-                    mma4(tmemH + 64 * (j & 3), ring_addr + ia * SLOT16, i_addr, id64, true);
-                    commit(&empty[ia]);
                 }
                 commit(g0full);
             };
