@@ -96,7 +96,7 @@ def test_mad768_full_step_properties_and_oracle_subsample():
     print(f"[tc-vs-fp32] mad768 640 queries: max |tc - fp32| over {n_all} spans / probabilities {worst:.3e}, "
           f"{n_over} above {TC_TOL}")
     # 288 000 values, 10x the sample of the oracle test: the 7-sigma extreme of a 1.3e-4 rms error sits AT the bound
-    # (8.2e-4, 8.9e-4 and 1.02e-3 on three builds that differ in rounding-irrelevant details).  The north_star gate
+    # (8.2e-4, 8.9e-4, 1.02e-3 and - final build - 7.99e-4 on four builds that differ in rounding-irrelevant details).  The north_star gate
     # (max <= 1e-3 against the ORACLE) is asserted in tests/test_gpu_tc.py; here: at most 2 values in 288 000 above it,
     # none above 1.2e-3.
     assert worst <= 1.2 * TC_TOL and n_over <= 2, (worst, n_over)
